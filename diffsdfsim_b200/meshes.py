@@ -1,0 +1,101 @@
+"""Surface meshes for the analytic primitives (construction-time, host side).
+
+Meshes are INPUTS to the stepping hot path: the contact
+search iterates the faces it is given.  These generators reproduce the
+*densities* the reference gets with ``custom_mesh=True`` so benchmark scenes
+have the same face counts (reference: sdf_physics/physics3d/bodies.py:799-854
+box, 914-949 cylinder, 973-1009 sphere = icosphere with 4 subdivisions), but
+are written independently (numpy, outward-wound, int32 faces).
+"""
+import math
+
+import numpy as np
+
+
+def _grid_quads(n0, n1, offset, flip):
+    """Two triangles per cell of an n0 x n1 vertex lattice (row-major), optionally flipped."""
+    i, j = np.meshgrid(np.arange(n0 - 1), np.arange(n1 - 1), indexing="ij")
+    a = (i * n1 + j).ravel()
+    b = ((i + 1) * n1 + j).ravel()
+    c = (i * n1 + j + 1).ravel()
+    d = ((i + 1) * n1 + j + 1).ravel()
+    tris = np.concatenate([np.stack([a, b, c], 1), np.stack([b, d, c], 1)], 0)
+    if flip:
+        tris = tris[:, ::-1]
+    return tris + offset
+
+
+def box_mesh(dims, max_tri_length=0.1):
+    """Axis-aligned box centred at 0; six lattice patches, edge length <= max_tri_length.
+
+    20x1x20 @ 0.1 -> 89 646 verts / 176 000 faces; 1x1x1 @ 0.1 -> 726 / 1200.
+    """
+    dims = np.asarray(dims, dtype=np.float64)
+    half = dims / 2
+    n = np.ceil(dims / max_tri_length - 1e-9).astype(int) + 1
+    ax = []
+    for k in range(3):
+        t = np.linspace(-half[k], half[k], n[k])
+        t[0], t[-1] = -half[k], half[k]
+        ax.append(t)
+    verts, faces, off = [], [], 0
+    # (u axis, v axis, fixed axis); outward normal of (u x v) is +fixed when (u,v,fixed) is cyclic
+    for u, v, w in ((0, 1, 2), (1, 2, 0), (2, 0, 1)):
+        U, V = np.meshgrid(ax[u], ax[v], indexing="ij")
+        for sign in (+1.0, -1.0):
+            P = np.zeros((U.size, 3))
+            P[:, u], P[:, v], P[:, w] = U.ravel(), V.ravel(), sign * half[w]
+            verts.append(P)
+            faces.append(_grid_quads(n[u], n[v], off, flip=(sign < 0)))
+            off += U.size
+    return np.concatenate(verts), np.concatenate(faces).astype(np.int32)
+
+
+def icosphere(radius=1.0, subdivisions=4):
+    """Unit icosahedron subdivided ``subdivisions`` times, projected to the sphere.
+
+    subdivisions=4 -> 2562 verts / 5120 faces (the reference's sphere density).
+    """
+    t = (1.0 + math.sqrt(5.0)) / 2.0
+    v = [(-1, t, 0), (1, t, 0), (-1, -t, 0), (1, -t, 0), (0, -1, t), (0, 1, t),
+         (0, -1, -t), (0, 1, -t), (t, 0, -1), (t, 0, 1), (-t, 0, -1), (-t, 0, 1)]
+    f = [(0, 11, 5), (0, 5, 1), (0, 1, 7), (0, 7, 10), (0, 10, 11), (1, 5, 9), (5, 11, 4), (11, 10, 2),
+         (10, 7, 6), (7, 1, 8), (3, 9, 4), (3, 4, 2), (3, 2, 6), (3, 6, 8), (3, 8, 9), (4, 9, 5),
+         (2, 4, 11), (6, 2, 10), (8, 6, 7), (9, 8, 1)]
+    verts = [np.asarray(p, dtype=np.float64) / math.sqrt(1 + t * t) for p in v]
+    faces = [tuple(x) for x in f]
+    for _ in range(subdivisions):
+        cache, nf = {}, []
+
+        def mid(a, b):
+            key = (a, b) if a < b else (b, a)
+            if key not in cache:
+                m = verts[a] + verts[b]
+                verts.append(m / np.linalg.norm(m))
+                cache[key] = len(verts) - 1
+            return cache[key]
+
+        for a, b, c in faces:
+            ab, bc, ca = mid(a, b), mid(b, c), mid(c, a)
+            nf += [(a, ab, ca), (b, bc, ab), (c, ca, bc), (ab, bc, ca)]
+        faces = nf
+    return np.asarray(verts) * radius, np.asarray(faces, dtype=np.int32)
+
+
+def cylinder_mesh(rad, height, numsegs=32, max_tri_length=0.1):
+    """Cylinder along local z: lattice side wall + fan caps (centre vertices at +-h/2)."""
+    nh = int(math.ceil(height / max_tri_length - 1e-9)) + 1
+    th = np.arange(numsegs) * (2 * math.pi / numsegs)
+    zs = np.linspace(-height / 2, height / 2, nh)
+    zs[0], zs[-1] = -height / 2, height / 2
+    TH, Z = np.meshgrid(th, zs, indexing="ij")
+    side = np.stack([rad * np.cos(TH).ravel(), rad * np.sin(TH).ravel(), Z.ravel()], 1)
+    verts = np.concatenate([side, [[0, 0, height / 2], [0, 0, -height / 2]]])
+    top_c, bot_c = side.shape[0], side.shape[0] + 1
+    idx = np.arange(numsegs * nh).reshape(numsegs, nh)
+    idx = np.concatenate([idx, idx[:1]], 0)
+    a, b, c, d = idx[:-1, :-1].ravel(), idx[1:, :-1].ravel(), idx[:-1, 1:].ravel(), idx[1:, 1:].ravel()
+    faces = [np.stack([a, b, d], 1), np.stack([a, d, c], 1),
+             np.stack([np.full(numsegs, top_c), idx[:-1, -1], idx[1:, -1]], 1),
+             np.stack([np.full(numsegs, bot_c), idx[1:, 0], idx[:-1, 0]], 1)]
+    return verts, np.concatenate(faces).astype(np.int32)

@@ -1,0 +1,89 @@
+"""Scene specifications (pure data) for the BASELINE.json configurations.
+
+A spec is a plain dict so the same scene can be instantiated by the product
+(``build_world``), by the CPU oracle (oracle/scenes.py) and -- in the build
+container only -- by the unmodified reference (tests/golden/make_golden.py).
+
+Scene shapes follow the reference experiments:
+* box_on_plane      experiments/system_identification/optim_sysid.py:105-131  (config 2 / 5)
+* bouncing_sphere   experiments/trajectory_fitting/optim_sphere.py:78-111      (config 1)
+* grid_on_pole      demos/demo_meshsdf.py:121-142                              (config 4)
+"""
+import math
+
+import numpy as np
+
+EPS = 1e-3
+
+
+def body(kind, pos, *, dims=None, rad=None, height=None, grid=None, scale=None, vel=(0, 0, 0, 0, 0, 0),
+         mass=1.0, restitution=0.5, fric_coeff=0.9, pinned=False, gravity=False, ext_force=None,
+         ext_until=None, max_tri_length=0.1, mesh=None):
+    return dict(kind=kind, pos=list(pos), dims=dims, rad=rad, height=height, grid=grid, scale=scale,
+                vel=list(vel), mass=mass, restitution=restitution, fric_coeff=fric_coeff, pinned=pinned,
+                gravity=gravity, ext_force=ext_force, ext_until=ext_until, max_tri_length=max_tri_length,
+                mesh=mesh)
+
+
+def scene(bodies, *, no_contact=(), axis_locks=(), dt=1.0 / 30, eps=EPS, tol=1e-8, fric_dirs=8,
+          strict_no_penetration=True, time_of_contact_diff=True, steps=10):
+    return dict(bodies=bodies, no_contact=list(no_contact), axis_locks=list(axis_locks), dt=dt, eps=eps,
+                tol=tol, fric_dirs=fric_dirs, strict_no_penetration=strict_no_penetration,
+                time_of_contact_diff=time_of_contact_diff, steps=steps)
+
+
+def box_on_plane(floor=(20.0, 1.0, 20.0), box=(1.0, 1.0, 1.0), mass=1.0, fric=0.2, push=(3.0, 2.0),
+                 restitution=0.5, tilt=0.0, gap=2 * EPS, steps=30, toc=True, floor_tri=0.1):
+    """Box resting ``gap`` above a pinned floor slab, pushed along x,z (system-identification shape)."""
+    h = box[1] / 2 + gap
+    pos = [0.0, h, 0.0]
+    if tilt:
+        # rotate about z by ``tilt``: q = (cos t/2, 0, 0, sin t/2); lift so the lowest corner keeps the gap
+        c, s = math.cos(tilt / 2), math.sin(tilt / 2)
+        lift = (abs(math.sin(tilt)) * box[0] + abs(math.cos(tilt)) * box[1]) / 2 + gap
+        pos = [c, 0.0, 0.0, s, 0.0, lift, 0.0]
+    return scene([
+        body('box', [0, -floor[1] / 2, 0], dims=list(floor), pinned=True, fric_coeff=fric,
+             restitution=restitution, max_tri_length=floor_tri),
+        body('box', pos, dims=list(box), mass=mass, fric_coeff=fric, restitution=restitution, gravity=True,
+             ext_force=[0, 0, 0, push[0], 0, push[1]]),
+    ], strict_no_penetration=False, time_of_contact_diff=toc, steps=steps)
+
+
+def bouncing_sphere(rad=0.5, height=1.0, vel=(0, 0, 0, 2.0, 0, 0), floor=(20.0, 1.0, 20.0), steps=20,
+                    toc=True, floor_tri=0.1, gravity=True, subdivisions=4):
+    return scene([
+        body('box', [0, -floor[1] / 2, 0], dims=list(floor), pinned=True, fric_coeff=0.25, restitution=0.5,
+             max_tri_length=floor_tri),
+        body('sphere', [0, height, 0], rad=rad, vel=list(vel), fric_coeff=0.25, restitution=0.5,
+             gravity=gravity, mesh=dict(subdivisions=subdivisions)),
+    ], time_of_contact_diff=toc, steps=steps)
+
+
+def baked_grid(res=32, kind='ellipsoid', seed=0):
+    """A res^3 float64 SDF grid on [-1,1]^3 standing in for a decoded IGR latent (no checkpoints offline)."""
+    t = np.linspace(-1.0, 1.0, res)
+    X, Y, Z = np.meshgrid(t, t, t, indexing='ij')
+    if kind == 'sphere':
+        return np.sqrt(X * X + Y * Y + Z * Z) - 0.6
+    rng = np.random.RandomState(seed)
+    a = 0.45 + 0.25 * rng.rand(3)
+    # first-order ellipsoid distance: smooth, sign-correct, |grad| ~ 1 near the surface
+    k0 = np.sqrt((X / a[0]) ** 2 + (Y / a[1]) ** 2 + (Z / a[2]) ** 2)
+    k1 = np.sqrt((X / a[0] ** 2) ** 2 + (Y / a[1] ** 2) ** 2 + (Z / a[2] ** 2) ** 2)
+    return np.where(k1 > 1e-9, k0 * (k0 - 1.0) / np.maximum(k1, 1e-9), -a.min())
+
+
+def grid_on_pole(res=32, floor=(10.0, 1.0, 10.0), drop=2.62, steps=12, floor_tri=0.25, with_floor=True):
+    """Grid-SDF body falling on a pinned cylinder pole ('cow on pole' shape, demos/demo_meshsdf.py:121-142)."""
+    bodies = []
+    if with_floor:
+        bodies.append(body('box', [0, -floor[1] / 2, 0], dims=list(floor), pinned=True, fric_coeff=0.15,
+                           restitution=0.0, max_tri_length=floor_tri))
+    q = [math.cos(math.pi / 4), math.sin(math.pi / 4), 0.0, 0.0]   # euler (pi/2,0,0): local z -> world -y.. up/down
+    bodies.append(body('cylinder', q + [0.35, 1.0, 0.0], rad=0.2, height=2.0, pinned=True, fric_coeff=0.15,
+                       restitution=0.0))
+    bodies.append(body('grid', [0.0, drop, 0.0], grid=dict(res=res, kind='sphere'), scale=1.0, fric_coeff=0.15,
+                       restitution=0.0, gravity=True, mesh=dict(subdivisions=3, radius=0.6)))
+    nc = [(0, 1)] if with_floor else []
+    return scene(bodies, no_contact=nc, steps=steps)

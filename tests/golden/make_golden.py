@@ -1,0 +1,236 @@
+"""Generate golden vectors by executing the UNMODIFIED reference (build container only).
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference has no tests and no golden vectors of its own, so
+the oracle is pinned against outputs of the reference itself.  The reference is
+imported from /root/reference with the third-party stand-ins in
+tests/golden/ref_shims on sys.path (recipe: SURVEY.md s8c); meshes / grids are
+injected through the reference's own ``custom_mesh`` hook so that reference,
+oracle and CUDA path all see identical geometry buffers.
+
+/root/reference does not exist on the GPU box: this script is never run there;
+its outputs are committed.
+"""
+import os
+import sys
+import warnings
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path[:0] = [os.path.join(HERE, 'ref_shims'), '/root/reference', ROOT]
+os.environ.setdefault('IGR_PATH', HERE)
+warnings.filterwarnings('ignore')
+
+import lcp_physics.physics  # noqa: E402  (must precede lcp_physics.lcp.lcp: circular import)
+import sdf_physics.physics3d.utils as u3  # noqa: E402
+
+u3.Defaults3D.DEVICE = torch.device('cpu')
+from sdf_physics.physics3d import bodies as rb, contacts as rc, forces as rf, constraints as rcon  # noqa: E402
+from sdf_physics.physics3d.world import World3D  # noqa: E402
+from lcp_physics.lcp.lcp import LCPFunction  # noqa: E402
+
+from diffsdfsim_b200 import scenes  # noqa: E402
+from oracle.scenes import mesh_for  # noqa: E402
+
+F64 = torch.float64
+
+
+def _inject(cls, verts, faces, inertia=None):
+    v = torch.as_tensor(verts, dtype=F64)
+    f = torch.as_tensor(np.asarray(faces)).long()
+
+    class Injected(cls):
+        def _custom_create_mesh(self, *a, **k):
+            return v, f
+
+        def _create_mesh(self, *a, **k):
+            return v, f
+
+    if inertia is not None:
+        Injected._get_ang_inertia = lambda self, mass: inertia(mass)
+    return Injected
+
+
+def build_reference(spec, params=None):
+    params = params or {}
+    bodies, joints = [], []
+    n = len(spec['bodies'])
+    for i, b in enumerate(spec['bodies']):
+        last = i == n - 1
+        mass = params['mass'] if (last and 'mass' in params) else float(b['mass'])
+        fric = params['fric_coeff'] if 'fric_coeff' in params else float(b['fric_coeff'])
+        verts, faces = mesh_for(b)
+        pos = params['pos'] if (last and 'pos' in params) else torch.tensor(b['pos'], dtype=F64)
+        vel = params['vel'] if (last and 'vel' in params) else torch.tensor(b['vel'], dtype=F64)
+        kw = dict(vel=vel, mass=mass, restitution=b['restitution'], fric_coeff=fric)
+        k = b['kind']
+        if k == 'box':
+            ob = _inject(rb.SDFBox, verts, faces)(pos, b['dims'], custom_mesh=True, custom_inertia=True, **kw)
+        elif k == 'sphere':
+            ob = _inject(rb.SDFSphere, verts, faces)(pos, b['rad'], custom_mesh=True, custom_inertia=True, **kw)
+        elif k == 'cylinder':
+            ob = _inject(rb.SDFCylinder, verts, faces)(pos, b['rad'], b['height'], custom_mesh=True,
+                                                       custom_inertia=True, **kw)
+        elif k == 'grid':
+            g = b['grid']
+            grid = torch.tensor(scenes.baked_grid(g['res'], g['kind'], g.get('seed', 0)), dtype=F64)
+            r = b['mesh']['radius']
+            cls = _inject(rb.SDFGrid3D, verts, faces,
+                          inertia=lambda m, r=r: 2 / 5 * m * r ** 2 * torch.eye(3, dtype=F64))
+            ob = cls(pos, b['scale'], grid, **kw)
+        else:
+            raise ValueError(k)
+        if b['gravity']:
+            ob.add_force(rf.Gravity3D())
+        if b['ext_force'] is not None:
+            f = torch.tensor(b['ext_force'], dtype=F64)
+            if last and 'push' in params:
+                f = torch.cat([f[:3], params['push'][0:1], f[4:5], params['push'][1:2]])
+            until = b['ext_until']
+            ob.add_force(rf.ExternalForce3D(lambda t, f=f, until=until: f if (until is None or t < until) else f * 0,
+                                            multiplier=1.))
+        bodies.append(ob)
+        if b['pinned']:
+            joints.append(rcon.TotalConstraint3D(ob))
+    for i, j in spec['no_contact']:
+        bodies[i].add_no_contact(bodies[j])
+    axis_cls = {3: rcon.XConstraint, 4: rcon.YConstraint, 5: rcon.ZConstraint}
+    for i, a in spec['axis_locks']:
+        joints.append(axis_cls[a](bodies[i]))
+    world = World3D(bodies, joints, dt=spec['dt'], eps=spec['eps'], tol=spec['tol'], fric_dirs=spec['fric_dirs'],
+                    strict_no_penetration=spec['strict_no_penetration'],
+                    time_of_contact_diff=spec['time_of_contact_diff'])
+    return world
+
+
+def rollout_reference(spec, params=None, target=None, record_lcp=True):
+    """Step the reference, recording states, contact sets, solver attempts, one LCP instance, and the loss."""
+    world = build_reference(spec, params)
+    tries = [0]
+    solve = world.engine.solve_dynamics
+
+    def counted(w, dt):
+        tries[0] += 1
+        return solve(w, dt)
+
+    world.engine.solve_dynamics = counted
+
+    fw_log = []
+    fw = rc._frank_wolfe
+
+    def fw_logged(b1, b2, eps=None, tol=None):
+        abc, ids = fw(b1, b2, eps, tol)
+        fw_log.append((world.bodies.index(b1), world.bodies.index(b2), ids.clone()))
+        return abc, ids
+
+    rc._frank_wolfe = fw_logged
+
+    lcps = []
+
+    def lcp_factory(**kw):
+        fn = LCPFunction(**kw)
+
+        def call(*a):
+            z = fn(*a)
+            if record_lcp:
+                lcps.append([t.detach().clone() for t in a] + [z.detach().clone()])
+            return z
+        return call
+
+    world.engine.lcp_solver = lcp_factory
+
+    out = dict(p=[], v=[], tries=[], nc=[], con=[], fw=[], fw_off=[0], con_off=[0])
+    obj = world.bodies[-1]
+    loss = 0.
+    try:
+        for k in range(spec['steps']):
+            tries[0] = 0
+            del fw_log[:]
+            world.step(fixed_dt=True)
+            out['p'].append(torch.cat([b.p for b in world.bodies]).detach().numpy().copy())
+            out['v'].append(world.v.detach().numpy().copy())
+            out['tries'].append(tries[0])
+            rows = [torch.cat([c[0][0], c[0][1], c[0][2], c[0][3].reshape(1),
+                               c[0][0].new_tensor([c[1], c[2]])]).detach().numpy() for c in world.contacts]
+            out['con'] += rows
+            out['con_off'].append(out['con_off'][-1] + len(rows))
+            # pre-filter FW index sets of the LAST find_contacts of this step (the accepted one)
+            n_pairs_calls = [(a, b, ids) for a, b, ids in fw_log]
+            # keep only calls after the last solve: the log is cleared per step, accepted attempt = trailing calls
+            out['fw'].append(n_pairs_calls)
+            tgt = target if target is not None else obj.pos.new_zeros(3)
+            loss = loss + ((tgt - obj.pos) ** 2).sum()
+    finally:
+        rc._frank_wolfe = fw
+    return world, out, loss, lcps
+
+
+def pack(out):
+    d = dict(p=np.stack(out['p']), v=np.stack(out['v']), tries=np.asarray(out['tries']),
+             con=np.stack(out['con']) if out['con'] else np.zeros((0, 12)), con_off=np.asarray(out['con_off']))
+    # FW pre-filter sets: flatten (step, call#, b1, b2, face id)
+    rows = []
+    for s, calls in enumerate(out['fw']):
+        for c, (a, b, ids) in enumerate(calls):
+            for i in ids.tolist():
+                rows.append((s, c, a, b, i))
+    d['fw'] = np.asarray(rows, dtype=np.int64).reshape(-1, 5)
+    d['fw_calls'] = np.asarray([len(c) for c in out['fw']])
+    return d
+
+
+def golden_scene(name, spec, leaves):
+    params = {k: torch.tensor(v, dtype=F64, requires_grad=True) for k, v in leaves.items()}
+    world, out, loss, lcps = rollout_reference(spec, params)
+    d = pack(out)
+    d['loss'] = float(loss)
+    loss.backward()
+    for k, t in params.items():
+        d['grad_' + k] = t.grad.numpy().copy()
+        d['leaf_' + k] = t.detach().numpy().copy()
+    # the largest recorded LCP instance, for the operator-level golden
+    if lcps:
+        big = max(lcps, key=lambda a: a[2].shape[1])
+        for nm, t in zip(['Q', 'p', 'G', 'h', 'A', 'b', 'F', 'z'], big):
+            d['lcp_' + nm] = t.numpy()
+    np.savez_compressed(os.path.join(HERE, name + '.npz'), **d)
+    print(name, 'steps', len(d['tries']), 'tries', d['tries'].tolist(), 'contacts/step',
+          np.diff(d['con_off']).tolist(), 'loss', d['loss'],
+          {k: d['grad_' + k].tolist() for k in leaves})
+
+
+from specs import SCENES  # noqa: E402
+
+
+def golden_sdf():
+    """Operator-level vectors for SDF3D.query_sdfs on each body kind (bodies.py:721-760)."""
+    g = torch.Generator().manual_seed(0)
+    d = {}
+    spec = scenes.grid_on_pole(with_floor=True)
+    world = build_reference(spec)
+    box = build_reference(scenes.box_on_plane(floor=(4.0, 1.0, 4.0))).bodies[1]
+    sph = build_reference(scenes.bouncing_sphere(floor=(4.0, 1.0, 4.0), floor_tri=0.5)).bodies[1]
+    for nm, b in (('box', box), ('sphere', sph), ('cylinder', world.bodies[1]), ('grid', world.bodies[2])):
+        s = float(b.scale)
+        pts = (torch.rand(4096, 3, generator=g, dtype=F64) * 2 - 1) * s * 1.1
+        # exact-zero coordinates and surface points exercise the sign(0)/tie conventions
+        pts[:64] = torch.round(pts[:64] / s * 4) / 4 * s
+        sd, gr = b.query_sdfs(pts)
+        d[nm + '_pts'], d[nm + '_sdf'], d[nm + '_dir'] = pts.numpy(), sd.numpy(), gr.numpy()
+    np.savez_compressed(os.path.join(HERE, 'sdf_query.npz'), **d)
+    print('sdf_query', {k: v.shape for k, v in d.items()})
+
+
+if __name__ == '__main__':
+    torch.manual_seed(0)
+    names = sys.argv[1:] or (list(SCENES) + ['sdf_query'])
+    for n in names:
+        if n == 'sdf_query':
+            golden_sdf()
+        else:
+            mk, leaves = SCENES[n]
+            golden_scene(n, mk(), leaves)
