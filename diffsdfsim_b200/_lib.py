@@ -12,6 +12,7 @@ c_p = ctypes.c_void_p
 c_i = ctypes.c_int
 c_d = ctypes.c_double
 c_sz = ctypes.c_size_t
+c_ll = ctypes.c_longlong
 
 # name -> (restype, argtypes).  Must list every symbol include/dsdf_b200.h declares (tests/test_cabi.py checks).
 SIGNATURES = {
@@ -20,6 +21,10 @@ SIGNATURES = {
     'dsdf_lcp_smem_bytes': (c_sz, [c_i, c_i, c_i]),
     'dsdf_lcp_forward': (c_i, [c_p] * 8 + [c_i] * 4 + [c_d, c_i, c_i, c_i] + [c_p] * 8),
     'dsdf_lcp_backward': (c_i, [c_p] * 10 + [c_i] * 4 + [c_p] * 10),
+    'dsdf_sdf_query': (c_i, [c_i, c_p, c_p, c_i, c_ll, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
+    'dsdf_sdf_query_backward': (c_i, [c_i, c_p, c_p, c_i, c_ll, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
+    'dsdf_integrate': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p]),
+    'dsdf_integrate_backward': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
 }
 
 

@@ -1,0 +1,151 @@
+// SDF3D.query_sdfs on the device (sdf_physics/physics3d/bodies.py:721-760) for the four body kinds:
+//   box / sphere / cylinder analytic value + "failsafe" direction   (bodies.py:38-125)
+//   grid: trilinear value, on-the-fly central-difference direction, DiffGridSDF derivative (bodies.py:203-257)
+// Scalar-generic (double or Dual) -- see dsdf_math.cuh.
+#pragma once
+#include "dsdf_math.cuh"
+#include "../../include/dsdf_b200.h"
+
+namespace dsdf {
+
+// What a kernel needs to evaluate one body's SDF in that body's frame.
+struct SdfShape {
+    int kind;            // DSDF_SDF_*
+    double a, b, c;      // normalised parameters: box dims/scale; sphere r/scale; cylinder r/scale, h/scale
+    double scale;
+    const double* grid;  // (R,R,R) row-major, this world's grid (kind == GRID)
+    int res;
+};
+
+template <class S> struct SdfOut { S d; V3<S> n; };
+
+// ---- box (bodies.py:38-72), point u already divided by scale
+template <class S> __device__ __forceinline__ void box_eval(V3<S> u, double dx, double dy, double dz, bool want_n,
+                                                            S& value, V3<S>& dir) {
+    S qx = dabs(u.x) - cst(u.x, dx * 0.5), qy = dabs(u.y) - cst(u.x, dy * 0.5), qz = dabs(u.z) - cst(u.x, dz * 0.5);
+    // q.max(dim=1): first maximal index carries the gradient
+    S top = qx;
+    if (val(qy) > val(top)) top = qy;
+    if (val(qz) > val(top)) top = qz;
+    value = norm3(v3<S>(clamp_min0(qx), clamp_min0(qy), clamp_min0(qz))) + clamp_max0(top);
+    if (!want_n) return;
+    const double sx = val(u.x) < 0.0 ? -1.0 : 1.0, sy = val(u.y) < 0.0 ? -1.0 : 1.0, sz = val(u.z) < 0.0 ? -1.0 : 1.0;
+    const double tv = val(top);
+    const double inside = tv <= 0.0 ? 1.0 : 0.0;
+    V3<S> m = normalize3(v3<S>(maximum0(qx), maximum0(qy), maximum0(qz)));
+    V3<S> g = v3<S>((m.x + cst(m.x, inside * (val(qx) == tv ? 1.0 : 0.0))) * cst(m.x, sx),
+                    (m.y + cst(m.x, inside * (val(qy) == tv ? 1.0 : 0.0))) * cst(m.x, sy),
+                    (m.z + cst(m.x, inside * (val(qz) == tv ? 1.0 : 0.0))) * cst(m.x, sz));
+    dir = normalize3(g);
+}
+
+// ---- sphere (bodies.py:75-84)
+template <class S> __device__ __forceinline__ void sphere_eval(V3<S> u, double r, bool want_n, S& value, V3<S>& dir) {
+    value = norm3(u) - cst(u.x, r);
+    if (want_n) dir = normalize3(u);
+}
+
+// ---- cylinder along local z (bodies.py:87-125)
+template <class S> __device__ __forceinline__ void cylinder_eval(V3<S> u, double r, double h, bool want_n, S& value,
+                                                                 V3<S>& dir) {
+    S rho = norm2(u.x, u.y);
+    S q0 = dabs(rho) - cst(rho, r), q1 = dabs(u.z) - cst(rho, h * 0.5);
+    S top = q0;
+    if (val(q1) > val(top)) top = q1;
+    value = norm2(clamp_min0(q0), clamp_min0(q1)) + clamp_max0(top);
+    if (!want_n) return;
+    const double sz = val(u.z) < 0.0 ? -1.0 : 1.0;
+    const double tv = val(top);
+    const double inside = tv <= 0.0 ? 1.0 : 0.0;
+    S m0 = clamp_min0(q0), m1 = clamp_min0(q1);
+    normalize2(m0, m1);
+    S g0 = m0 + cst(m0, inside * (val(q0) == tv ? 1.0 : 0.0));
+    S g1 = m1 + cst(m0, inside * (val(q1) == tv ? 1.0 : 0.0));
+    S ex = u.x, ey = u.y;
+    normalize2(ex, ey);
+    dir = normalize3(v3<S>(g0 * ex, g0 * ey, g1 * cst(m0, sz)));
+}
+
+// ---- grid (bodies.py:203-257 + ev_sdf_utils.grid_interp semantics)
+// value: trilinear at idx=(u+1)/2*(R-1); direction: normalised trilinear interpolation of the central-difference
+// field (zero on the two boundary planes of each axis).  No derivative flows through the interpolation indices;
+// d value / d u := direction (DiffGridSDF.backward).
+__device__ __forceinline__ double grid_cd(const double* g, int R, int i, int j, int k, int axis) {
+    const int c = axis == 0 ? i : (axis == 1 ? j : k);
+    if (c <= 0 || c >= R - 1) return 0.0;
+    const size_t st = axis == 0 ? (size_t)R * R : (axis == 1 ? (size_t)R : 1);
+    const size_t o = ((size_t)i * R + j) * R + k;
+    return (g[o + st] - g[o - st]) / 2.0;
+}
+__device__ __forceinline__ bool grid_eval_raw(const double* g, int R, double ux, double uy, double uz, bool want_n,
+                                              double& value, double n[3]) {
+    const double ext = (double)(R - 1);
+    const double ix = (ux + 1.) * 0.5 * ext, iy = (uy + 1.) * 0.5 * ext, iz = (uz + 1.) * 0.5 * ext;
+    const bool ok = ix <= ext && ix >= 0.0 && iy <= ext && iy >= 0.0 && iz <= ext && iz >= 0.0;
+    value = 1.0;
+    n[0] = n[1] = n[2] = 0.0;
+    if (!ok) return false;
+    int bx = min(max((int)floor(ix), 0), R - 2), by = min(max((int)floor(iy), 0), R - 2),
+        bz = min(max((int)floor(iz), 0), R - 2);
+    const double tx = ix - bx, ty = iy - by, tz = iz - bz;
+    double acc = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int dx = 0; dx < 2; ++dx) {
+        const double wx = dx ? tx : 1 - tx;
+#pragma unroll
+        for (int dy = 0; dy < 2; ++dy) {
+            const double wy = dy ? ty : 1 - ty;
+#pragma unroll
+            for (int dz = 0; dz < 2; ++dz) {
+                const double wz = dz ? tz : 1 - tz;
+                const double w = wx * wy * wz;
+                const int i = bx + dx, j = by + dy, k = bz + dz;
+                acc = acc + g[((size_t)i * R + j) * R + k] * w;
+                if (want_n) {
+                    a0 = a0 + grid_cd(g, R, i, j, k, 0) * w;
+                    a1 = a1 + grid_cd(g, R, i, j, k, 1) * w;
+                    a2 = a2 + grid_cd(g, R, i, j, k, 2) * w;
+                }
+            }
+        }
+    }
+    value = acc;
+    if (want_n) {
+        V3<double> d = normalize3(v3<double>(a0, a1, a2));
+        n[0] = d.x; n[1] = d.y; n[2] = d.z;
+    }
+    return true;
+}
+
+// ---- SDF3D.query_sdfs: p in the body frame -> sdf (scaled back) and unit direction. Outside |p|<=scale: (scale, 0).
+template <class S>
+__device__ __forceinline__ SdfOut<S> sdf_query(const SdfShape& sh, V3<S> p, bool want_n = true) {
+    SdfOut<S> o;
+    const double sc = sh.scale;
+    S zero = cst(p.x, 0.0);
+    o.n = v3<S>(zero, zero, zero);
+    const bool inside = fabs(val(p.x)) <= sc && fabs(val(p.y)) <= sc && fabs(val(p.z)) <= sc;
+    if (!inside) { o.d = cst(p.x, 1.0 * sc); return o; }
+    S scs = cst(p.x, sc);
+    V3<S> u = v3<S>(p.x / scs, p.y / scs, p.z / scs);
+    S value;
+    V3<S> dir = o.n;
+    if (sh.kind == DSDF_SDF_BOX) box_eval<S>(u, sh.a, sh.b, sh.c, want_n, value, dir);
+    else if (sh.kind == DSDF_SDF_SPHERE) sphere_eval<S>(u, sh.a, want_n, value, dir);
+    else if (sh.kind == DSDF_SDF_CYLINDER) cylinder_eval<S>(u, sh.a, sh.b, want_n, value, dir);
+    else {
+        double v, n[3];
+        // the custom backward (Dual pass) always needs the direction
+        grid_eval_raw(sh.grid, sh.res, val(u.x), val(u.y), val(u.z), want_n || needs_tan(p.x), v, n);
+        // tangent of the value := direction . du ; direction itself carries no tangent
+        double dv = n[0] * tan_(u.x) + n[1] * tan_(u.y) + n[2] * tan_(u.z);
+        value = cst(p.x, v);
+        set_tangent(value, dv);
+        dir = v3<S>(cst(p.x, n[0]), cst(p.x, n[1]), cst(p.x, n[2]));
+    }
+    o.d = value * scs;
+    if (want_n) o.n = normalize3(dir);
+    return o;
+}
+
+}  // namespace dsdf

@@ -1,0 +1,95 @@
+"""torch.autograd wrappers over the C-ABI kernels (thin: pointer marshalling only, no arithmetic)."""
+import torch
+
+from . import _lib
+
+F64 = torch.float64
+KIND = {'box': 0, 'sphere': 1, 'cylinder': 2, 'grid': 3}
+
+
+def _c(t):
+    return t.contiguous() if t is not None else None
+
+
+class _SdfQuery(torch.autograd.Function):
+    """SDF3D.query_sdfs (bodies.py:721-760): pts (W,N,3) -> sdf (W,N), dir (W,N,3)."""
+
+    @staticmethod
+    def forward(ctx, pts, shape, grid, kind, want_dir):
+        L = _lib.lib()
+        _lib.require_cuda(pts, shape)
+        pts, shape = _c(pts), _c(shape)
+        W, N = pts.shape[0], pts.shape[1]
+        res, stride = 0, 0
+        if kind == 3:
+            grid = _c(grid)
+            res = grid.shape[-1]
+            assert grid.dim() == 3 or grid.shape[0] == W, 'grid must be (R,R,R) shared or (W,R,R,R) per world'
+            stride = res ** 3 if grid.dim() == 4 else 0
+        sdf = torch.empty(W, N, dtype=F64, device=pts.device)
+        d = torch.empty(W, N, 3, dtype=F64, device=pts.device) if want_dir else None
+        rc = L.dsdf_sdf_query(kind, _lib.ptr(shape), _lib.ptr(grid) if kind == 3 else None, res, stride,
+                              _lib.ptr(pts), W, N, int(want_dir), _lib.ptr(sdf), _lib.ptr(d), _lib.stream())
+        _lib.check(rc, 'dsdf_sdf_query')
+        ctx.save_for_backward(pts, shape, grid if kind == 3 else pts.new_empty(0))
+        ctx.meta = (kind, res, stride, want_dir)
+        if want_dir:
+            return sdf, d
+        ctx.mark_non_differentiable()
+        return sdf, pts.new_empty(0)
+
+    @staticmethod
+    def backward(ctx, gsdf, gdir):
+        L = _lib.lib()
+        pts, shape, grid = ctx.saved_tensors
+        kind, res, stride, want_dir = ctx.meta
+        W, N = pts.shape[0], pts.shape[1]
+        gpts = torch.empty_like(pts)
+        gdir = _c(gdir) if (want_dir and gdir is not None and gdir.numel()) else None
+        rc = L.dsdf_sdf_query_backward(kind, _lib.ptr(shape), _lib.ptr(grid) if kind == 3 else None, res, stride,
+                                       _lib.ptr(pts), W, N, _lib.ptr(_c(gsdf)), _lib.ptr(gdir), _lib.ptr(gpts),
+                                       _lib.stream())
+        _lib.check(rc, 'dsdf_sdf_query_backward')
+        return gpts, None, None, None, None
+
+
+def sdf_query(kind, shape, pts, grid=None, want_dir=True):
+    """kind: 'box'|'sphere'|'cylinder'|'grid' (or int); shape (W,4); pts (W,N,3); grid (W,R,R,R) or (R,R,R)."""
+    k = KIND[kind] if isinstance(kind, str) else int(kind)
+    sdf, d = _SdfQuery.apply(pts, shape, grid, k, want_dir)
+    return (sdf, d) if want_dir else sdf
+
+
+class _Integrate(torch.autograd.Function):
+    """Body3D.move (bodies.py:488-496) for all worlds/bodies: p (W,nb,7), v (W,nb,6), dt (W)."""
+
+    @staticmethod
+    def forward(ctx, p, v, dt, active):
+        L = _lib.lib()
+        _lib.require_cuda(p, v, dt)
+        p, v, dt = _c(p), _c(v), _c(dt)
+        W, nb = p.shape[0], p.shape[1]
+        out = torch.empty_like(p)
+        rc = L.dsdf_integrate(_lib.ptr(p), _lib.ptr(v), _lib.ptr(dt), _lib.ptr(active), W, nb, _lib.ptr(out),
+                              _lib.stream())
+        _lib.check(rc, 'dsdf_integrate')
+        ctx.save_for_backward(p, v, dt, active if active is not None else p.new_empty(0))
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        L = _lib.lib()
+        p, v, dt, active = ctx.saved_tensors
+        active = active if active.numel() else None
+        W, nb = p.shape[0], p.shape[1]
+        gp, gv = torch.empty_like(p), torch.empty_like(v)
+        gdt = torch.empty(W, nb, dtype=F64, device=p.device)
+        rc = L.dsdf_integrate_backward(_lib.ptr(p), _lib.ptr(v), _lib.ptr(dt), _lib.ptr(active), W, nb,
+                                       _lib.ptr(_c(g)), _lib.ptr(gp), _lib.ptr(gv), _lib.ptr(gdt), _lib.stream())
+        _lib.check(rc, 'dsdf_integrate_backward')
+        return gp, gv, gdt.sum(1), None
+
+
+def integrate(p, v, dt, active=None):
+    """active: optional uint8 (W) mask; inactive worlds pass their pose through."""
+    return _Integrate.apply(p, v, dt, active)

@@ -75,6 +75,34 @@ int dsdf_lcp_backward(const double* Q, const double* G, const double* A, const d
                       double* dQ, double* dp, double* dG, double* dh, double* dA, double* db, double* dF,
                       int32_t* status, void* ws, void* stream);
 
+/* ------------------------------------------------------------ SDF query ----
+ * Replaces SDF3D.query_sdfs(pts_loc, return_grads)  (sdf_physics/physics3d/bodies.py:721-760) with the
+ * analytic SDFs (bodies.py:38-125) and the grid SDF (bodies.py:203-257; ev_sdf_utils.grid_interp).
+ * shape (W,4) = [a,b,c,scale]: box dims/scale | sphere r/scale | cylinder r/scale,h/scale | grid: unused.
+ * grid: W grids of res^3 doubles, world w at grid + w*grid_world_stride (stride 0 = shared grid).
+ * pts (W,N,3) body-frame points -> sdf (W,N), dir (W,N,3) unit gradient (NULL/want_dir=0 to skip).
+ * Outside the cube |p| <= scale: sdf = scale, dir = 0.
+ */
+int dsdf_sdf_query(int kind, const double* shape, const double* grid, int res, long long grid_world_stride,
+                   const double* pts, int W, int N, int want_dir, double* sdf, double* dir, void* stream);
+/* VJP of the above w.r.t. pts with torch-autograd conventions (DiffGridSDF.backward for grids, bodies.py:253-257):
+ * gpts (W,N,3) = gsdf * d sdf/d pts + gdir . d dir/d pts ; gsdf / gdir may be NULL. */
+int dsdf_sdf_query_backward(int kind, const double* shape, const double* grid, int res, long long grid_world_stride,
+                            const double* pts, int W, int N, const double* gsdf, const double* gdir, double* gpts,
+                            void* stream);
+
+/* ----------------------------------------------------------- integrator ----
+ * Replaces Body3D.move (sdf_physics/physics3d/bodies.py:488-496): q <- standardize(quat(expmap(w dt)) * q),
+ * x <- x + v dt.  p (W,nb,7) = [qw,qx,qy,qz,x,y,z], v (W,nb,6) = [w,v], dt (W), active (W) uint8 or NULL;
+ * inactive worlds copy p through.  The world-frame inertia update of set_p (bodies.py:509-511) is fused
+ * into the dynamics kernel that consumes it.
+ */
+int dsdf_integrate(const double* p, const double* v, const double* dt, const unsigned char* active, int W, int nb,
+                   double* p_out, void* stream);
+/* gp (W,nb,7), gv (W,nb,6), gdt (W,nb) [per body; caller sums over bodies] from gp_out (W,nb,7). */
+int dsdf_integrate_backward(const double* p, const double* v, const double* dt, const unsigned char* active, int W,
+                            int nb, const double* gp_out, double* gp, double* gv, double* gdt, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
