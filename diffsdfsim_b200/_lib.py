@@ -19,12 +19,19 @@ SIGNATURES = {
     'dsdf_version': (c_i, []),
     'dsdf_lcp_workspace_bytes': (c_sz, [c_i, c_i, c_i, c_i]),
     'dsdf_lcp_smem_bytes': (c_sz, [c_i, c_i, c_i]),
-    'dsdf_lcp_forward': (c_i, [c_p] * 8 + [c_i] * 4 + [c_d, c_i, c_i, c_i] + [c_p] * 8),
-    'dsdf_lcp_backward': (c_i, [c_p] * 10 + [c_i] * 4 + [c_p] * 10),
+    'dsdf_lcp_forward': (c_i, [c_p] * 8 + [c_i] * 5 + [c_d, c_i, c_i, c_i] + [c_p] * 8),
+    'dsdf_lcp_backward': (c_i, [c_p] * 10 + [c_i] * 5 + [c_p] * 10),
     'dsdf_sdf_query': (c_i, [c_i, c_p, c_p, c_i, c_ll, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     'dsdf_sdf_query_backward': (c_i, [c_i, c_p, c_p, c_i, c_ll, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     'dsdf_integrate': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p]),
     'dsdf_integrate_backward': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
+    'dsdf_contacts_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
+    'dsdf_contact_chunks_per_face_count': (c_i, [c_i]),
+    'dsdf_contacts_detect': (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_d, c_i, c_i, c_i]
+                             + [c_p] * 10),
+    'dsdf_contact_geometry_backward': (c_i, [c_p, c_p, c_p, c_i, c_i, c_d, c_i, c_i] + [c_p] * 7),
+    'dsdf_dynamics_assemble': (c_i, [c_p] * 12 + [c_i] * 4 + [c_p] * 7),
+    'dsdf_dynamics_assemble_backward': (c_i, [c_p] * 12 + [c_i] * 6 + [c_p] * 17),
 }
 
 

@@ -15,9 +15,12 @@ CSRC = os.path.join(HERE, 'csrc')
 OUT = os.path.join(HERE, 'libdsdf_b200.so')
 OBJ = os.path.join(HERE, 'csrc', '_build')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
-FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17', '--use_fast_math=false',
+FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
          '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr']
-FLAGS = [f for f in FLAGS if f != '--use_fast_math=false']
+# Per-file extras.  The contact refinement makes round-off-level decisions (arg-min ties in Frank-Wolfe, which
+# body's normal to use on flat-flat contacts) that the reference takes with un-fused IEEE multiply/add (torch
+# element-wise ops): compile that file without FMA contraction so the same ties break the same way.
+EXTRA = {'dsdf_contacts.cu': ['-fmad=false']}
 
 
 def _sources():
@@ -31,7 +34,7 @@ def _stamp():
             if f.endswith(('.cu', '.cuh', '.h')):
                 with open(os.path.join(root, f), 'rb') as fh:
                     h.update(f.encode() + fh.read())
-    h.update(' '.join(FLAGS).encode())
+    h.update((' '.join(FLAGS) + repr(sorted(EXTRA.items()))).encode())
     return h.hexdigest()
 
 
@@ -45,7 +48,8 @@ def build(force=False, verbose=False):
 
     def cc(src):
         obj = os.path.join(OBJ, os.path.basename(src)[:-3] + '.o')
-        r = subprocess.run([NVCC] + FLAGS + ['-c', src, '-o', obj], capture_output=True, text=True)
+        r = subprocess.run([NVCC] + FLAGS + EXTRA.get(os.path.basename(src), []) + ['-c', src, '-o', obj],
+                           capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError('nvcc failed for %s:\n%s' % (src, r.stderr))
         with open(obj + '.ptxas.log', 'w') as fh:

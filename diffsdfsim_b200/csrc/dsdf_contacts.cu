@@ -1,0 +1,825 @@
+// SDF collision query for all worlds: broad phase -> cube overlap -> centroid candidate pass ->
+// Frank-Wolfe refinement -> contact construction -> normal-cluster / convex-hull filter -> compaction.
+//
+// Replaces (paths relative to the reference):
+//   World.find_contacts + py3ode broad phase   lcp_physics/physics/world.py:396-399 (AABB of the rotated cube, pairs i<j)
+//   FWContactHandler.__call__/_search_contacts  sdf_physics/physics3d/contacts.py:221-272
+//   _overlap                                    contacts.py:27-36
+//   _frank_wolfe                                contacts.py:39-94
+//   _compute_contacts                           contacts.py:161-214
+//   _filter_contacts (scipy Qhull on the host)  contacts.py:97-158
+// Kernels: overlap_kernel (CTA per world x pair), candidate_kernel (all faces, warp-ballot compaction),
+// refine_kernel (CTA per world: FW with the reference's pair-global early exit, contact geometry, filter),
+// contact_geometry_bwd_kernel (forward-mode duals w.r.t. the two poses).
+#include "dsdf_dense.cuh"
+#include "dsdf_sdf.cuh"
+
+namespace dsdf {
+
+struct BodyGeom {                 // mirrors dsdf_body_geom in include/dsdf_b200.h
+    int kind, nverts, nfaces, res;
+    const double* verts;          // (nverts,3) body frame; world w at verts + w*vstride
+    const int* faces;             // (nfaces,3)
+    const double* grid;           // res^3; world w at grid + w*gstride
+    long long vstride, gstride;
+};
+
+__device__ __forceinline__ void load_pose(const double* p, int w, int nb, int b, Q4<double>& q, V3<double>& x) {
+    const double* s = p + ((size_t)w * nb + b) * 7;
+    q = q4<double>(s[0], s[1], s[2], s[3]);
+    x = v3<double>(s[4], s[5], s[6]);
+}
+__device__ __forceinline__ SdfShape body_shape(const BodyGeom& g, const double* shape, int w, int nb, int b) {
+    const double* s = shape + ((size_t)w * nb + b) * 4;
+    SdfShape sh;
+    sh.kind = g.kind; sh.a = s[0]; sh.b = s[1]; sh.c = s[2]; sh.scale = s[3];
+    sh.grid = g.grid ? g.grid + (size_t)w * g.gstride : nullptr;
+    sh.res = g.res;
+    return sh;
+}
+__device__ __forceinline__ V3<double> load_vert(const BodyGeom& g, int w, int vi) {
+    const double* v = g.verts + (size_t)w * g.vstride + (size_t)vi * 3;
+    return v3<double>(v[0], v[1], v[2]);
+}
+// vertex of b1 (body frame) -> world -> b2 frame, same operation order as contacts.py:42 / bodies.py:718
+__device__ __forceinline__ V3<double> to_b2(V3<double> v, Q4<double> q1, V3<double> x1, Q4<double> q2i, V3<double> x2) {
+    return qapply(q2i, (qapply(q1, v) + x1) - x2);
+}
+
+// ------------------------------------------------------------------------------------------ broad phase + _overlap
+__global__ void __launch_bounds__(256)
+overlap_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs, const double* __restrict__ p,
+               const double* __restrict__ shape, const unsigned char* __restrict__ active, int nb, int npairs,
+               double body_eps, int* __restrict__ ovl) {
+    const int pair = blockIdx.x, w = blockIdx.y, tid = threadIdx.x;
+    if (active && !active[w]) return;
+    const int i = pairs[2 * pair], j = pairs[2 * pair + 1];
+    Q4<double> qi, qj; V3<double> xi, xj;
+    load_pose(p, w, nb, i, qi, xi);
+    load_pose(p, w, nb, j, qj, xj);
+    const double si = shape[((size_t)w * nb + i) * 4 + 3], sj = shape[((size_t)w * nb + j) * 4 + 3];
+    // AABB of the rotated cube of half side scale + eps (declared py3ode semantics)
+    M3<double> Ri = q2mat(qi), Rj = q2mat(qj);
+    bool hit = true;
+#pragma unroll
+    for (int a = 0; a < 3; ++a) {
+        const double hi = (fabs(Ri.m[3 * a]) + fabs(Ri.m[3 * a + 1]) + fabs(Ri.m[3 * a + 2])) * (si + body_eps);
+        const double hj = (fabs(Rj.m[3 * a]) + fabs(Rj.m[3 * a + 1]) + fabs(Rj.m[3 * a + 2])) * (sj + body_eps);
+        const double dc = a == 0 ? xi.x - xj.x : (a == 1 ? xi.y - xj.y : xi.z - xj.z);
+        hit = hit && (fabs(dc) <= hi + hj);
+    }
+    int result = 0;
+    if (hit) {
+        // any vertex of i inside j's cube AND any vertex of j inside i's cube
+        const BodyGeom gi = geom[i], gj = geom[j];
+        const Q4<double> qii = qinv(qi), qji = qinv(qj);
+        int found_ij = 0, found_ji = 0;
+        for (int base = 0; base < gi.nverts && !found_ij; base += 256 * 4) {
+            int f = 0;
+            for (int u = 0; u < 4; ++u) {
+                const int v = base + u * 256 + tid;
+                if (v < gi.nverts) {
+                    V3<double> t = to_b2(load_vert(gi, w, v), qi, xi, qji, xj);
+                    f |= (-sj <= t.x && t.x <= sj && -sj <= t.y && t.y <= sj && -sj <= t.z && t.z <= sj);
+                }
+            }
+            found_ij = __syncthreads_or(f);
+        }
+        if (found_ij) {
+            for (int base = 0; base < gj.nverts && !found_ji; base += 256 * 4) {
+                int f = 0;
+                for (int u = 0; u < 4; ++u) {
+                    const int v = base + u * 256 + tid;
+                    if (v < gj.nverts) {
+                        V3<double> t = to_b2(load_vert(gj, w, v), qj, xj, qii, xi);
+                        f |= (-si <= t.x && t.x <= si && -si <= t.y && t.y <= si && -si <= t.z && t.z <= si);
+                    }
+                }
+                found_ji = __syncthreads_or(f);
+            }
+        }
+        result = found_ij && found_ji;
+    }
+    if (tid == 0) ovl[(size_t)w * npairs + pair] = result;
+}
+
+// ------------------------------------------------------------------------------------------ centroid candidate pass
+// contacts.py:44-52: sdf(centroid) < max_i |centroid - v_i| + eps  and  |grad| > 1e-12
+enum { CAND_FPT = 4 };
+__global__ void __launch_bounds__(256)
+candidate_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs, const int* __restrict__ chunk_prefix,
+                 int ndirs, const double* __restrict__ p, const double* __restrict__ shape,
+                 const unsigned char* __restrict__ active, const int* __restrict__ ovl, int nb, int npairs,
+                 double eps, int capK, int* __restrict__ cand, int* __restrict__ ccnt) {
+    const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
+    if (active && !active[w]) return;
+    int d = 0;
+    while (d + 1 < ndirs && (int)blockIdx.x >= chunk_prefix[d + 1]) ++d;
+    const int chunk = blockIdx.x - chunk_prefix[d];
+    const int pair = d >> 1;
+    if (!ovl[(size_t)w * npairs + pair]) return;
+    const int i1 = (d & 1) ? pairs[2 * pair + 1] : pairs[2 * pair];
+    const int i2 = (d & 1) ? pairs[2 * pair] : pairs[2 * pair + 1];
+    const BodyGeom g1 = geom[i1];
+    const SdfShape s2 = body_shape(geom[i2], shape, w, nb, i2);
+    Q4<double> q1, q2; V3<double> x1, x2;
+    load_pose(p, w, nb, i1, q1, x1);
+    load_pose(p, w, nb, i2, q2, x2);
+    const Q4<double> q2i = qinv(q2);
+    int* my_cand = cand + ((size_t)w * ndirs + d) * capK;
+    int* my_cnt = ccnt + (size_t)w * ndirs + d;
+#pragma unroll 1
+    for (int u = 0; u < CAND_FPT; ++u) {
+        const int f = (chunk * CAND_FPT + u) * 256 + tid;
+        bool is_cand = false;
+        if (f < g1.nfaces) {
+            const int ia = g1.faces[3 * f], ib = g1.faces[3 * f + 1], ic = g1.faces[3 * f + 2];
+            const V3<double> a = to_b2(load_vert(g1, w, ia), q1, x1, q2i, x2);
+            const V3<double> b = to_b2(load_vert(g1, w, ib), q1, x1, q2i, x2);
+            const V3<double> c = to_b2(load_vert(g1, w, ic), q1, x1, q2i, x2);
+            const V3<double> ctr = v3<double>((a.x + b.x + c.x) / 3, (a.y + b.y + c.y) / 3, (a.z + b.z + c.z) / 3);
+            const SdfOut<double> o = sdf_query<double>(s2, ctr, true);
+            double rad = norm3(ctr - a);
+            rad = fmax(rad, norm3(ctr - b));
+            rad = fmax(rad, norm3(ctr - c));
+            is_cand = (o.d < rad + eps) && (norm3(o.n) > 1e-12);
+        }
+        const unsigned m = __ballot_sync(DSDF_FULL, is_cand);
+        if (m) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(my_cnt, __popc(m));
+            base = __shfl_sync(DSDF_FULL, base, 0);
+            if (is_cand) {
+                const int slot = base + __popc(m & ((1u << lane) - 1));
+                if (slot < capK) my_cand[slot] = f;
+            }
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------ contact geometry
+template <class S> struct ContactGeo { V3<S> n, p1, p2; S pen; };
+
+template <class S> __device__ __forceinline__ V3<S> lift(V3<double> a, S proto) {
+    return v3<S>(cst(proto, a.x), cst(proto, a.y), cst(proto, a.z));
+}
+__device__ __forceinline__ V3<double> strip(V3<double> a) { return a; }
+__device__ __forceinline__ V3<Dual> strip(V3<Dual> a) { return v3<Dual>(Dual(a.x.v), Dual(a.y.v), Dual(a.z.v)); }
+
+__device__ __forceinline__ double laplacian_fd(const SdfShape& s, V3<double> c, double d0, double h) {
+    double acc = 0.0;
+#pragma unroll
+    for (int ax = 0; ax < 3; ++ax) {
+        V3<double> sh = v3<double>(ax == 0 ? h : 0.0, ax == 1 ? h : 0.0, ax == 2 ? h : 0.0);
+        const double qp = sdf_query<double>(s, c + sh, false).d;
+        const double qm = sdf_query<double>(s, c - sh, false).d;
+        acc = acc + ((qp - 2 * d0) + qm);
+    }
+    return acc;
+}
+
+// contacts.py:161-214 for one contact; c_tri = sum(abc * local verts of the face) is pose-independent.
+template <class S>
+__device__ ContactGeo<S> contact_geometry(const SdfShape& s1, const SdfShape& s2, Q4<S> q1, V3<S> x1, Q4<S> q2, V3<S> x2,
+                                          V3<double> c_tri, double fd_eps, bool detach_b2) {
+    S proto = q1.w;
+    V3<S> c1 = lift<S>(c_tri, proto);
+    SdfOut<S> o1 = sdf_query<S>(s1, c1, true);
+    c1 = c1 - o1.n * o1.d;
+    o1 = sdf_query<S>(s1, c1, true);
+    V3<S> cw = qapply(q1, c1) + x1;
+    V3<S> c2 = qapply(qinv(q2), cw - x2);
+    if (detach_b2) c2 = strip(c2);
+    SdfOut<S> o2 = sdf_query<S>(s2, c2, true);
+    const V3<double> c1v = v3<double>(val(c1.x), val(c1.y), val(c1.z));
+    const V3<double> c2v = v3<double>(val(c2.x), val(c2.y), val(c2.z));
+    const double lap1 = laplacian_fd(s1, c1v, val(o1.d), fd_eps);
+    const double lap2 = laplacian_fd(s2, c2v, val(o2.d), fd_eps);
+    const bool stable = fabs(lap2) < fabs(lap1);
+    ContactGeo<S> g;
+    g.n = stable ? qapply(q2, o2.n) : neg(qapply(q1, o1.n));
+    g.p2 = qapply(q2, c2 - o2.n * o2.d);
+    g.p1 = qapply(q1, c1);
+    g.pen = -o2.d;
+    return g;
+}
+
+// ------------------------------------------------------------------------------------------ block helpers
+__device__ inline void bitonic_sort_int(int* a, int n2) {      // n2 power of two, ascending
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const int x = a[i], y = a[l];
+                    const bool up = (i & k) == 0;
+                    if ((x > y) == up) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+// (key double, payload int) ascending by key then payload
+__device__ inline void bitonic_sort_kv(double* key, double* key2, int* pay, int n2) {
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const double x = key[i], y = key[l], x2 = key2[i], y2 = key2[l];
+                    const bool gt = (x > y) || (x == y && (x2 > y2 || (x2 == y2 && pay[i] > pay[l])));
+                    const bool up = (i & k) == 0;
+                    if (gt == up) {
+                        key[i] = y; key[l] = x; key2[i] = y2; key2[l] = x2;
+                        const int t = pay[i]; pay[i] = pay[l]; pay[l] = t;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+}
+// order-preserving compaction offsets: returns exclusive prefix of flag over index order 0..n-1; *total = sum.
+// idx loop layout: element e handled by thread e % nt in round e / nt.  scan buffer: n ints.
+__device__ inline void block_exclusive_scan(int* buf, int n, int* total) {
+    // simple Hillis-Steele over shared memory (n <= 1024), in place, exclusive
+    __syncthreads();
+    __shared__ int carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n; base += blockDim.x) {
+        const int i = base + threadIdx.x;
+        int v = i < n ? buf[i] : 0;
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        int incl = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(DSDF_FULL, incl, o); if (lane >= o) incl += t; }
+        __shared__ int wsum[32];
+        if (lane == 31) wsum[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            int s = lane < (int)(blockDim.x >> 5) ? wsum[lane] : 0;
+            int si = s;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(DSDF_FULL, si, o); if (lane >= o) si += t; }
+            wsum[lane] = si - s;
+        }
+        __syncthreads();
+        const int excl = carry + wsum[warp] + incl - v;
+        if (i < n) buf[i] = excl;
+        __syncthreads();
+        if (threadIdx.x == blockDim.x - 1) carry = excl + v;
+        __syncthreads();
+    }
+    *total = carry;
+    __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------ refine kernel
+struct RefineSmem {
+    double* P;      // [9][capK] candidate triangle in b2 frame, later GEO rows 0..8
+    double* X;      // [3][capK] FW iterate, later GEO row 9 (pen) + scratch
+    double* ABC;    // [3][capK]
+    double* HK;     // [2][capK] hull sort keys
+    int* ID;        // [capK] face ids
+    int* SC;        // [capK] scan / flags
+    int* CL;        // [capK] cluster id
+    int* HI;        // [capK] hull payload
+    int* KEEP;      // [capK]
+    double* red;    // [40]
+};
+
+__host__ __device__ inline size_t refine_smem_bytes(int capK) {
+    return (size_t)capK * (17 * sizeof(double) + 5 * sizeof(int)) + 40 * sizeof(double) + 64;
+}
+
+struct DirResult { int count; int valid; };
+
+// One search direction (mesh body i1 -> SDF body i2) for world w.  On return the first `count` slots of
+// GEO (=P rows 0..8 + X row 0), ABC and ID hold the pre-filter contacts in ascending face order.
+__device__ DirResult search_direction(const RefineSmem& sm, int capK, const BodyGeom& g1, const SdfShape& s1,
+                                      const SdfShape& s2, Q4<double> q1, V3<double> x1, Q4<double> q2, V3<double> x2,
+                                      int w, const int* cand, int ncand, double eps, double tol, double fd_eps,
+                                      bool detach_b2) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int K = min(ncand, capK);
+    DirResult r; r.count = 0; r.valid = 1;
+    if (K == 0) return r;
+    int n2 = 1;
+    while (n2 < K) n2 <<= 1;
+    for (int i = tid; i < n2; i += nt) sm.ID[i] = i < K ? cand[i] : 0x7fffffff;
+    __syncthreads();
+    bitonic_sort_int(sm.ID, n2);
+    const Q4<double> q2i = qinv(q2);
+    // init: vertices in b2 frame, start at the vertex with the smallest SDF (contacts.py:57-61)
+    for (int k = tid; k < K; k += nt) {
+        const int f = sm.ID[k];
+        double best = 0.0; int bi = 0;
+#pragma unroll
+        for (int v = 0; v < 3; ++v) {
+            const V3<double> t = to_b2(load_vert(g1, w, g1.faces[3 * f + v]), q1, x1, q2i, x2);
+            sm.P[(3 * v + 0) * capK + k] = t.x; sm.P[(3 * v + 1) * capK + k] = t.y; sm.P[(3 * v + 2) * capK + k] = t.z;
+            const double d = sdf_query<double>(s2, t, false).d;
+            if (v == 0 || d < best) { best = d; bi = v; }
+        }
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            sm.X[c * capK + k] = sm.P[(3 * bi + c) * capK + k];
+            sm.ABC[c * capK + k] = c == bi ? 1.0 : 0.0;
+        }
+    }
+    __syncthreads();
+    // Frank-Wolfe, <= 32 iterations, PAIR-GLOBAL exit (contacts.py:63-82)
+    for (int it = 0; it < 32; ++it) {
+        int any_active = 0, any_pen = 0;
+        // phase 1: evaluate (no state change until the exit test is known)
+        // each thread handles at most ceil(capK/nt) candidates; keep decisions in registers via recompute in phase 2
+        for (int k = tid; k < K; k += nt) {
+            const V3<double> x = v3<double>(sm.X[k], sm.X[capK + k], sm.X[2 * capK + k]);
+            const SdfOut<double> o = sdf_query<double>(s2, x, true);
+            double dmin = 0.0; int pick = 0;
+#pragma unroll
+            for (int v = 0; v < 3; ++v) {
+                const double dp = sm.P[(3 * v) * capK + k] * o.n.x + sm.P[(3 * v + 1) * capK + k] * o.n.y +
+                                  sm.P[(3 * v + 2) * capK + k] * o.n.z;
+                if (v == 0 || dp < dmin) { dmin = dp; pick = v; }
+            }
+            const V3<double> s = v3<double>(sm.P[(3 * pick) * capK + k], sm.P[(3 * pick + 1) * capK + k],
+                                            sm.P[(3 * pick + 2) * capK + k]);
+            const double gain = (x.x - s.x) * o.n.x + (x.y - s.y) * o.n.y + (x.z - s.z) * o.n.z;
+            const int act = fabs(gain) > tol;
+            any_active |= act;
+            any_pen |= (o.d < -tol);
+            sm.SC[k] = act ? pick : -1;
+        }
+        // __syncthreads_or returns a predicate, not a bitwise OR: one barrier per flag
+        const int blk_active = __syncthreads_or(any_active);
+        const int blk_pen = __syncthreads_or(any_pen);
+        if (!blk_active || blk_pen) break;
+        const double gamma = 2.0 / (it + 2.0);
+        for (int k = tid; k < K; k += nt) {
+            const int pick = sm.SC[k];
+            if (pick >= 0) {
+#pragma unroll
+                for (int c = 0; c < 3; ++c) {
+                    sm.X[c * capK + k] = (1.0 - gamma) * sm.X[c * capK + k] + gamma * sm.P[(3 * pick + c) * capK + k];
+                    sm.ABC[c * capK + k] *= (1.0 - gamma);
+                }
+                sm.ABC[pick * capK + k] += gamma;
+            }
+            // frozen candidates: gamma = 0 -> x, abc unchanged (x = 1*x + 0*s, abc *= 1, += 0)
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    // push onto b1's surface and final threshold (contacts.py:84-91)
+    const Q4<double> rel = qmul(q2i, q1);
+    for (int k = tid; k < K; k += nt) {
+        const int f = sm.ID[k];
+        const V3<double> va = load_vert(g1, w, g1.faces[3 * f]), vb = load_vert(g1, w, g1.faces[3 * f + 1]),
+                         vc = load_vert(g1, w, g1.faces[3 * f + 2]);
+        const double a = sm.ABC[k], b = sm.ABC[capK + k], c = sm.ABC[2 * capK + k];
+        const V3<double> xb1 = v3<double>(va.x * a + vb.x * b + vc.x * c, va.y * a + vb.y * b + vc.y * c,
+                                          va.z * a + vb.z * b + vc.z * c);
+        const SdfOut<double> o1 = sdf_query<double>(s1, xb1, true);
+        const V3<double> dir = qapply(rel, o1.n);
+        const V3<double> x = v3<double>(sm.X[k] - o1.d * dir.x, sm.X[capK + k] - o1.d * dir.y,
+                                        sm.X[2 * capK + k] - o1.d * dir.z);
+        const double d = sdf_query<double>(s2, x, false).d;
+        sm.SC[k] = d <= eps ? 1 : 0;
+        // stash the body-frame triangle point for the geometry pass
+        sm.X[k] = xb1.x; sm.X[capK + k] = xb1.y; sm.X[2 * capK + k] = xb1.z;
+    }
+    int total = 0;
+    for (int k = tid; k < K; k += nt) sm.KEEP[k] = sm.SC[k];
+    __syncthreads();
+    block_exclusive_scan(sm.SC, K, &total);
+    // order-preserving compaction into the front (read everything first, then write)
+    {
+        const int rounds = (K + nt - 1) / nt;
+        for (int rd = 0; rd < rounds; ++rd) {
+            const int k = rd * nt + tid;
+            double t0 = 0, t1 = 0, t2 = 0, a0 = 0, a1 = 0, a2 = 0; int id = 0, dst = -1;
+            if (k < K && sm.KEEP[k]) {
+                dst = sm.SC[k];
+                t0 = sm.X[k]; t1 = sm.X[capK + k]; t2 = sm.X[2 * capK + k];
+                a0 = sm.ABC[k]; a1 = sm.ABC[capK + k]; a2 = sm.ABC[2 * capK + k];
+                id = sm.ID[k];
+            }
+            __syncthreads();
+            if (dst >= 0) {      // dst <= k and all smaller k already moved in earlier rounds / this round's reads done
+                sm.X[dst] = t0; sm.X[capK + dst] = t1; sm.X[2 * capK + dst] = t2;
+                sm.ABC[dst] = a0; sm.ABC[capK + dst] = a1; sm.ABC[2 * capK + dst] = a2;
+                sm.ID[dst] = id;
+            }
+            __syncthreads();
+        }
+    }
+    // contact geometry for every pre-filter contact (the reference's no_grad _compute_contacts)
+    int bad = 0;
+    for (int k = tid; k < total; k += nt) {
+        const V3<double> ct = v3<double>(sm.X[k], sm.X[capK + k], sm.X[2 * capK + k]);
+        const ContactGeo<double> g = contact_geometry<double>(s1, s2, q1, x1, q2, x2, ct, fd_eps, detach_b2);
+        sm.P[0 * capK + k] = g.n.x; sm.P[1 * capK + k] = g.n.y; sm.P[2 * capK + k] = g.n.z;
+        sm.P[3 * capK + k] = g.p1.x; sm.P[4 * capK + k] = g.p1.y; sm.P[5 * capK + k] = g.p1.z;
+        sm.P[6 * capK + k] = g.p2.x; sm.P[7 * capK + k] = g.p2.y; sm.P[8 * capK + k] = g.p2.z;
+        sm.HK[k] = g.pen;                                  // pen parked in HK row 0 until the filter needs HK
+        bad |= !(g.pen <= tol);
+    }
+    r.valid = !__syncthreads_or(bad);
+    r.count = total;
+    return r;
+}
+
+// Qhull-like round-off bound for coordinates of magnitude maxabs in `dim` dimensions (qh_distround)
+__device__ __forceinline__ double distround(int dim, double maxabs) {
+    return 2.220446049250313e-16 * (dim * sqrt((double)dim) * maxabs * 1.01 + maxabs);
+}
+
+// _filter_contacts (contacts.py:97-158): on entry n contacts in GEO (P rows) ; on exit KEEP[k] in {0,1}.
+// Returns status bits (4 = 3-D hull of >4 points needed: kept all of that cluster).
+__device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    int status = 0;
+    for (int k = tid; k < n; k += nt) sm.KEEP[k] = 1;
+    __syncthreads();
+    if (n <= 1) return 0;
+    const double* NX = sm.P; const double* NY = sm.P + capK; const double* NZ = sm.P + 2 * capK;
+    const double* PX = sm.P + 3 * capK; const double* PY = sm.P + 4 * capK; const double* PZ = sm.P + 5 * capK;
+    // zero normals are dropped; CL = -1 unassigned, -2 dropped
+    for (int k = tid; k < n; k += nt) {
+        const double nn = sqrt(NX[k] * NX[k] + NY[k] * NY[k] + NZ[k] * NZ[k]);
+        sm.CL[k] = nn > 1e-12 ? -1 : -2;
+        sm.KEEP[k] = 0;
+    }
+    __syncthreads();
+    for (int cl = 0; cl < n; ++cl) {
+        // representative = first unassigned
+        int first = 0x7fffffff;
+        for (int k = tid; k < n; k += nt) if (sm.CL[k] == -1) { first = k; break; }
+        __shared__ int s_first;
+        if (tid == 0) s_first = 0x7fffffff;
+        __syncthreads();
+        if (first != 0x7fffffff) atomicMin(&s_first, first);
+        __syncthreads();
+        const int rep = s_first;
+        if (rep == 0x7fffffff) break;
+        const double rx = NX[rep], ry = NY[rep], rz = NZ[rep];
+        for (int k = tid; k < n; k += nt) {
+            if (sm.CL[k] == -1) {
+                const double dp = NX[k] * rx + NY[k] * ry + NZ[k] * rz;
+                if (acos(fmin(dp, 1.0)) < 1e-2) sm.CL[k] = cl;
+            }
+        }
+        __syncthreads();
+        // gather members (ascending) into HI[0..m)
+        for (int k = tid; k < n; k += nt) sm.SC[k] = sm.CL[k] == cl;
+        int m = 0;
+        block_exclusive_scan(sm.SC, n, &m);
+        for (int k = tid; k < n; k += nt) if (sm.CL[k] == cl) sm.HI[sm.SC[k]] = k;
+        __syncthreads();
+        if (m == 1) { if (tid == 0) sm.KEEP[sm.HI[0]] = 1; __syncthreads(); continue; }
+        // statistics: mean/variance per axis, max |coord|
+        double s0 = 0, s1 = 0, s2 = 0, mx = 0;
+        for (int e = tid; e < m; e += nt) {
+            const int k = sm.HI[e];
+            s0 += PX[k]; s1 += PY[k]; s2 += PZ[k];
+            mx = fmax(mx, fmax(fabs(PX[k]), fmax(fabs(PY[k]), fabs(PZ[k]))));
+        }
+        s0 = block_reduce<RED_SUM>(s0, sm.red); s1 = block_reduce<RED_SUM>(s1, sm.red);
+        s2 = block_reduce<RED_SUM>(s2, sm.red); mx = block_reduce<RED_MAX>(mx, sm.red);
+        const double m0 = s0 / m, m1 = s1 / m, m2 = s2 / m;
+        double v0 = 0, v1 = 0, v2 = 0;
+        for (int e = tid; e < m; e += nt) {
+            const int k = sm.HI[e];
+            v0 += (PX[k] - m0) * (PX[k] - m0); v1 += (PY[k] - m1) * (PY[k] - m1); v2 += (PZ[k] - m2) * (PZ[k] - m2);
+        }
+        double var[3];
+        var[0] = block_reduce<RED_SUM>(v0, sm.red) / (m - 1);
+        var[1] = block_reduce<RED_SUM>(v1, sm.red) / (m - 1);
+        var[2] = block_reduce<RED_SUM>(v2, sm.red) / (m - 1);
+        // axis order: amin = first argmin (dropped first), then of the remaining two the first argmin is dropped next
+        int amin = 0;
+        if (var[1] < var[amin]) amin = 1;
+        if (var[2] < var[amin]) amin = 2;
+        const int r0 = amin == 0 ? 1 : 0, r1 = amin == 2 ? 1 : 2;          // remaining axes in order
+        const int drop2 = var[r1] < var[r0] ? r1 : r0;                       // first argmin among remaining
+        const int keep1 = drop2 == r0 ? r1 : r0;
+        const double* PA[3] = {PX, PY, PZ};
+        // extremes along the 1-D axis (first min / first max index, like argmin/argmax)
+        double lo = INFINITY, hi = -INFINITY;
+        for (int e = tid; e < m; e += nt) { const double c = PA[keep1][sm.HI[e]]; lo = fmin(lo, c); hi = fmax(hi, c); }
+        lo = block_reduce<RED_MIN>(lo, sm.red); hi = block_reduce<RED_MAX>(hi, sm.red);
+        __shared__ int s_lo, s_hi;
+        if (tid == 0) { s_lo = 0x7fffffff; s_hi = 0x7fffffff; }
+        __syncthreads();
+        for (int e = tid; e < m; e += nt) {
+            const double c = PA[keep1][sm.HI[e]];
+            if (c == lo) atomicMin(&s_lo, e);
+            if (c == hi) atomicMin(&s_hi, e);
+        }
+        __syncthreads();
+        const int e_lo = s_lo, e_hi = s_hi;
+        // --- is the set flat (3-D Qhull raises) ?  thickness w.r.t. the plane through a, b, c
+        bool flat3 = m < 4;
+        const int ka = sm.HI[e_lo], kb = sm.HI[e_hi];
+        const V3<double> A = v3<double>(PX[ka], PY[ka], PZ[ka]), B = v3<double>(PX[kb], PY[kb], PZ[kb]);
+        const V3<double> AB = B - A;
+        const double lab = norm3(AB);
+        // farthest point from line AB
+        double far = -1.0;
+        for (int e = tid; e < m; e += nt) {
+            const int k = sm.HI[e];
+            const V3<double> AP = v3<double>(PX[k], PY[k], PZ[k]) - A;
+            const double dl = lab > 0 ? norm3(cross(AB, AP)) / lab : norm3(AP);
+            far = fmax(far, dl);
+        }
+        far = block_reduce<RED_MAX>(far, sm.red);
+        __shared__ int s_far;
+        if (tid == 0) s_far = 0x7fffffff;
+        __syncthreads();
+        for (int e = tid; e < m; e += nt) {
+            const int k = sm.HI[e];
+            const V3<double> AP = v3<double>(PX[k], PY[k], PZ[k]) - A;
+            const double dl = lab > 0 ? norm3(cross(AB, AP)) / lab : norm3(AP);
+            if (dl == far) atomicMin(&s_far, e);
+        }
+        __syncthreads();
+        const bool collinear3 = !(far > 3.0 * distround(2, mx));
+        if (!flat3 && !collinear3) {
+            const int kc = sm.HI[s_far];
+            const V3<double> C = v3<double>(PX[kc], PY[kc], PZ[kc]);
+            V3<double> nrm = cross(AB, C - A);
+            const double ln = norm3(nrm);
+            double th = 0.0;
+            for (int e = tid; e < m; e += nt) {
+                const int k = sm.HI[e];
+                th = fmax(th, fabs(dot(nrm, v3<double>(PX[k], PY[k], PZ[k]) - A)) / ln);
+            }
+            th = block_reduce<RED_MAX>(th, sm.red);
+            flat3 = !(th > 4.0 * distround(3, mx));
+        } else {
+            flat3 = true;
+        }
+        if (!flat3) {
+            // genuine 3-D point set: every point of a tetrahedron is a hull vertex; larger sets are kept whole (flagged)
+            if (m > 4) status |= 4;
+            for (int e = tid; e < m; e += nt) sm.KEEP[sm.HI[e]] = 1;
+            __syncthreads();
+            continue;
+        }
+        // --- 2-D after dropping the min-variance axis: collinear (2-D Qhull raises) ?
+        const int u_ax = r0, v_ax = r1;
+        bool line2 = m < 3;
+        if (!line2) {
+            // extremes along the larger-variance remaining axis define the reference line
+            const int ke_lo = sm.HI[e_lo], ke_hi = sm.HI[e_hi];
+            const double ax_ = PA[u_ax][ke_lo], ay_ = PA[v_ax][ke_lo], bx_ = PA[u_ax][ke_hi], by_ = PA[v_ax][ke_hi];
+            const double l2 = sqrt((bx_ - ax_) * (bx_ - ax_) + (by_ - ay_) * (by_ - ay_));
+            double fd2 = 0.0, mx2 = 0.0;
+            for (int e = tid; e < m; e += nt) {
+                const int k = sm.HI[e];
+                const double px = PA[u_ax][k], py = PA[v_ax][k];
+                const double cr = (bx_ - ax_) * (py - ay_) - (by_ - ay_) * (px - ax_);
+                fd2 = fmax(fd2, l2 > 0 ? fabs(cr) / l2 : sqrt((px - ax_) * (px - ax_) + (py - ay_) * (py - ay_)));
+                mx2 = fmax(mx2, fmax(fabs(px), fabs(py)));
+            }
+            fd2 = block_reduce<RED_MAX>(fd2, sm.red);
+            mx2 = block_reduce<RED_MAX>(mx2, sm.red);
+            line2 = !(fd2 > 3.0 * distround(2, mx2));
+        }
+        if (line2) {
+            // 1-D: min and max along the surviving axis, or a single point (contacts.py:143-150)
+            if (tid == 0) {
+                sm.KEEP[sm.HI[e_lo]] = 1;
+                if (hi - lo > eps) sm.KEEP[sm.HI[e_hi]] = 1;
+            }
+            __syncthreads();
+            continue;
+        }
+        // --- planar convex hull (strict vertices only): sort by (u,v), monotone chain on one thread
+        int n2 = 1;
+        while (n2 < m) n2 <<= 1;
+        double* KU = sm.HK; double* KV = sm.HK + capK;
+        for (int e = tid; e < n2; e += nt) {
+            if (e < m) { const int k = sm.HI[e]; KU[e] = PA[u_ax][k]; KV[e] = PA[v_ax][k]; }
+            else { KU[e] = INFINITY; KV[e] = INFINITY; sm.HI[e] = 0x7fffffff; }
+        }
+        __syncthreads();
+        bitonic_sort_kv(KU, KV, sm.HI, n2);
+        if (tid == 0) {
+            double mxc = 0.0;
+            for (int e = 0; e < m; ++e) mxc = fmax(mxc, fmax(fabs(KU[e]), fabs(KV[e])));
+            const double tol_d = 2.0 * distround(2, mxc);
+            int* H = sm.SC;                 // stack of sorted positions
+            int top = 0;
+            // exact duplicates (faces sharing a vertex yield the same contact point): only the first (lowest
+            // contact index, the sort is stable in it) can be a hull vertex -- compact them away first
+            int mu = 0;
+            for (int e = 0; e < m; ++e) {
+                if (mu > 0 && KU[e] == KU[mu - 1] && KV[e] == KV[mu - 1]) continue;
+                KU[mu] = KU[e]; KV[mu] = KV[e]; sm.HI[mu] = sm.HI[e]; ++mu;
+            }
+            m = mu;
+            // lower chain
+            for (int e = 0; e < m; ++e) {
+                while (top >= 2) {
+                    const int a = H[top - 2], b = H[top - 1];
+                    const double ex = KU[e] - KU[a], ey = KV[e] - KV[a];
+                    const double cr = (KU[b] - KU[a]) * ey - (KV[b] - KV[a]) * ex;   // > 0: left turn keeps b
+                    const double len = sqrt(ex * ex + ey * ey);
+                    if (cr > tol_d * len) break;
+                    --top;
+                }
+                H[top++] = e;
+            }
+            const int lower = top + 1;
+            for (int e = m - 2; e >= 0; --e) {
+                while (top >= lower) {
+                    const int a = H[top - 2], b = H[top - 1];
+                    const double ex = KU[e] - KU[a], ey = KV[e] - KV[a];
+                    const double cr = (KU[b] - KU[a]) * ey - (KV[b] - KV[a]) * ex;
+                    const double len = sqrt(ex * ex + ey * ey);
+                    if (cr > tol_d * len) break;
+                    --top;
+                }
+                H[top++] = e;
+            }
+            --top;                           // last point equals the first
+            if (m == 1) { top = 1; H[0] = 0; }
+            for (int t = 0; t < top; ++t) sm.KEEP[sm.HI[H[t]]] = 1;
+        }
+        __syncthreads();
+    }
+    __syncthreads();
+    return status;
+}
+
+__global__ void __launch_bounds__(256)
+refine_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs, int ndirs,
+              const double* __restrict__ p, const double* __restrict__ shape, const unsigned char* __restrict__ active,
+              const int* __restrict__ ovl, int nb, int npairs, double eps, double tol, double fd_eps, int detach_b2,
+              int capK, const int* __restrict__ cand, const int* __restrict__ ccnt, int maxc,
+              int* __restrict__ count, int* __restrict__ cbody, int* __restrict__ cface, double* __restrict__ cabc,
+              double* __restrict__ cgeo, int* __restrict__ wstatus, int* __restrict__ pre_ids, int* __restrict__ pre_cnt) {
+    extern __shared__ double smraw[];
+    const int w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    if (active && !active[w]) return;
+    RefineSmem sm;
+    sm.P = smraw; sm.X = sm.P + 9 * (size_t)capK; sm.ABC = sm.X + 3 * (size_t)capK; sm.HK = sm.ABC + 3 * (size_t)capK;
+    sm.red = sm.HK + 2 * (size_t)capK;
+    sm.ID = reinterpret_cast<int*>(sm.red + 40);
+    sm.SC = sm.ID + capK; sm.CL = sm.SC + capK; sm.HI = sm.CL + capK; sm.KEEP = sm.HI + capK;
+    int nout = 0, status = 0;
+    for (int pair = 0; pair < npairs; ++pair) {
+        if (!ovl[(size_t)w * npairs + pair]) {
+            if (pre_cnt && tid == 0) { pre_cnt[(size_t)w * ndirs + 2 * pair] = -1; pre_cnt[(size_t)w * ndirs + 2 * pair + 1] = -1; }
+            continue;
+        }
+        for (int rev = 0; rev < 2; ++rev) {
+            const int d = 2 * pair + rev;
+            const int i1 = rev ? pairs[2 * pair + 1] : pairs[2 * pair];
+            const int i2 = rev ? pairs[2 * pair] : pairs[2 * pair + 1];
+            const BodyGeom g1 = geom[i1];
+            const SdfShape s1 = body_shape(g1, shape, w, nb, i1);
+            const SdfShape s2 = body_shape(geom[i2], shape, w, nb, i2);
+            Q4<double> q1, q2; V3<double> x1, x2;
+            load_pose(p, w, nb, i1, q1, x1);
+            load_pose(p, w, nb, i2, q2, x2);
+            const int ncand = ccnt[(size_t)w * ndirs + d];
+            if (ncand > capK) status |= 1;
+            DirResult r = search_direction(sm, capK, g1, s1, s2, q1, x1, q2, x2, w,
+                                           cand + ((size_t)w * ndirs + d) * capK, ncand, eps, tol, fd_eps, detach_b2 != 0);
+            if (pre_cnt) {
+                if (tid == 0) pre_cnt[(size_t)w * ndirs + d] = r.count;
+                for (int k = tid; k < r.count; k += nt) pre_ids[((size_t)w * ndirs + d) * capK + k] = sm.ID[k];
+            }
+            // stash pen (HK row 0) into X row 0 before the filter reuses HK
+            for (int k = tid; k < r.count; k += nt) sm.X[k] = sm.HK[k];
+            __syncthreads();
+            if (r.valid) status |= filter_contacts(sm, capK, r.count, eps);
+            else { status |= 8; for (int k = tid; k < r.count; k += nt) sm.KEEP[k] = 1; __syncthreads(); }
+            // append kept contacts in ascending face order
+            for (int k = tid; k < r.count; k += nt) sm.SC[k] = sm.KEEP[k];
+            int nk = 0;
+            block_exclusive_scan(sm.SC, r.count, &nk);
+            for (int k = tid; k < r.count; k += nt) {
+                if (!sm.KEEP[k]) continue;
+                const int o = nout + sm.SC[k];
+                if (o >= maxc) continue;
+                const size_t oo = (size_t)w * maxc + o;
+                cbody[2 * oo] = i1; cbody[2 * oo + 1] = i2;
+                cface[oo] = sm.ID[k];
+                cabc[3 * oo] = sm.ABC[k]; cabc[3 * oo + 1] = sm.ABC[capK + k]; cabc[3 * oo + 2] = sm.ABC[2 * capK + k];
+#pragma unroll
+                for (int c = 0; c < 9; ++c) cgeo[10 * oo + c] = sm.P[(size_t)c * capK + k];
+                cgeo[10 * oo + 9] = sm.X[k];
+            }
+            if (nout + nk > maxc) status |= 2;
+            nout = min(nout + nk, maxc);
+            __syncthreads();
+            if (!r.valid) {                       // contacts.py:238-240: reverse direction only after a valid first one
+                if (rev == 0 && pre_cnt && tid == 0) pre_cnt[(size_t)w * ndirs + d + 1] = -1;
+                break;
+            }
+        }
+    }
+    if (tid == 0) { count[w] = nout; wstatus[w] = status; }
+}
+
+// ------------------------------------------------------------------------------------------ geometry VJP w.r.t. poses
+// One CTA per world; thread (body, component) accumulates over that world's contacts sequentially (deterministic).
+__global__ void __launch_bounds__(128)
+contact_geometry_bwd_kernel(const BodyGeom* __restrict__ geom, const double* __restrict__ p,
+                            const double* __restrict__ shape, int nb, double fd_eps, int detach_b2, int maxc,
+                            const int* __restrict__ count, const int* __restrict__ cbody, const int* __restrict__ cface,
+                            const double* __restrict__ cabc, const double* __restrict__ ggeo, double* __restrict__ gp) {
+    const int w = blockIdx.x;
+    const int nc = min(count[w], maxc);
+    for (int t = threadIdx.x; t < nb * 7; t += blockDim.x) {
+        const int body = t / 7, comp = t % 7;
+        double acc = 0.0;
+        for (int k = 0; k < nc; ++k) {
+            const size_t oo = (size_t)w * maxc + k;
+            const int i1 = cbody[2 * oo], i2 = cbody[2 * oo + 1];
+            if (body != i1 && body != i2) continue;
+            const BodyGeom g1 = geom[i1];
+            const SdfShape s1 = body_shape(g1, shape, w, nb, i1);
+            const SdfShape s2 = body_shape(geom[i2], shape, w, nb, i2);
+            const double* P1 = p + ((size_t)w * nb + i1) * 7;
+            const double* P2 = p + ((size_t)w * nb + i2) * 7;
+            const int s1seed = body == i1 ? comp : -1, s2seed = body == i2 ? comp : -1;
+            auto D = [](const double* s, int k_, int seed) { return Dual(s[k_], seed == k_ ? 1.0 : 0.0); };
+            Q4<Dual> q1 = q4<Dual>(D(P1, 0, s1seed), D(P1, 1, s1seed), D(P1, 2, s1seed), D(P1, 3, s1seed));
+            V3<Dual> x1 = v3<Dual>(D(P1, 4, s1seed), D(P1, 5, s1seed), D(P1, 6, s1seed));
+            Q4<Dual> q2 = q4<Dual>(D(P2, 0, s2seed), D(P2, 1, s2seed), D(P2, 2, s2seed), D(P2, 3, s2seed));
+            V3<Dual> x2 = v3<Dual>(D(P2, 4, s2seed), D(P2, 5, s2seed), D(P2, 6, s2seed));
+            const int f = cface[oo];
+            const V3<double> va = load_vert(g1, w, g1.faces[3 * f]), vb = load_vert(g1, w, g1.faces[3 * f + 1]),
+                             vc = load_vert(g1, w, g1.faces[3 * f + 2]);
+            const double a = cabc[3 * oo], b = cabc[3 * oo + 1], c = cabc[3 * oo + 2];
+            const V3<double> ct = v3<double>(va.x * a + vb.x * b + vc.x * c, va.y * a + vb.y * b + vc.y * c,
+                                             va.z * a + vb.z * b + vc.z * c);
+            const ContactGeo<Dual> g = contact_geometry<Dual>(s1, s2, q1, x1, q2, x2, ct, fd_eps, detach_b2 != 0);
+            const double* gg = ggeo + 10 * oo;
+            acc += gg[0] * g.n.x.d + gg[1] * g.n.y.d + gg[2] * g.n.z.d + gg[3] * g.p1.x.d + gg[4] * g.p1.y.d +
+                   gg[5] * g.p1.z.d + gg[6] * g.p2.x.d + gg[7] * g.p2.y.d + gg[8] * g.p2.z.d + gg[9] * g.pen.d;
+        }
+        gp[((size_t)w * nb + body) * 7 + comp] = acc;
+    }
+}
+
+}  // namespace dsdf
+
+using namespace dsdf;
+
+extern "C" {
+
+size_t dsdf_contacts_workspace_bytes(int W, int npairs, int capK) {
+    const size_t ndirs = 2 * (size_t)npairs;
+    return ((size_t)W * npairs + (size_t)W * ndirs + (size_t)W * ndirs * capK + 16) * sizeof(int);
+}
+
+int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, const int32_t* chunk_prefix, int total_chunks,
+                         int npairs, const double* p, const double* shape, const unsigned char* active,
+                         int W, int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
+                         int capK, int maxc, int32_t* count, int32_t* cbody, int32_t* cface, double* cabc, double* cgeo,
+                         int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, void* ws, void* stream) {
+    if (W <= 0 || nb <= 0 || npairs < 0 || capK < 32 || capK > 1024 || maxc <= 0) return -1;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (npairs == 0) {
+        cudaMemsetAsync(count, 0, sizeof(int) * W, st);   // note: inactive worlds are also zeroed in this trivial case
+        cudaMemsetAsync(wstatus, 0, sizeof(int) * W, st);
+        return (int)cudaGetLastError();
+    }
+    const int ndirs = 2 * npairs;
+    int* ovl = (int*)ws;
+    int* ccnt = ovl + (size_t)W * npairs;
+    int* cand = ccnt + (size_t)W * ndirs;
+    const size_t smem = refine_smem_bytes(capK);
+    if (smem > 227 * 1024) return -2;
+    cudaMemsetAsync(ccnt, 0, sizeof(int) * (size_t)W * ndirs, st);
+    const BodyGeom* G = reinterpret_cast<const BodyGeom*>(geom);
+    overlap_kernel<<<dim3(npairs, W), 256, 0, st>>>(G, pairs, p, shape, active, nb, npairs, body_eps, ovl);
+    if (total_chunks > 0)
+        candidate_kernel<<<dim3(total_chunks, W), 256, 0, st>>>(G, pairs, chunk_prefix, ndirs, p, shape, active, ovl, nb,
+                                                              npairs, eps, capK, cand, ccnt);
+    cudaError_t e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return (int)e;
+    refine_kernel<<<W, 256, smem, st>>>(G, pairs, ndirs, p, shape, active, ovl, nb, npairs, eps, tol, fd_eps, detach_b2,
+                                        capK, cand, ccnt, maxc, count, cbody, cface, cabc, cgeo, wstatus, pre_ids, pre_cnt);
+    return (int)cudaGetLastError();
+}
+
+int dsdf_contact_chunks_per_face_count(int nfaces) { return (nfaces + 256 * CAND_FPT - 1) / (256 * CAND_FPT); }
+
+int dsdf_contact_geometry_backward(const dsdf_body_geom* geom, const double* p, const double* shape, int W, int nb,
+                                   double fd_eps, int detach_b2, int maxc, const int32_t* count, const int32_t* cbody,
+                                   const int32_t* cface, const double* cabc, const double* ggeo, double* gp, void* stream) {
+    if (W <= 0 || nb <= 0 || maxc <= 0) return -1;
+    contact_geometry_bwd_kernel<<<W, 128, 0, (cudaStream_t)stream>>>(reinterpret_cast<const BodyGeom*>(geom), p, shape, nb,
+                                                                    fd_eps, detach_b2, maxc, count, cbody, cface, cabc,
+                                                                    ggeo, gp);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

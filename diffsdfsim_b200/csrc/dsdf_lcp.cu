@@ -261,13 +261,19 @@ __global__ void __launch_bounds__(256)
 lcp_forward_kernel(const double* __restrict__ Q, const double* __restrict__ p, const double* __restrict__ G,
                    const double* __restrict__ h, const double* __restrict__ A, const double* __restrict__ b,
                    const double* __restrict__ F, const int32_t* __restrict__ nineq_w,
-                   int nz, int neq, int niCap, double eps, int not_improved_lim, int max_iter, int check_spd,
+                   int nz, int neq, int niCap, int niS, double eps, int not_improved_lim, int max_iter, int check_spd,
                    double* __restrict__ xo, double* __restrict__ nuo, double* __restrict__ lamo,
                    double* __restrict__ so, int32_t* __restrict__ status_o, int32_t* __restrict__ iters_o,
                    double* __restrict__ ws) {
     extern __shared__ double sm[];
     const int w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    const LcpSmem L = lcp_layout(nz, neq, niCap);
+    const LcpSmem L = lcp_layout(nz, neq, niS);     // shared memory sized for niS rows; global strides use niCap
+    if (nineq_w && nineq_w[w] < 0) return;          // masked world: outputs untouched
+    if (nineq_w && nineq_w[w] > niS) {              // does not fit the launch's shared memory: flag, NaN outputs
+        for (int i = tid; i < nz; i += nt) xo[(size_t)w * nz + i] = NAN;
+        if (tid == 0) { status_o[w] = DSDF_LCP_TOO_LARGE; if (iters_o) iters_o[w] = 0; }
+        return;
+    }
     const int ni = nineq_w ? min(nineq_w[w], niCap) : niCap;
     LcpCtx c = lcp_ctx(sm, L, ni);
     const double* Qw = Q + (size_t)w * nz * nz;
@@ -417,13 +423,15 @@ lcp_backward_kernel(const double* __restrict__ Q, const double* __restrict__ G, 
                     const double* __restrict__ F, const int32_t* __restrict__ nineq_w,
                     const double* __restrict__ xs, const double* __restrict__ nus, const double* __restrict__ lams,
                     const double* __restrict__ ss, const double* __restrict__ gz,
-                    int nz, int neq, int niCap,
+                    int nz, int neq, int niCap, int niS,
                     double* __restrict__ dQ, double* __restrict__ dp, double* __restrict__ dG, double* __restrict__ dh,
                     double* __restrict__ dA, double* __restrict__ db, double* __restrict__ dF,
                     int32_t* __restrict__ status_o, double* __restrict__ ws) {
     extern __shared__ double sm[];
     const int w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
-    const LcpSmem L = lcp_layout(nz, neq, niCap);
+    const LcpSmem L = lcp_layout(nz, neq, niS);
+    if (nineq_w && nineq_w[w] < 0) return;          // masked world: outputs untouched
+    if (nineq_w && nineq_w[w] > niS) { if (tid == 0 && status_o) status_o[w] = DSDF_LCP_TOO_LARGE; return; }
     const int ni = nineq_w ? min(nineq_w[w], niCap) : niCap;
     LcpCtx c = lcp_ctx(sm, L, ni);
     const double* Qw = Q + (size_t)w * nz * nz;
@@ -482,42 +490,44 @@ size_t dsdf_lcp_workspace_bytes(int W, int nz, int neq, int nineq) {
 
 size_t dsdf_lcp_smem_bytes(int nz, int neq, int nineq) { return lcp_layout(nz, neq, nineq).bytes; }
 
-static int lcp_check(int W, int nz, int neq, int nineq, size_t* smem) {
+static int lcp_check(int W, int nz, int neq, int nineq, int* nineq_smem, size_t* smem) {
     if (W <= 0 || nz <= 0 || neq < 0 || nineq < 0) return -1;
-    *smem = lcp_layout(nz, neq, nineq).bytes;
+    if (*nineq_smem <= 0 || *nineq_smem > nineq) *nineq_smem = nineq;
+    *smem = lcp_layout(nz, neq, *nineq_smem).bytes;
     if (*smem > 227 * 1024) return -2;
     return 0;
 }
 
 int dsdf_lcp_forward(const double* Q, const double* p, const double* G, const double* h,
                      const double* A, const double* b, const double* F, const int32_t* nineq_w,
-                     int W, int nz, int neq, int nineq,
+                     int W, int nz, int neq, int nineq, int nineq_smem,
                      double eps, int not_improved_lim, int max_iter, int check_spd,
                      double* x, double* nu, double* lam, double* s,
                      int32_t* status, int32_t* iters, void* ws, void* stream) {
     size_t smem;
-    int rc = lcp_check(W, nz, neq, nineq, &smem);
+    int rc = lcp_check(W, nz, neq, nineq, &nineq_smem, &smem);
     if (rc) return rc;
     cudaError_t e = cudaFuncSetAttribute(lcp_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    lcp_forward_kernel<<<W, 256, smem, (cudaStream_t)stream>>>(Q, p, G, h, A, b, F, nineq_w, nz, neq, nineq, eps,
-                                                               not_improved_lim, max_iter, check_spd, x, nu, lam, s,
+    lcp_forward_kernel<<<W, 256, smem, (cudaStream_t)stream>>>(Q, p, G, h, A, b, F, nineq_w, nz, neq, nineq, nineq_smem,
+                                                               eps, not_improved_lim, max_iter, check_spd, x, nu, lam, s,
                                                                status, iters, (double*)ws);
     return (int)cudaGetLastError();
 }
 
 int dsdf_lcp_backward(const double* Q, const double* G, const double* A, const double* F,
                       const int32_t* nineq_w, const double* x, const double* nu, const double* lam,
-                      const double* s, const double* gz, int W, int nz, int neq, int nineq,
+                      const double* s, const double* gz, int W, int nz, int neq, int nineq, int nineq_smem,
                       double* dQ, double* dp, double* dG, double* dh, double* dA, double* db, double* dF,
                       int32_t* status, void* ws, void* stream) {
     size_t smem;
-    int rc = lcp_check(W, nz, neq, nineq, &smem);
+    int rc = lcp_check(W, nz, neq, nineq, &nineq_smem, &smem);
     if (rc) return rc;
     cudaError_t e = cudaFuncSetAttribute(lcp_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
     lcp_backward_kernel<<<W, 256, smem, (cudaStream_t)stream>>>(Q, G, A, F, nineq_w, x, nu, lam, s, gz, nz, neq, nineq,
-                                                                dQ, dp, dG, dh, dA, db, dF, status, (double*)ws);
+                                                                nineq_smem, dQ, dp, dG, dh, dA, db, dF, status,
+                                                                (double*)ws);
     return (int)cudaGetLastError();
 }
 

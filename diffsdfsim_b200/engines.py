@@ -1,0 +1,125 @@
+"""Engine plug-in: ``PdipmEngine.solve_dynamics(world, dt) -> new_v`` (lcp_physics/physics/engines.py:22-83), batched.
+
+``World3D(engine='PdipmEngine')`` resolves this class by name exactly like the reference (utils.get_instance);
+``B200Engine`` is an alias.  One call assembles the mixed LCP of every active world on the device
+(dsdf_dynamics_assemble), solves it (dsdf_lcp_forward, one CTA per world) and negates the solution.
+Backward = dsdf_lcp_backward + dsdf_dynamics_assemble_backward.
+"""
+import torch
+
+from . import _lib
+from .lcp import lcp_backward_raw, lcp_solve_raw
+
+F64 = torch.float64
+
+
+def _assemble(L, p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody, geo, fd):
+    W, nb = p.shape[0], p.shape[1]
+    maxc = geo.shape[1]
+    nz, ni = 6 * nb, maxc * (2 + fd)
+    dev = p.device
+    Q = torch.empty(W, nz, nz, dtype=F64, device=dev)
+    pv = torch.empty(W, nz, dtype=F64, device=dev)
+    G = torch.empty(W, ni, nz, dtype=F64, device=dev)
+    h = torch.empty(W, ni, dtype=F64, device=dev)
+    Fm = torch.empty(W, ni, ni, dtype=F64, device=dev)
+    nin = torch.empty(W, dtype=torch.int32, device=dev)
+    rc = L.dsdf_dynamics_assemble(_lib.ptr(p), _lib.ptr(v), _lib.ptr(mass), _lib.ptr(Ibody), _lib.ptr(fric),
+                                  _lib.ptr(rest), _lib.ptr(f), _lib.ptr(dt), _lib.ptr(active), _lib.ptr(count),
+                                  _lib.ptr(cbody), _lib.ptr(geo), W, nb, maxc, fd, _lib.ptr(Q), _lib.ptr(pv),
+                                  _lib.ptr(G), _lib.ptr(h), _lib.ptr(Fm), _lib.ptr(nin), _lib.stream())
+    _lib.check(rc, 'dsdf_dynamics_assemble')
+    return Q, pv, G, h, Fm, nin
+
+
+class _Dynamics(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, p, v, mass, Ibody, fric, rest, f, dt, geo, count, cbody, A, b, active, cfg):
+        L = _lib.lib()
+        _lib.require_cuda(p, v)
+        c = lambda t: t.contiguous()
+        p, v, mass, Ibody, fric, rest, f, dt, geo = [c(t) for t in (p, v, mass, Ibody, fric, rest, f, dt, geo)]
+        fd, max_iter = cfg['fric_dirs'], cfg['max_iter']
+        Q, pv, G, h, Fm, nin = _assemble(L, p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody, geo, fd)
+        x, nu, lam, s, status, iters = lcp_solve_raw(Q, pv, G, h, A, b, Fm, nin, max_iter=max_iter, check_spd=False,
+                                                     nineq_smem=cfg['ni_smem'])
+        W, nb = p.shape[0], p.shape[1]
+        new_v = (-x).reshape(W, nb, 6)
+        if active is not None:
+            new_v = torch.where(active.bool().reshape(W, 1, 1), new_v, v)
+        ctx.save_for_backward(p, v, mass, Ibody, fric, rest, f, dt, geo, count, cbody, A, x, nu, lam, s, nin,
+                              active if active is not None else p.new_empty(0))
+        ctx.cfg = cfg
+        cfg['last_status'], cfg['last_iters'] = status, iters
+        ctx.mark_non_differentiable(status)
+        return new_v, status
+
+    @staticmethod
+    def backward(ctx, gv_new, _gstatus):
+        L = _lib.lib()
+        (p, v, mass, Ibody, fric, rest, f, dt, geo, count, cbody, A, x, nu, lam, s, nin, active) = ctx.saved_tensors
+        active = active if active.numel() else None
+        cfg = ctx.cfg
+        fd = cfg['fric_dirs']
+        W, nb = p.shape[0], p.shape[1]
+        maxc = geo.shape[1]
+        Q, pv, G, h, Fm, _ = _assemble(L, p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody, geo, fd)
+        gz = (-gv_new).reshape(W, 6 * nb).contiguous()
+        gpass = None
+        if active is not None:
+            am = active.bool().reshape(W, 1)
+            gpass = torch.where(am, torch.zeros_like(gz), -gz).reshape(W, nb, 6)   # inactive worlds: new_v = v
+            gz = torch.where(am, gz, torch.zeros_like(gz))
+        dQ, dp, dG, dh, _, _, dF = lcp_backward_raw(Q, G, A, Fm, x, nu, lam, s, gz, nin,
+                                                    need=(True, True, True, True, False, False, True),
+                                                    nineq_smem=cfg['ni_smem'])
+        dev = p.device
+        gp = torch.empty_like(p)
+        gv = torch.empty_like(v)
+        gmass, gI = torch.empty_like(mass), torch.empty_like(Ibody)
+        gfric, grest, gf = torch.empty_like(fric), torch.empty_like(rest), torch.empty_like(f)
+        gdt, ggeo = torch.empty(W, dtype=F64, device=dev), torch.empty_like(geo)
+        rc = L.dsdf_dynamics_assemble_backward(
+            _lib.ptr(p), _lib.ptr(v), _lib.ptr(mass), _lib.ptr(Ibody), _lib.ptr(fric), _lib.ptr(rest), _lib.ptr(f),
+            _lib.ptr(dt), _lib.ptr(active), _lib.ptr(count), _lib.ptr(cbody), _lib.ptr(geo), W, nb, maxc, fd,
+            int(cfg['stop_contact_grad']), int(cfg['stop_friction_grad']), _lib.ptr(Q), _lib.ptr(G), _lib.ptr(dQ),
+            _lib.ptr(dp), _lib.ptr(dG), _lib.ptr(dh), _lib.ptr(dF), _lib.ptr(gp), _lib.ptr(gv), _lib.ptr(gmass),
+            _lib.ptr(gI), _lib.ptr(gfric), _lib.ptr(grest), _lib.ptr(gf), _lib.ptr(gdt), _lib.ptr(ggeo), _lib.stream())
+        _lib.check(rc, 'dsdf_dynamics_assemble_backward')
+        if gpass is not None:
+            gv = gv + gpass
+        return gp, gv, gmass, gI, gfric, grest, gf, gdt, ggeo, None, None, None, None, None, None
+
+
+class Engine:
+    """engines.py:16-20."""
+
+    def solve_dynamics(self, world, dt):
+        raise NotImplementedError
+
+
+class PdipmEngine(Engine):
+    """Primal-dual interior-point LCP engine (engines.py:22-83) over all worlds at once."""
+
+    def __init__(self, max_iter=10):
+        self.max_iter = max_iter
+        self.last_status = None
+
+    def solve_dynamics(self, world, dt, active=None):
+        """dt: (W,) tensor (may carry grad).  Returns new_v (W,nb,6)."""
+        st = world.state
+        f = world.apply_forces(world.t)
+        cfg = dict(fric_dirs=world.fric_dirs, max_iter=self.max_iter, stop_contact_grad=world.stop_contact_grad,
+                   stop_friction_grad=world.stop_friction_grad,
+                   ni_smem=max(world.max_nc, 1) * (2 + world.fric_dirs))
+        new_v, status = _Dynamics.apply(st.p, st.v, st.mass, st.Ibody, st.fric, st.rest, f, dt, world.contact_geo,
+                                        world.contact_set.count, world.contact_set.body, world.A, world.b, active, cfg)
+        self.last_status = status
+        return new_v
+
+    def post_stabilization(self, world):
+        raise NotImplementedError('post-stabilisation (engines.py:85-121) is off by default in the reference '
+                                  '(utils.py:64) and listed under "next" in SURVEY.md s8f')
+
+
+B200Engine = PdipmEngine

@@ -30,7 +30,8 @@ def _batch(*xs):
     return 1
 
 
-def lcp_solve_raw(Q, p, G, h, A, b, F, nineq_w=None, eps=1e-12, not_improved_lim=3, max_iter=20, check_spd=True):
+def lcp_solve_raw(Q, p, G, h, A, b, F, nineq_w=None, eps=1e-12, not_improved_lim=3, max_iter=20, check_spd=True,
+                  nineq_smem=0):
     """Launch the forward kernel on contiguous f64 CUDA tensors; returns (x, nu, lam, s, status, iters)."""
     L = _lib.lib()
     _lib.require_cuda(Q, p, G, h, F)
@@ -47,14 +48,15 @@ def lcp_solve_raw(Q, p, G, h, A, b, F, nineq_w=None, eps=1e-12, not_improved_lim
     ws = torch.empty(L.dsdf_lcp_workspace_bytes(B, nz, neq, ni) // 8 + 1, dtype=F64, device=dev)
     rc = L.dsdf_lcp_forward(_lib.ptr(Q), _lib.ptr(p), _lib.ptr(G), _lib.ptr(h),
                             _lib.ptr(A) if neq else None, _lib.ptr(b) if neq else None, _lib.ptr(F),
-                            _lib.ptr(nineq_w), B, nz, neq, ni, eps, not_improved_lim, max_iter, int(check_spd),
+                            _lib.ptr(nineq_w), B, nz, neq, ni, int(nineq_smem), eps, not_improved_lim, max_iter,
+                            int(check_spd),
                             _lib.ptr(x), _lib.ptr(nu), _lib.ptr(lam), _lib.ptr(s), _lib.ptr(status), _lib.ptr(iters),
                             _lib.ptr(ws), _lib.stream())
     _lib.check(rc, 'dsdf_lcp_forward')
     return x, nu, lam, s, status, iters
 
 
-def lcp_backward_raw(Q, G, A, F, x, nu, lam, s, gz, nineq_w=None, need=(True,) * 7):
+def lcp_backward_raw(Q, G, A, F, x, nu, lam, s, gz, nineq_w=None, need=(True,) * 7, nineq_smem=0):
     L = _lib.lib()
     B, nz = x.shape
     ni = G.shape[1]
@@ -68,7 +70,7 @@ def lcp_backward_raw(Q, G, A, F, x, nu, lam, s, gz, nineq_w=None, need=(True,) *
     ws = torch.empty(L.dsdf_lcp_workspace_bytes(B, nz, neq, ni) // 8 + 1, dtype=F64, device=dev)
     rc = L.dsdf_lcp_backward(_lib.ptr(Q), _lib.ptr(G), _lib.ptr(A) if neq else None, _lib.ptr(F), _lib.ptr(nineq_w),
                              _lib.ptr(x), _lib.ptr(nu), _lib.ptr(lam), _lib.ptr(s), _lib.ptr(gz.contiguous()),
-                             B, nz, neq, ni, _lib.ptr(dQ), _lib.ptr(dp), _lib.ptr(dG), _lib.ptr(dh), _lib.ptr(dA),
+                             B, nz, neq, ni, int(nineq_smem), _lib.ptr(dQ), _lib.ptr(dp), _lib.ptr(dG), _lib.ptr(dh), _lib.ptr(dA),
                              _lib.ptr(db), _lib.ptr(dF), _lib.ptr(status), _lib.ptr(ws), _lib.stream())
     _lib.check(rc, 'dsdf_lcp_backward')
     return dQ, dp, dG, dh, dA, db, dF

@@ -99,3 +99,20 @@ def cylinder_mesh(rad, height, numsegs=32, max_tri_length=0.1):
              np.stack([np.full(numsegs, top_c), idx[:-1, -1], idx[1:, -1]], 1),
              np.stack([np.full(numsegs, bot_c), idx[1:, 0], idx[:-1, 0]], 1)]
     return verts, np.concatenate(faces).astype(np.int32)
+
+
+def mesh_inertia(verts, faces):
+    """Unit-mass inertia tensor about the body origin of a closed, outward-wound triangle mesh.
+
+    Same quantity the reference integrates with Mirtich-style projection integrals
+    (sdf_physics/physics3d/bodies.py:260-395); computed here by signed-tetrahedron decomposition.
+    """
+    v = np.asarray(verts, dtype=np.float64)
+    f = np.asarray(faces)
+    a, b, c = v[f[:, 0]], v[f[:, 1]], v[f[:, 2]]
+    det = np.einsum('ij,ij->i', a, np.cross(b, c))
+    vol = det.sum() / 6.0
+    canon = (np.ones((3, 3)) + np.eye(3)) / 120.0
+    A = np.stack([a, b, c], axis=2)                       # columns a,b,c
+    C = np.einsum('f,fij,jk,flk->il', det, A, canon, A)
+    return (np.trace(C) * np.eye(3) - C) / vol

@@ -32,6 +32,69 @@ def scene(bodies, *, no_contact=(), axis_locks=(), dt=1.0 / 30, eps=EPS, tol=1e-
                 time_of_contact_diff=time_of_contact_diff, steps=steps)
 
 
+def make_bodies(spec, device=None, params=None, W=1):
+    """Instantiate the product's bodies for a spec.  ``params`` may override, for the LAST body, 'mass' (W,),
+    'pos' (W,3|7), 'vel' (W,6), 'push' (W,2) and, for all bodies, 'fric_coeff' (W,) -- mirroring how the
+    reference experiments parametrise their scenes (optim_sysid.py:105-131).  Returns (bodies, constraints)."""
+    import torch
+    from . import bodies as B, constraints as C, forces as Fo, meshes
+    params = params or {}
+    out, cons = [], []
+    n = len(spec['bodies'])
+    for i, b in enumerate(spec['bodies']):
+        last = i == n - 1
+        kw = dict(vel=params['vel'] if (last and 'vel' in params) else b['vel'],
+                  mass=params['mass'] if (last and 'mass' in params) else b['mass'],
+                  restitution=b['restitution'],
+                  fric_coeff=params['fric_coeff'] if 'fric_coeff' in params else b['fric_coeff'], device=device)
+        pos = params['pos'] if (last and 'pos' in params) else b['pos']
+        k = b['kind']
+        if k == 'box':
+            ob = B.SDFBox(pos, b['dims'], max_tri_length=b['max_tri_length'], **kw)
+        elif k == 'sphere':
+            ob = B.SDFSphere(pos, b['rad'], subdivisions=(b['mesh'] or {}).get('subdivisions', 4), **kw)
+        elif k == 'cylinder':
+            ob = B.SDFCylinder(pos, b['rad'], b['height'], max_tri_length=b['max_tri_length'], **kw)
+        elif k == 'grid':
+            g = b['grid']
+            grid = baked_grid(g['res'], g['kind'], g.get('seed', 0)) if isinstance(g, dict) else g
+            m = b['mesh']
+            r = m['radius']
+            ob = B.SDFGrid3D(pos, b['scale'], grid, meshes.icosphere(r, m.get('subdivisions', 3)),
+                             inertia=(2 / 5 * r ** 2 * np.eye(3)), **kw)
+        else:
+            raise ValueError(k)
+        if b['gravity']:
+            ob.add_force(Fo.Gravity3D())
+        if b['ext_force'] is not None:
+            f = torch.tensor(b['ext_force'], dtype=torch.float64, device=ob.p.device)
+            if last and 'push' in params:
+                push = params['push']
+                z = push.new_zeros(push.shape[0])
+                f = torch.stack([z, z, z, push[:, 0], z + float(b['ext_force'][4]), push[:, 1]], 1)
+            ob.add_force(Fo.ExternalForce3D(Fo.constant_force(f, b['ext_until']), multiplier=1.0))
+        out.append(ob)
+        if b['pinned']:
+            cons.append(C.TotalConstraint3D(ob))
+    for i, j in spec['no_contact']:
+        out[i].add_no_contact(out[j])
+    axis_cls = {3: C.XConstraint, 4: C.YConstraint, 5: C.ZConstraint}
+    for i, a in spec['axis_locks']:
+        cons.append(axis_cls[a](out[i]))
+    return out, cons
+
+
+def build_world(spec, device=None, params=None, **world_kw):
+    """World3D for a spec (batched when any parameter carries a leading world dimension)."""
+    from .world import World3D
+    bodies, cons = make_bodies(spec, device, params)
+    kw = dict(dt=spec['dt'], eps=spec['eps'], tol=spec['tol'], fric_dirs=spec['fric_dirs'],
+              strict_no_penetration=spec['strict_no_penetration'],
+              time_of_contact_diff=spec['time_of_contact_diff'])
+    kw.update(world_kw)
+    return World3D(bodies, cons, **kw)
+
+
 def box_on_plane(floor=(20.0, 1.0, 20.0), box=(1.0, 1.0, 1.0), mass=1.0, fric=0.2, push=(3.0, 2.0),
                  restitution=0.5, tilt=0.0, gap=2 * EPS, steps=30, toc=True, floor_tri=0.1):
     """Box resting ``gap`` above a pinned floor slab, pushed along x,z (system-identification shape)."""

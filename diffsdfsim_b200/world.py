@@ -1,0 +1,381 @@
+"""``World3D`` -- drop-in for sdf_physics.physics3d.world.World3D, stepping W independent worlds at once.
+
+Constructor and ``step`` signatures follow the reference (sdf_physics/physics3d/world.py:33-46,
+lcp_physics/physics/world.py:43-139, 241-379).  Each world runs the reference's per-world state machine
+(solve -> move -> find_contacts -> accept | halve dt and retry | give up below dt/2^10 when not strict;
+after a short accepted sub-step the remaining time is taken next; time-of-contact differential on first
+touch), expressed with per-world masks: one "round" = one attempt of every still-active world.
+All arithmetic of the round runs in the CUDA kernels (engines.py, contacts.py, ops.py); this file only
+routes tensors and merges accepted/rejected worlds with ``torch.where``.
+"""
+import torch
+
+from . import contacts as contacts_module
+from . import engines as engines_module
+from . import ops
+from .contacts import ContactDetector, GeometryTable, differentiable_geometry
+from .transforms import quaternion_to_matrix, so3_exponential_map
+from .utils import Defaults3D, default_device, get_instance
+
+F64 = torch.float64
+BASE_TOL = 1e-6      # lcp_physics/physics/utils.py:43 -- the TOL read by World.H.backward (world.py:204)
+
+
+class WorldState:
+    """SoA over worlds: p (W,nb,7), v (W,nb,6), mass (W,nb), Ibody (W,nb,3,3), fric (W,nb), rest (W,nb)."""
+    __slots__ = ('p', 'v', 'mass', 'Ibody', 'fric', 'rest')
+
+
+class TimeOfContact(torch.autograd.Function):
+    """World.H (lcp_physics/physics/world.py:141-237), all worlds at once.
+
+    Forward: identity on dt.  Backward: dL/dtheta = -(dD/dh)^+ dD/dtheta dL/dh per world over its new contacts,
+    with D the gap function of world.py:151-171.  Every contact's D depends only on its own rows, so the
+    Jacobians the reference takes with autograd.functional.jacobian are the per-row gradients of sum(D).
+    """
+
+    @staticmethod
+    def gap(h, c1, c2, v1, v2, x1, x2, R1, R2, n2, a1, a2):
+        hh = h[..., None]
+        Rih = so3_exponential_map(hh * v1[..., :3]) @ R1
+        Rjh = so3_exponential_map(hh * v2[..., :3]) @ R2
+        xi = x1 + hh * v1[..., 3:] + 0.5 * a1[..., 3:] * hh * hh
+        xj = x2 + hh * v2[..., 3:] + 0.5 * a2[..., 3:] * hh * hh
+        ci_w = (Rih @ c1[..., None])[..., 0] + xi
+        ci_j = (Rjh.transpose(-1, -2) @ (ci_w - xj)[..., None])[..., 0]
+        return (n2 * (c2 - ci_j)).sum(-1)
+
+    @staticmethod
+    def forward(ctx, h, mask, *args):
+        ctx.save_for_backward(h, mask, *args)
+        return h.clone()
+
+    @staticmethod
+    def backward(ctx, gh):
+        h, mask, *args = ctx.saved_tensors
+        C = mask.shape[1]
+        with torch.enable_grad():
+            hk = h.detach()[:, None].expand(-1, C).clone().requires_grad_(True)
+            ins = [a.detach().clone().requires_grad_(True) for a in args]
+            D = TimeOfContact.gap(hk, *ins)
+            grads = torch.autograd.grad((D * mask).sum(), [hk] + ins)
+        dD_dh = grads[0] * mask
+        dD_dh = torch.where(dD_dh < BASE_TOL / h.detach()[:, None], torch.zeros_like(dD_dh), dD_dh)
+        den = (dD_dh ** 2).sum(1, keepdim=True)
+        inv = torch.where(den > 1e-5, dD_dh / torch.where(den > 1e-5, den, torch.ones_like(den)), torch.zeros_like(dD_dh))
+        outs = [gh, None]
+        for g in grads[1:]:
+            wgt = (-inv * gh[:, None]).reshape(inv.shape + (1,) * (g.dim() - 2))
+            outs.append(wgt * g)
+        return tuple(outs)
+
+
+class World3D:
+    def __init__(self, bodies, constraints=[], dt=Defaults3D.DT, engine=Defaults3D.ENGINE,
+                 contact_callback=Defaults3D.CONTACT, eps=Defaults3D.EPSILON, tol=Defaults3D.TOL,
+                 fric_dirs=Defaults3D.FRIC_DIRS, post_stab=Defaults3D.POST_STABILIZATION,
+                 strict_no_penetration=True, time_of_contact_diff=True, stop_contact_grad=False,
+                 stop_friction_grad=False, detach_contact_b2=False, device=None, capK=768, maxc=16,
+                 record_prefilter=False):
+        if post_stab:
+            raise NotImplementedError('post_stab (off by default in the reference) is not built yet')
+        self.engine = get_instance(engines_module, engine)
+        self.contact_callback = get_instance(contacts_module, contact_callback)
+        self.device = torch.device(device) if device is not None else default_device()
+        self.bodies = list(bodies)
+        self.nb = len(self.bodies)
+        self.W = max(b.batch() for b in self.bodies)
+        self.batched = self.W > 1
+        self.vec_len = 6
+        self.dt, self.eps, self.tol, self.fric_dirs = dt, eps, tol, fric_dirs
+        self.strict_no_pen = strict_no_penetration
+        self.time_of_contact_diff = time_of_contact_diff
+        self.stop_contact_grad, self.stop_friction_grad = stop_contact_grad, stop_friction_grad
+        self.detach_contact_b2 = detach_contact_b2
+        self.maxc = maxc
+        W, nb, dev = self.W, self.nb, self.device
+        for i, b in enumerate(self.bodies):
+            b._world, b._index = self, i
+
+        def ex(t, *shape):
+            return t.to(dev).expand(W, *shape)
+
+        st = self.state = WorldState()
+        st.p = torch.stack([ex(b.p, 7) for b in self.bodies], 1).contiguous()
+        st.v = torch.stack([ex(b.v, 6) for b in self.bodies], 1).contiguous()
+        st.mass = torch.stack([ex(b.mass) for b in self.bodies], 1).contiguous()
+        st.Ibody = torch.stack([ex(b.ang_inertia, 3, 3) for b in self.bodies], 1).contiguous()
+        st.fric = torch.stack([ex(b.fric_coeff) for b in self.bodies], 1).contiguous()
+        st.rest = torch.stack([ex(b.restitution) for b in self.bodies], 1).contiguous()
+        self.shape = torch.stack([ex(b.shape_rows(), 4) for b in self.bodies], 1).contiguous().detach()
+        self.body_eps = float(self.bodies[0].eps)
+
+        # equality rows: constant 0/1 selections (constraints.py)
+        self.joints = []
+        rows = []
+        for j in constraints:
+            i1 = self.bodies.index(j.body1)
+            self.joints.append((j, i1, None))
+            rows += [(i1, a) for a in j.rows()]
+        self.num_constraints = len(rows)
+        nz = 6 * nb
+        A = torch.zeros(len(rows), nz, dtype=F64)
+        for r, (i, a) in enumerate(rows):
+            A[r, 6 * i + a] = 1
+        self.A = A.to(dev).unsqueeze(0).expand(W, -1, -1).contiguous() if rows else None
+        self.b = torch.zeros(W, len(rows), dtype=F64, device=dev) if rows else None
+
+        # contact detection set-up (replaces the py3ode HashSpace of world.py:69-72)
+        self.table = GeometryTable(self.bodies, W, dev)
+        self.pairs = [(i, j) for i in range(nb) for j in range(i + 1, nb)
+                      if self.bodies[j] not in self.bodies[i].no_contact]
+        self.detector = ContactDetector(self.table, self.pairs, W, nb, dev, capK=capK, maxc=maxc,
+                                        record_prefilter=record_prefilter)
+
+        self.t = torch.zeros(W, dtype=F64, device=dev)
+        self.t_host = 0.0
+        self.last_dt = torch.zeros(W, dtype=F64, device=dev)
+        self.toc_flag = torch.zeros(W, dtype=torch.bool, device=dev)
+        self.trajectory, self.observations = [], []
+        self.stats = {'rounds': [], 'attempts': torch.zeros(W, dtype=torch.int64, device=dev)}
+        self.static_inverse = False
+        self.contact_set = self.detector.new_set()
+        self.contact_geo = None
+        self.find_contacts()
+        if self.strict_no_pen:
+            assert not bool(((self.contact_set.status & 8) != 0).any()), \
+                'Interpenetration at start:\n{}'.format(self.contacts_of(0))
+        self._check_capacity(self.contact_set)
+
+    # ------------------------------------------------------------------ reference-style accessors
+    @property
+    def v(self):
+        v = self.state.v.reshape(self.W, -1)
+        return v if self.batched else v[0]
+
+    def get_v(self):
+        return self.v
+
+    def set_v(self, new_v):
+        self.state.v = new_v.reshape(self.W, self.nb, 6).to(self.device)
+        self._sync_bodies()
+
+    def get_p(self):
+        p = self.state.p.reshape(self.W, -1)
+        return p if self.batched else p[0]
+
+    def set_p(self, new_p):
+        self.state.p = new_p.reshape(self.W, self.nb, 7).to(self.device)
+        self._sync_bodies()
+
+    def _body_pose_changed(self, i):
+        B = self.bodies[i]
+        p = self.state.p.clone()
+        p[:, i] = B.p.to(self.device).expand(self.W, 7)
+        self.state.p = p
+
+    def _sync_bodies(self):
+        for i, b in enumerate(self.bodies):
+            b.p, b.v = self.state.p[:, i], self.state.v[:, i]
+
+    def apply_forces(self, t):
+        """(W,nb,6) generalized forces; t is the step start time (host float) -- see forces.py."""
+        fs = []
+        for b in self.bodies:
+            if not b.forces:
+                fs.append(torch.zeros(self.W, 6, dtype=F64, device=self.device))
+                continue
+            tot = 0
+            for f in b.forces:
+                tt = self.t if getattr(f, 'vectorized', False) else self.t_host
+                tot = tot + f.force(tt).to(self.device)
+            fs.append(tot.expand(self.W, 6))
+        return torch.stack(fs, 1).contiguous()
+
+    def M(self):
+        """Block-diagonal world-frame mass matrix (physics3d/world.py:48-50) from the assembly kernel: (W,nz,nz)."""
+        Q = self.lcp_matrices()[0]
+        return Q if self.batched else Q[0]
+
+    def Je(self):
+        if self.A is None:
+            return torch.zeros(0, 6 * self.nb, dtype=F64, device=self.device)
+        return self.A if self.batched else self.A[0]
+
+    def lcp_matrices(self, dt=None):
+        """(Q, p, G, h, A, b, F, nineq_w) exactly as handed to the LCP kernel (engines.py:56-79 layout)."""
+        from . import _lib
+        st = self.state
+        dtt = self._dt_tensor(self.dt if dt is None else dt)
+        f = self.apply_forces(self.t)
+        Q, pv, G, h, Fm, nin = engines_module._assemble(
+            _lib.lib(), st.p.detach().contiguous(), st.v.detach().contiguous(), st.mass.detach().contiguous(),
+            st.Ibody.detach().contiguous(), st.fric.detach().contiguous(), st.rest.detach().contiguous(),
+            f.detach().contiguous(), dtt, None, self.contact_set.count, self.contact_set.body,
+            self.contact_geo.detach().contiguous(), self.fric_dirs)
+        return Q, pv, G, h, self.A, self.b, Fm, nin
+
+    def contacts_of(self, w=0):
+        """Reference-format contact list of world w: [((normal, p1, p2, pen), i1, i2), ...] (contacts.py:266-270)."""
+        n = int(self.contact_set.count[w])
+        g, bd = self.contact_geo[w], self.contact_set.body[w]
+        return [((g[k, 0:3], g[k, 3:6], g[k, 6:9], g[k, 9]), int(bd[k, 0]), int(bd[k, 1])) for k in range(n)]
+
+    @property
+    def contacts(self):
+        return self.contacts_of(0) if not self.batched else [self.contacts_of(w) for w in range(self.W)]
+
+    def _dt_tensor(self, dt):
+        if isinstance(dt, torch.Tensor):
+            return dt.to(self.device).expand(self.W).contiguous() if dt.dim() <= 1 else dt
+        return torch.full((self.W,), float(dt), dtype=F64, device=self.device)
+
+    def _check_capacity(self, cs):
+        st = cs.status
+        bad = int((st & 1).max().item()) | (int(((st & 2) != 0).logical_and((st & 8) == 0).any().item()) << 1)
+        if bad & 1:
+            raise RuntimeError('contact candidate capacity exceeded: raise capK')
+        if bad & 2:
+            raise RuntimeError('contact capacity exceeded on an accepted state: raise maxc')
+
+    # ------------------------------------------------------------------ contact detection
+    def find_contacts(self, active=None):
+        """world.py:396-399 for all (active) worlds; keeps the geometry attached to the pose graph."""
+        cs = self.contact_set.clone() if active is not None else self.detector.new_set()
+        self.detector.detect(self.state.p.detach().contiguous(), self.shape, cs, active, eps=self.eps, tol=self.tol,
+                             fd_eps=Defaults3D.EPSILON, body_eps=self.body_eps, detach_b2=self.detach_contact_b2)
+        self.contact_set = cs
+        self.max_nc = int(cs.count.max())
+        self.contact_geo = differentiable_geometry(self.state.p, self.shape, cs, self.table, Defaults3D.EPSILON,
+                                                   self.detach_contact_b2)
+        return cs
+
+    # ------------------------------------------------------------------ stepping
+    def step(self, fixed_dt=False):
+        """world.py:119-139.  Returns had_contacts: python bool for a single world, (W,) bool tensor otherwise."""
+        st = self.state
+        self._undo = (st.p, st.v, self.contact_set, self.contact_geo, self.t.clone(), self.t_host, self.toc_flag.clone(),
+                      self.last_dt, len(self.trajectory))
+        W, dev = self.W, self.device
+        end_t = self.t + self.dt
+        dt_try = torch.full((W,), float(self.dt), dtype=F64, device=dev)
+        active = torch.ones(W, dtype=torch.bool, device=dev)
+        had = torch.zeros(W, dtype=torch.bool, device=dev)
+        rounds = 0
+        while True:
+            rounds += 1
+            accept = self._attempt(active, dt_try)
+            self.stats['attempts'] += active.long()
+            had |= accept & (self.contact_set.count > 0)
+            # rejected worlds retry with half the step (world.py:348); accepted ones take the remaining time
+            dt_try = torch.where(active & ~accept, dt_try / 2, dt_try)
+            if fixed_dt:
+                more = accept & (self.t < end_t)
+                dt_try = torch.where(more, end_t - self.t, dt_try)
+                active = (active & ~accept) | more
+            else:
+                active = active & ~accept
+            if not bool(active.any()):
+                break
+        self.stats['rounds'].append(rounds)
+        self.t_host += self.dt
+        self._sync_bodies()
+        self.trajectory.append((self.t.clone() if self.batched else float(self.t[0]), self.get_p(), self.v,
+                                self.contact_set, None))
+        return had if self.batched else bool(had[0])
+
+    def undo_step(self):
+        """world.py:106-116."""
+        st = self.state
+        (st.p, st.v, self.contact_set, self.contact_geo, self.t, self.t_host, self.toc_flag, self.last_dt, ntraj) = self._undo
+        del self.trajectory[ntraj:]
+        self._sync_bodies()
+
+    def _attempt(self, active, dt_try):
+        """One solve -> move -> find_contacts attempt of every active world (body of world.py:249-356)."""
+        st = self.state
+        W, nb = self.W, self.nb
+        act8 = active.to(torch.uint8).contiguous()
+        dt_ = dt_try
+        if self.time_of_contact_diff:
+            # world.py:253-257: value == dt_try, carries -d last_dt
+            dt_ = torch.where(self.toc_flag, -self.last_dt + (self.last_dt.detach() + dt_try), dt_try)
+        new_v = self.engine.solve_dynamics(self, dt_.contiguous(), act8)
+        p_try = ops.integrate(st.p, new_v, dt_.contiguous(), act8)
+        cs = self.contact_set.clone()
+        self.detector.detect(p_try.detach().contiguous(), self.shape, cs, act8, eps=self.eps, tol=self.tol,
+                             fd_eps=Defaults3D.EPSILON, body_eps=self.body_eps, detach_b2=self.detach_contact_b2)
+        geo = differentiable_geometry(p_try, self.shape, cs, self.table, Defaults3D.EPSILON, self.detach_contact_b2)
+        pen_bad = (cs.status & 8) != 0
+        clean = active & ~pen_bad
+        accept = clean
+        if not self.strict_no_pen:
+            accept = clean | (active & (dt_try < self.dt / 2 ** 10))         # world.py:345-347 (give up, keep going)
+        self._check_capacity_masked(cs, accept)
+
+        # contacts between body pairs that had no contact at the start of the sub-step (world.py:273-274)
+        kk = torch.arange(self.maxc, device=self.device)[None, :]
+        new_valid = kk < cs.count[:, None]
+        old_valid = kk < self.contact_set.count[:, None]
+        bn, bo = cs.body.long(), self.contact_set.body.long()
+        pid_new = torch.minimum(bn[..., 0], bn[..., 1]) * nb + torch.maximum(bn[..., 0], bn[..., 1])
+        pid_old = torch.minimum(bo[..., 0], bo[..., 1]) * nb + torch.maximum(bo[..., 0], bo[..., 1])
+        seen = ((pid_new[:, :, None] == pid_old[:, None, :]) & old_valid[:, None, :]).any(2)
+        toc_mask = new_valid & ~seen & clean[:, None]
+        toc_now = toc_mask.any(1)
+        if self.time_of_contact_diff and bool(toc_now.any()):
+            dt_h = self._time_of_contact(dt_, p_try, new_v, geo, cs, toc_mask)
+            p_redo = ops.integrate(st.p, new_v, dt_h.contiguous(), toc_now.to(torch.uint8).contiguous())
+            p_try = torch.where(toc_now[:, None, None], p_redo, p_try)
+            self.last_dt = torch.where(toc_now, dt_h, self.last_dt)
+        self.toc_flag = torch.where(clean, toc_now, self.toc_flag)    # a give-up accept leaves toc_contacts untouched
+
+        # commit accepted worlds
+        a3 = accept[:, None, None]
+        st.p = torch.where(a3, p_try, st.p)
+        st.v = torch.where(a3, new_v, st.v)
+        old = self.contact_set
+        for k in ('count', 'status'):
+            setattr(cs, k, torch.where(accept, getattr(cs, k), getattr(old, k)))
+        cs.body = torch.where(a3, cs.body, old.body)
+        cs.face = torch.where(accept[:, None], cs.face, old.face)
+        cs.abc = torch.where(a3, cs.abc, old.abc)
+        cs.geo = torch.where(a3, cs.geo, old.geo)
+        self.contact_geo = torch.where(a3, geo, self.contact_geo)
+        self.contact_set = cs
+        self.max_nc = int(cs.count.max())          # sizes the LCP kernel's shared memory for the next solve
+        self.t = torch.where(accept, self.t + dt_try, self.t)
+        return accept
+
+    def _check_capacity_masked(self, cs, accept):
+        st = cs.status
+        bad = ((st & 1) != 0).any() | (((st & 2) != 0) & accept).any()
+        if bool(bad):
+            raise RuntimeError('contact capacity exceeded (capK=%d, maxc=%d): raise World3D(capK=..., maxc=...)'
+                               % (self.detector.capK, self.maxc))
+
+    def _time_of_contact(self, dt_, p_try, new_v, geo, cs, toc_mask):
+        """Gather of world.py:275-327 for all worlds (padded to maxc) + the H function."""
+        st = self.state
+        W, C = self.W, self.maxc
+        i1 = cs.body[..., 0].long().clamp(0, self.nb - 1)
+        i2 = cs.body[..., 1].long().clamp(0, self.nb - 1)
+
+        def per_contact(x, idx):
+            return torch.gather(x, 1, idx[..., None].expand(W, C, x.shape[-1]))
+
+        v1, v2 = per_contact(new_v, i1), per_contact(new_v, i2)
+        pp1, pp2 = per_contact(p_try, i1), per_contact(p_try, i2)
+        f = self.apply_forces(self.t)
+        acc = f / st.mass[..., None]
+        a1, a2 = per_contact(acc, i1), per_contact(acc, i2)
+        h = dt_[:, None, None]
+        x1 = pp1[..., 4:] - h * v1[..., 3:]
+        x2 = pp2[..., 4:] - h * v2[..., 3:]
+        R1 = so3_exponential_map(-h * v1[..., :3]) @ quaternion_to_matrix(pp1[..., :4])
+        R2 = so3_exponential_map(-h * v2[..., :3]) @ quaternion_to_matrix(pp2[..., :4])
+        n, c1, c2 = geo[..., 0:3], geo[..., 3:6], geo[..., 6:9]
+        c1 = (R1.transpose(-1, -2) @ c1[..., None])[..., 0]
+        c2 = (R2.transpose(-1, -2) @ c2[..., None])[..., 0]
+        n2 = (R2.transpose(-1, -2) @ n[..., None])[..., 0]
+        return TimeOfContact.apply(dt_, toc_mask.to(F64), c1, c2, v1, v2, x1, x2, R1, R2, n2, a1, a2)

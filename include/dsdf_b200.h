@@ -31,6 +31,7 @@ extern "C" {
 #define DSDF_LCP_Q_NOT_SPD    2   /* SPD check failed                    (lcp.py:109-113)   */
 #define DSDF_LCP_FACTOR_FAIL  4   /* LU of R + D^-1 hit a zero pivot -> best iterate returned (batch.py:134-137) */
 #define DSDF_LCP_INACCURATE   8   /* best residual > 1                   (batch.py:165,229) */
+#define DSDF_LCP_TOO_LARGE   16   /* nineq_w[w] > nineq_smem: not solved (x = NaN)                  */
 
 /* SDF kinds */
 #define DSDF_SDF_BOX      0
@@ -52,6 +53,9 @@ int dsdf_version(void);
  * number of ACTIVE inequality rows of each world (rows/cols beyond it ignored).
  * Outputs: x (W,nz) nu (W,neq) lam (W,nineq) s (W,nineq) = best-residual
  * iterate; status (W) bit mask; iters (W) iterations run.
+ * nineq_smem (0 = nineq): rows the launch sizes its shared memory for; lets a batch be padded to a large
+ * capacity `nineq` (global strides) while the CTA only holds max_w nineq_w[w] rows.  A world with more active
+ * rows gets status DSDF_LCP_TOO_LARGE.
  * ws: workspace of dsdf_lcp_workspace_bytes(...) bytes.
  * Every reduction the reference takes over the whole batch tensor is taken per
  * world here (the reference engine only ever runs nBatch = 1).
@@ -60,7 +64,7 @@ size_t dsdf_lcp_workspace_bytes(int W, int nz, int neq, int nineq);
 size_t dsdf_lcp_smem_bytes(int nz, int neq, int nineq);   /* > 227 KiB: problem too large for this kernel */
 int dsdf_lcp_forward(const double* Q, const double* p, const double* G, const double* h,
                      const double* A, const double* b, const double* F, const int32_t* nineq_w,
-                     int W, int nz, int neq, int nineq,
+                     int W, int nz, int neq, int nineq, int nineq_smem,
                      double eps, int not_improved_lim, int max_iter, int check_spd,
                      double* x, double* nu, double* lam, double* s,
                      int32_t* status, int32_t* iters, void* ws, void* stream);
@@ -71,7 +75,7 @@ int dsdf_lcp_forward(const double* Q, const double* p, const double* G, const do
  */
 int dsdf_lcp_backward(const double* Q, const double* G, const double* A, const double* F,
                       const int32_t* nineq_w, const double* x, const double* nu, const double* lam,
-                      const double* s, const double* gz, int W, int nz, int neq, int nineq,
+                      const double* s, const double* gz, int W, int nz, int neq, int nineq, int nineq_smem,
                       double* dQ, double* dp, double* dG, double* dh, double* dA, double* db, double* dF,
                       int32_t* status, void* ws, void* stream);
 
@@ -102,6 +106,84 @@ int dsdf_integrate(const double* p, const double* v, const double* dt, const uns
 /* gp (W,nb,7), gv (W,nb,6), gdt (W,nb) [per body; caller sums over bodies] from gp_out (W,nb,7). */
 int dsdf_integrate_backward(const double* p, const double* v, const double* dt, const unsigned char* active, int W,
                             int nb, const double* gp_out, double* gp, double* gv, double* gdt, void* stream);
+
+/* ------------------------------------------------------ SDF collision query ----
+ * Per-body geometry handed to the contact kernels.  Meshes and grids are INPUTS of the hot path
+ * (the reference meshes bodies at construction time: bodies.py:638, 652-712).
+ */
+typedef struct dsdf_body_geom {
+    int32_t kind, nverts, nfaces, res;
+    const double* verts;          /* (nverts,3) body frame; world w at verts + w*vert_world_stride (0 = shared) */
+    const int32_t* faces;         /* (nfaces,3), shared by all worlds */
+    const double* grid;           /* res^3 SDF samples on [-1,1]^3 (kind == GRID); world w at grid + w*grid_world_stride */
+    long long vert_world_stride, grid_world_stride;
+} dsdf_body_geom;
+
+/* per-world contact status bits (int32) */
+#define DSDF_CON_CAND_OVERFLOW  1   /* more centroid candidates than capK in some direction */
+#define DSDF_CON_OVERFLOW       2   /* more contacts than maxc */
+#define DSDF_CON_HULL3D         4   /* a non-planar normal cluster of > 4 points was kept unfiltered */
+#define DSDF_CON_PENETRATION    8   /* some pen > tol: the step attempt will be rejected (world.py:270) */
+
+/* Replaces World.find_contacts (lcp_physics/physics/world.py:396-399) with FWContactHandler
+ * (sdf_physics/physics3d/contacts.py:221-272): broad phase (AABB of each body's rotated cube of half side
+ * scale+body_eps, pairs (i<j) from `pairs` (npairs,2), no_contact pairs already removed), _overlap (:27-36),
+ * _frank_wolfe (:39-94), _compute_contacts (:161-214), _filter_contacts (:97-158), both search directions with the
+ * reference's "reverse only if the first is valid" rule (:238-240).
+ * p (W,nb,7), shape (W,nb,4), active (W) uint8 or NULL (inactive worlds keep their previous outputs).
+ * chunk_prefix (2*npairs+1): candidate-kernel CTA offsets per search direction, chunk count of direction d =
+ *   dsdf_contact_chunks_per_face_count(nfaces of the mesh body of d); total_chunks = chunk_prefix[2*npairs].
+ * Outputs (capacity maxc contacts per world, ordered pair -> direction -> face id):
+ *   count (W); cbody (W,maxc,2) = (mesh body, sdf body); cface (W,maxc) face id on the mesh body;
+ *   cabc (W,maxc,3) barycentrics; cgeo (W,maxc,10) = [normal(3), p1(3), p2(3), pen]; wstatus (W).
+ *   pre_ids (W,2*npairs,capK) / pre_cnt (W,2*npairs): PRE-filter contact face ids per direction (parity
+ *   evidence; -1 = direction not searched); both may be NULL.
+ */
+size_t dsdf_contacts_workspace_bytes(int W, int npairs, int capK);
+int dsdf_contact_chunks_per_face_count(int nfaces);
+int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, const int32_t* chunk_prefix, int total_chunks,
+                         int npairs, const double* p, const double* shape, const unsigned char* active,
+                         int W, int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
+                         int capK, int maxc, int32_t* count, int32_t* cbody, int32_t* cface, double* cabc, double* cgeo,
+                         int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, void* ws, void* stream);
+/* VJP of cgeo w.r.t. the poses (the reference's grad-enabled second _compute_contacts, contacts.py:262-264):
+ * gp (W,nb,7) from ggeo (W,maxc,10). */
+int dsdf_contact_geometry_backward(const dsdf_body_geom* geom, const double* p, const double* shape, int W, int nb,
+                                   double fd_eps, int detach_b2, int maxc, const int32_t* count, const int32_t* cbody,
+                                   const int32_t* cface, const double* cabc, const double* ggeo, double* gp, void* stream);
+
+/* ------------------------------------------------------------- dynamics ----
+ * Replaces the matrix assembly of PdipmEngine.solve_dynamics (lcp_physics/physics/engines.py:31-79) with
+ * World3D.M/Jc/Jf (sdf_physics/physics3d/world.py:48-101), orthogonal (physics3d/utils.py:247-256) and
+ * World.restitutions/mu/E (lcp_physics/physics/world.py:402-409, 480-501), for all worlds:
+ *   Q = blockdiag_b(R(q_b) I_b R(q_b)', m_b 1)      (W,nz,nz),  nz = 6 nb
+ *   pvec = Q v + dt f                                (W,nz)
+ *   G = [Jc; Jf; 0]   h = [e (Jc v); 0; 0]           (W,niCap,nz), (W,niCap),  niCap = maxc (2 + fric_dirs)
+ *   F  (E, mu, -E' blocks)                            (W,niCap,niCap)
+ *   nineq_w = nc (2 + fric_dirs), or -1 for inactive worlds (dsdf_lcp_* then skip them)
+ * Inputs: p (W,nb,7) v (W,nb,6) mass (W,nb) Ibody (W,nb,3,3) fric (W,nb) rest (W,nb) f (W,nb,6) dt (W)
+ * active (W) uint8|NULL, contacts count (W) cbody (W,maxc,2) cgeo (W,maxc,10).  fric_dirs in {4, 8}.
+ * The equality rows A (pinned bodies / axis locks) are constant and supplied by the caller to dsdf_lcp_*.
+ * new_v = -x of dsdf_lcp_forward (engines.py:81-82).
+ */
+int dsdf_dynamics_assemble(const double* p, const double* v, const double* mass, const double* Ibody,
+                           const double* fric, const double* rest, const double* f, const double* dt,
+                           const unsigned char* active, const int32_t* count, const int32_t* cbody, const double* cgeo,
+                           int W, int nb, int maxc, int fric_dirs,
+                           double* Q, double* pvec, double* G, double* h, double* F, int32_t* nineq_w, void* stream);
+/* Reverse mode of the assembly: contracts the LCP gradients (dQ, dp, dG, dh, dF of dsdf_lcp_backward) onto the
+ * physical inputs.  stop_contact_grad / stop_friction_grad detach the contact tuple in Jc / Jf
+ * (physics3d/world.py:59-62, 77-80).  Outputs: gp (W,nb,7) gv (W,nb,6) gmass (W,nb) gI (W,nb,3,3) gfric (W,nb)
+ * grest (W,nb) gf (W,nb,6) gdt (W) ggeo (W,maxc,10). */
+int dsdf_dynamics_assemble_backward(const double* p, const double* v, const double* mass, const double* Ibody,
+                                    const double* fric, const double* rest, const double* f, const double* dt,
+                                    const unsigned char* active, const int32_t* count, const int32_t* cbody,
+                                    const double* cgeo, int W, int nb, int maxc, int fric_dirs,
+                                    int stop_contact_grad, int stop_friction_grad,
+                                    const double* Q, const double* G,
+                                    const double* dQ, const double* dp, const double* dG, const double* dh, const double* dF,
+                                    double* gp, double* gv, double* gmass, double* gI, double* gfric, double* grest,
+                                    double* gf, double* gdt, double* ggeo, void* stream);
 
 #ifdef __cplusplus
 }

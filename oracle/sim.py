@@ -255,7 +255,9 @@ class TimeOfContact(torch.autograd.Function):
         with torch.enable_grad():
             jac = torch.autograd.functional.jacobian(TimeOfContact.gap, saved, strict=True)
         dD_dh = jac[0].clone()
-        dD_dh[dD_dh < DEFAULT_TOL / h] = 0.
+        # world.py:204 reads Defaults.TOL of the 2-D base module (lcp_physics/physics/utils.py:43 = 1e-6),
+        # not Defaults3D.TOL
+        dD_dh[dD_dh < 1e-6 / h] = 0.
         den = torch.sum(dD_dh ** 2, dim=0)
         w = dD_dh / den if den > 1e-5 else 0. * dD_dh
         outs = [gh]
@@ -316,6 +318,7 @@ class World:
         b1, b2 = self.bodies[i1], self.bodies[i2]
         with torch.no_grad():
             abc, ids = frank_wolfe(b1, b2, self.eps, self.tol)
+            self.last_prefilter.append((i1, i2, ids.clone()))
             n, p1, p2, pen = contact_geometry(b1, b2, abc, ids, detach_b2=self.detach_contact_b2)
             ok = bool(torch.all(pen <= self.tol))
             if ok:
@@ -333,6 +336,7 @@ class World:
         """world.py:396-399 + handler dispatch contacts.py:221-244."""
         self.contacts = []
         self.last_search = []
+        self.last_prefilter = []
         half = [b.aabb_half() for b in self.bodies]
         for i in range(self.nb):
             for j in range(i + 1, self.nb):
