@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""Benchmark of the differentiable stepping hot path: world-steps/s, forward + backward.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--worlds 4096] [--sim-steps 30]
+    torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[1], "system_identification shape"): W independent worlds per GPU, each a 1x1x1
+SDFBox (726 verts / 1200 faces) resting 2*eps above a pinned 20x1x20 floor slab (89 646 verts / 176 000 faces,
+shared mesh), gravity + a constant push, per-world mass / friction / push; one bench step = one optimisation
+iteration = `sim_steps` calls of World3D.step(fixed_dt=True) (with all their sub-steps) + loss.backward(),
+loss = sum ||pos||^2, gradients w.r.t. the per-world mass, friction and push.
+
+One JSON line on stdout (rank 0).  See the task contract for the keys; `roofline` describes the dominant kernel
+by measured time, `cpu_baseline` the oracle port timed on this host.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+METRIC = 'world-steps/sec fwd+bwd'
+UNIT = 'world-steps/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--worlds', type=int, default=4096, help='worlds per GPU')
+    ap.add_argument('--sim-steps', type=int, default=30)
+    ap.add_argument('--cpu-worlds', type=int, default=2, help='worlds of the bounded CPU sample')
+    ap.add_argument('--cpu-sim-steps', type=int, default=8)
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    return ap.parse_args()
+
+
+def measured_peaks():
+    try:
+        with open(os.path.join(ROOT, 'MEASURED_PEAKS.json')) as fh:
+            return json.load(fh), 'measured'
+    except Exception:
+        return {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0}, 'fallback'
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag = index, [], False
+
+    def run(self):
+        q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
+             'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap')
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                      '--format=csv,noheader,nounits'], capture_output=True, text=True, timeout=5).stdout
+                self.rows.append([c.strip() for c in out.strip().split(',')])
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
+        mx = [int(r[1]) for r in self.rows if len(r) > 1 and r[1].isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith('active')})
+        return {'sm_mhz': sm[len(sm) // 2] if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+def make_params(W, device, seed):
+    """Per-world parameters in PINNED host memory (the optimisation variables of the sysid experiment)."""
+    g = torch.Generator().manual_seed(seed)
+    host = {'mass': 0.9 + 0.2 * torch.rand(W, generator=g, dtype=torch.float64),
+            'fric_coeff': 0.01 + 0.24 * torch.rand(W, generator=g, dtype=torch.float64),
+            'push': 2.0 + 3.0 * torch.rand(W, 2, generator=g, dtype=torch.float64)}
+    if device.type == 'cuda':
+        host = {k: v.pin_memory() for k, v in host.items()}
+    return host
+
+
+def gpu_iteration(spec, params_dev, sim_steps, device):
+    """One optimisation iteration through the public API: build the world, roll out, backward."""
+    from diffsdfsim_b200 import scenes
+    leaves = {k: v.detach().requires_grad_(True) for k, v in params_dev.items()}
+    world = scenes.build_world(spec, device=device, params=leaves)
+    loss = 0.
+    for _ in range(sim_steps):
+        world.step(fixed_dt=True)
+        loss = loss + (world.bodies[-1].pos ** 2).sum()
+    loss.backward()
+    return loss.detach(), {k: v.grad for k, v in leaves.items()}, world
+
+
+def run_ours(args):
+    import torch.distributed as dist
+    from diffsdfsim_b200 import _lib, scenes
+    rank = int(os.environ.get('RANK', 0))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    world_size = int(os.environ.get('WORLD_SIZE', 1))
+    assert torch.cuda.is_available(), 'bench.py --impl ours needs a CUDA device (no CPU fallback)'
+    torch.cuda.set_device(local)
+    device = torch.device('cuda', local)
+    if world_size > 1:
+        dist.init_process_group('nccl', device_id=device)
+    _lib.lib()
+    W = args.worlds
+    spec = scenes.box_on_plane(steps=args.sim_steps)
+    host = make_params(W, device, seed=rank)
+    dev = {k: v.to(device) for k, v in host.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host.values())
+    out_host = {k: torch.empty_like(v).pin_memory() for k, v in host.items()}
+    loss_host = torch.empty(1, dtype=torch.float64).pin_memory()
+    d2h = h2d + 8
+
+    def allreduce(loss, grads):
+        # shared-parameter reduction of batched system identification: loss and the summed gradients
+        if world_size > 1:
+            buf = torch.stack([loss] + [g.sum() for g in grads.values()])
+            dist.all_reduce(buf)
+            return buf[0]
+        return loss
+
+    def barrier():
+        if world_size > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        loss, grads, world = gpu_iteration(spec, dev, args.sim_steps, device)
+        allreduce(loss, grads)
+    # ---- device-resident timing ("value") with per-entry-point CUDA events
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    barrier()
+    _lib.reset_counters(profile=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        loss, grads, world = gpu_iteration(spec, dev, args.sim_steps, device)
+        allreduce(loss, grads)
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    launches = _lib.kernel_launches()
+    prof = _lib.profile_summary()
+    attempts = float(world.stats['attempts'].double().mean()) / args.sim_steps
+    # ---- end-to-end timing: pinned host -> device inputs, device -> host loss and gradients, every step
+    _lib.reset_counters(profile=False)
+    barrier()
+    e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2.record()
+    for _ in range(args.steps):
+        devp = {k: v.to(device, non_blocking=True) for k, v in host.items()}
+        loss, grads, _ = gpu_iteration(spec, devp, args.sim_steps, device)
+        loss = allreduce(loss, grads)
+        loss_host.copy_(loss.reshape(1), non_blocking=True)
+        for k in grads:
+            out_host[k].copy_(grads[k], non_blocking=True)
+        torch.cuda.synchronize()
+    e3.record()
+    barrier()
+    ms_e2e = e2.elapsed_time(e3)
+    sampler.stop_flag = True
+    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
+    if world_size > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, ms_e2e = float(t[0]), float(t[1])
+    units = W * args.sim_steps * args.steps * world_size
+    if rank != 0:
+        return None
+    peaks, which = measured_peaks()
+    # dominant entry point by measured device time
+    top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else ('none', (1, 0.0))
+    roof = roofline(top[0], top[1], W, spec, peaks, which, attempts)
+    line = {
+        'metric': METRIC, 'value': units / (ms / 1e3), 'unit': UNIT, 'n_gpus': world_size, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+        'config': {'workload': 'box_on_plane sysid: %d worlds/GPU x %d World3D.step + backward; floor 176000 faces '
+                               '(shared), box 1200 faces; grads wrt per-world mass, friction, push' % (W, args.sim_steps),
+                   'worlds_per_gpu': W, 'sim_steps': args.sim_steps, 'attempts_per_world_step': attempts,
+                   'l2_policy': 'per-step working set (LCP matrices %.1f GB/step) exceeds L2' %
+                                (W * 160 * 160 * 8 / 1e9)},
+        'e2e': {'value': units / (ms_e2e / 1e3), 'unit': UNIT, 'h2d_bytes_per_step': h2d, 'd2h_bytes_per_step': d2h},
+        'gpu_launches': launches,
+        'clocks': sampler.summary(),
+        'roofline': roof,
+        'kernel_ms_per_step': {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+    }
+    return line
+
+
+def roofline(name, stat, W, spec, peaks, which, attempts):
+    """Algorithmic bytes per launch of the dominant entry point / its measured average duration."""
+    calls, total_ms = stat
+    avg_ms = total_ms / max(calls, 1)
+    nb, maxc, fd = 2, 16, 8
+    nz, ni = 6 * nb, maxc * (2 + fd)
+    if name.startswith('dsdf_lcp'):
+        # compulsory: read Q, p, G, h, A, F rows of the ACTIVE problem (~10 contacts) + write x, lam, s
+        nia = 100
+        per_world = 8 * (nz * nz + nz + nia * nz + nia + 6 * nz + nia * nia + nz + 2 * nia)
+    elif name == 'dsdf_contacts_detect':
+        # per world and search direction: poses + the candidate/contact lists; shared meshes count once per launch
+        per_world = 2 * 7 * 8 * 2 + 300 * 4 * 2 + 16 * (4 + 8 + 24 + 80)
+        shared = 176000 * 12 + 89646 * 24 + 1200 * 12 + 726 * 24
+        alg = per_world * W + shared
+        return {'kernel': name, 'bound': 'hbm', 'achieved': alg / 1e9 / (avg_ms / 1e3), 'peak': peaks['hbm_gbs'],
+                'unit': 'GB/s', 'frac': alg / 1e9 / (avg_ms / 1e3) / peaks['hbm_gbs'], 'traffic': None,
+                'peak_source': which, 'avg_launch_ms': avg_ms, 'algorithmic_bytes_per_launch': alg}
+    else:
+        per_world = 8 * (nz * nz + ni * nz)
+    alg = per_world * W
+    ach = alg / 1e9 / (avg_ms / 1e3)
+    return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s',
+            'frac': ach / peaks['hbm_gbs'], 'traffic': None, 'peak_source': which, 'avg_launch_ms': avg_ms,
+            'algorithmic_bytes_per_launch': alg}
+
+
+def cpu_sample(n_worlds, sim_steps, seed=0):
+    """The oracle port (oracle/, CPU float64, one world at a time like the reference) on a bounded sample."""
+    from oracle.scenes import build as build_oracle
+    from diffsdfsim_b200 import scenes
+    torch.set_num_threads(os.cpu_count() or 1)
+    spec = scenes.box_on_plane(steps=sim_steps)
+    host = make_params(n_worlds, torch.device('cpu'), seed)
+    t0 = time.time()
+    for w in range(n_worlds):
+        leaves = dict(mass=host['mass'][w].clone().requires_grad_(True),
+                      fric_coeff=host['fric_coeff'][w].clone().requires_grad_(True),
+                      push=host['push'][w].clone().requires_grad_(True))
+        ow = build_oracle(spec, leaves)
+        loss = 0.
+        for _ in range(sim_steps):
+            ow.step()
+            loss = loss + (ow.bodies[-1].pos ** 2).sum()
+        loss.backward()
+    dt = time.time() - t0
+    return n_worlds * sim_steps / dt, dt
+
+
+def run_reference(args):
+    """The reference's CPU implementation of the path: here the oracle port (the reference is pure Python/torch with
+    un-vendored dependencies and cannot travel to the GPU box)."""
+    rank = int(os.environ.get('RANK', 0))
+    if rank != 0:
+        return None
+    vals = []
+    for _ in range(args.warmup):
+        cpu_sample(1, 2)
+    t0 = time.time()
+    for k in range(args.steps):
+        v, _ = cpu_sample(args.cpu_worlds, args.cpu_sim_steps, seed=k)
+        vals.append(v)
+    total = time.time() - t0
+    units = args.cpu_worlds * args.cpu_sim_steps * args.steps
+    value = units / total
+    sample = '%d worlds x %d World.step + backward per bench step (same scene, same meshes), sequential worlds' % (
+        args.cpu_worlds, args.cpu_sim_steps)
+    return {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
+            'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total / args.steps * 1e3,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
+            'config': {'workload': 'box_on_plane sysid (bounded CPU sample of the 4096-world workload)',
+                       'worlds_per_gpu': args.worlds, 'sim_steps': args.sim_steps},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample},
+            'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+
+
+def main():
+    args = parse()
+    if args.impl == 'reference':
+        line = run_reference(args)
+        if line is not None:
+            print(json.dumps(line))
+        return
+    line = run_ours(args)
+    if line is None:
+        return
+    if args.gpus == 1 and not args.no_cpu_baseline:
+        v, secs = cpu_sample(args.cpu_worlds, args.cpu_sim_steps)
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
+                                'sample': '%d worlds x %d World.step + backward, sequential worlds, %.1f s of CPU work'
+                                          % (args.cpu_worlds, args.cpu_sim_steps, secs)}
+    print(json.dumps(line))
+
+
+if __name__ == '__main__':
+    main()

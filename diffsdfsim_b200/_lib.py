@@ -25,13 +25,14 @@ SIGNATURES = {
     'dsdf_sdf_query_backward': (c_i, [c_i, c_p, c_p, c_i, c_ll, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     'dsdf_integrate': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p]),
     'dsdf_integrate_backward': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
-    'dsdf_contacts_workspace_bytes': (c_sz, [c_i, c_i, c_i]),
-    'dsdf_contact_chunks_per_face_count': (c_i, [c_i]),
-    'dsdf_contacts_detect': (c_i, [c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_d, c_i, c_i, c_i]
-                             + [c_p] * 10),
+    'dsdf_contacts_detect': (c_i, [c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_d, c_i, c_i, c_i]
+                             + [c_p] * 9),
     'dsdf_contact_geometry_backward': (c_i, [c_p, c_p, c_p, c_i, c_i, c_d, c_i, c_i] + [c_p] * 7),
     'dsdf_dynamics_assemble': (c_i, [c_p] * 12 + [c_i] * 4 + [c_p] * 7),
     'dsdf_dynamics_assemble_backward': (c_i, [c_p] * 12 + [c_i] * 6 + [c_p] * 17),
+    'dsdf_dynamics_solve_smem_bytes': (c_sz, [c_i] * 4),
+    'dsdf_dynamics_solve': (c_i, [c_p] * 13 + [c_i] * 6 + [c_d, c_i, c_i] + [c_p] * 7),
+    'dsdf_dynamics_solve_backward': (c_i, [c_p] * 13 + [c_i] * 8 + [c_p] * 14),
 }
 
 
@@ -53,6 +54,47 @@ def lib():
             fn.restype, fn.argtypes = res, args
         _lib = L
     return _lib
+
+
+# CUDA kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
+KERNELS_PER_CALL = {
+    'dsdf_lcp_forward': 1, 'dsdf_lcp_backward': 1, 'dsdf_sdf_query': 1, 'dsdf_sdf_query_backward': 1,
+    'dsdf_integrate': 1, 'dsdf_integrate_backward': 1, 'dsdf_contacts_detect': 1,
+    'dsdf_contact_geometry_backward': 1, 'dsdf_dynamics_assemble': 1, 'dsdf_dynamics_assemble_backward': 1,
+    'dsdf_dynamics_solve': 1, 'dsdf_dynamics_solve_backward': 1,
+}
+PROFILE = None      # set to {} to record (start, end) CUDA events around every entry-point call
+LAUNCHES = {}       # name -> number of calls since reset_counters()
+
+
+def reset_counters(profile=False):
+    global PROFILE
+    LAUNCHES.clear()
+    PROFILE = {} if profile else None
+
+
+def kernel_launches():
+    return sum(KERNELS_PER_CALL.get(k, 1) * n for k, n in LAUNCHES.items())
+
+
+def call(name, *args):
+    """Invoke an entry point of the library (counts launches; optionally brackets it with CUDA events)."""
+    fn = getattr(lib(), name)
+    LAUNCHES[name] = LAUNCHES.get(name, 0) + 1
+    if PROFILE is None:
+        return fn(*args)
+    s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    s.record()
+    rc = fn(*args)
+    e.record()
+    PROFILE.setdefault(name, []).append((s, e))
+    return rc
+
+
+def profile_summary():
+    """name -> (calls, total ms) from the recorded events (synchronises)."""
+    torch.cuda.synchronize()
+    return {k: (len(v), sum(s.elapsed_time(e) for s, e in v)) for k, v in (PROFILE or {}).items()}
 
 
 def ptr(t):

@@ -12,8 +12,47 @@ from . import _lib
 
 F64 = torch.float64
 _GEOM_DTYPE = np.dtype([('kind', 'i4'), ('nverts', 'i4'), ('nfaces', 'i4'), ('res', 'i4'), ('verts', 'u8'),
-                        ('faces', 'u8'), ('grid', 'u8'), ('vstride', 'i8'), ('gstride', 'i8')], align=True)
-assert _GEOM_DTYPE.itemsize == 56
+                        ('faces', 'u8'), ('grid', 'u8'), ('vstride', 'i8'), ('gstride', 'i8'),
+                        ('cell_lo', 'f8', (3,)), ('cell_inv', 'f8'), ('cell_dims', 'i4', (3,)), ('has_cells', 'i4'),
+                        ('fcell_start', 'u8'), ('fcell_items', 'u8'), ('vcell_start', 'u8'), ('vcell_items', 'u8')],
+                       align=True)
+assert _GEOM_DTYPE.itemsize == 136
+
+
+def build_cell_index(verts, faces, target=32, max_cells=1 << 18):
+    """Uniform grid over a body-frame mesh: faces binned by centroid, vertices by position (CSR, int32).
+
+    Cell size ~ sqrt(target * mean face area) so a cell of a surface patch holds about `target` faces.
+    Returns (lo (3,), inv_h, dims (3,), fstart, fitems, vstart, vitems) as numpy arrays.
+    """
+    v = np.asarray(verts, dtype=np.float64)
+    f = np.asarray(faces, dtype=np.int64)
+    tri = v[f]
+    cen = (tri[:, 0] + tri[:, 1] + tri[:, 2]) / 3.0
+    area = 0.5 * np.linalg.norm(np.cross(tri[:, 1] - tri[:, 0], tri[:, 2] - tri[:, 0]), axis=1)
+    h = float(np.sqrt(max(target * area.mean(), 1e-12)))
+    lo = np.minimum(v.min(0), cen.min(0))
+    hi = np.maximum(v.max(0), cen.max(0))
+    ext = np.maximum(hi - lo, 1e-9)
+    while True:
+        dims = np.maximum(np.ceil(ext / h).astype(np.int64), 1)
+        if dims.prod() <= max_cells:
+            break
+        h *= 1.5
+    lo = lo - 1e-9 * (1.0 + np.abs(lo))
+    inv = 1.0 / h
+
+    def csr(pts):
+        ijk = np.clip(np.floor((pts - lo) * inv).astype(np.int64), 0, dims - 1)
+        cell = (ijk[:, 0] * dims[1] + ijk[:, 1]) * dims[2] + ijk[:, 2]
+        order = np.argsort(cell, kind='stable')
+        start = np.zeros(dims.prod() + 1, dtype=np.int64)
+        np.add.at(start, cell + 1, 1)
+        return np.cumsum(start).astype(np.int32), order.astype(np.int32)
+
+    fs, fi = csr(cen)
+    vs, vi = csr(v)
+    return lo, inv, dims.astype(np.int32), fs, fi, vs, vi
 
 
 class GeometryTable:
@@ -39,8 +78,14 @@ class GeometryTable:
                 gptr = grid.data_ptr()
                 self.keep.append(grid)
             self.keep += [verts, faces]
+            cell = (np.zeros(3), 0.0, np.zeros(3, dtype=np.int32), 0, 0, 0, 0, 0)
+            if not per_world:
+                lo, inv, dims, fs, fi, vs, vi = build_cell_index(verts.cpu().numpy(), faces.cpu().numpy())
+                dev_arrays = [torch.from_numpy(a).to(device) for a in (fs, fi, vs, vi)]
+                self.keep += dev_arrays
+                cell = (lo, inv, dims, 1) + tuple(a.data_ptr() for a in dev_arrays)
             rows[i] = (b.kind, nverts, faces.shape[0], res, verts.data_ptr(), faces.data_ptr(), gptr,
-                       nverts * 3 if per_world else 0, gstride)
+                       nverts * 3 if per_world else 0, gstride) + cell
             self.nfaces.append(int(faces.shape[0]))
         self.rows = rows
         self.dev = torch.from_numpy(rows.view(np.uint8).copy()).to(device)
@@ -65,18 +110,10 @@ class ContactDetector:
     """Owns the work buffers of ``dsdf_contacts_detect`` for one batched world."""
 
     def __init__(self, table, pairs, W, nb, device, capK=768, maxc=16, record_prefilter=False):
-        L = _lib.lib()
+        _lib.lib()
         self.table, self.W, self.nb, self.capK, self.maxc = table, W, nb, capK, maxc
         self.npairs = len(pairs)
         self.pairs = torch.tensor(pairs, dtype=torch.int32, device=device).reshape(-1, 2).contiguous()
-        prefix = [0]
-        for (i, j) in pairs:
-            prefix.append(prefix[-1] + L.dsdf_contact_chunks_per_face_count(table.nfaces[i]))   # direction i -> j
-            prefix.append(prefix[-1] + L.dsdf_contact_chunks_per_face_count(table.nfaces[j]))   # direction j -> i
-        self.total_chunks = prefix[-1]
-        self.prefix = torch.tensor(prefix, dtype=torch.int32, device=device)
-        self.ws = torch.empty(L.dsdf_contacts_workspace_bytes(W, max(self.npairs, 1), capK) // 4 + 4,
-                              dtype=torch.int32, device=device)
         self.device = device
         self.record_prefilter = record_prefilter
 
@@ -99,12 +136,11 @@ class ContactDetector:
         """Fill ``out`` (a ContactSet) for the active worlds; values only (no autograd graph)."""
         L = _lib.lib()
         _lib.require_cuda(p, shape)
-        rc = L.dsdf_contacts_detect(self.table.ptr(), _lib.ptr(self.pairs), _lib.ptr(self.prefix), self.total_chunks,
-                                    self.npairs, _lib.ptr(p), _lib.ptr(shape), _lib.ptr(active), self.W, self.nb,
-                                    eps, tol, fd_eps, body_eps, int(detach_b2), self.capK, self.maxc,
-                                    _lib.ptr(out.count), _lib.ptr(out.body), _lib.ptr(out.face), _lib.ptr(out.abc),
-                                    _lib.ptr(out.geo), _lib.ptr(out.status), _lib.ptr(out.pre_ids),
-                                    _lib.ptr(out.pre_cnt), _lib.ptr(self.ws), _lib.stream())
+        rc = _lib.call('dsdf_contacts_detect', self.table.ptr(), _lib.ptr(self.pairs), self.npairs, _lib.ptr(p),
+                       _lib.ptr(shape), _lib.ptr(active), self.W, self.nb, eps, tol, fd_eps, body_eps, int(detach_b2),
+                       self.capK, self.maxc, _lib.ptr(out.count), _lib.ptr(out.body), _lib.ptr(out.face),
+                       _lib.ptr(out.abc), _lib.ptr(out.geo), _lib.ptr(out.status), _lib.ptr(out.pre_ids),
+                       _lib.ptr(out.pre_cnt), _lib.stream())
         _lib.check(rc, 'dsdf_contacts_detect')
         return out
 
@@ -128,7 +164,7 @@ class _ContactGeometry(torch.autograd.Function):
         p, shape, count, body, face, abc = ctx.saved_tensors
         W, nb = p.shape[0], p.shape[1]
         gp = torch.empty_like(p)
-        rc = L.dsdf_contact_geometry_backward(ctx.table.ptr(), _lib.ptr(p), _lib.ptr(shape), W, nb, ctx.fd_eps,
+        rc = _lib.call('dsdf_contact_geometry_backward', ctx.table.ptr(), _lib.ptr(p), _lib.ptr(shape), W, nb, ctx.fd_eps,
                                               int(ctx.detach_b2), geo_cap(body), _lib.ptr(count), _lib.ptr(body),
                                               _lib.ptr(face), _lib.ptr(abc), _lib.ptr(ggeo.contiguous()), _lib.ptr(gp),
                                               _lib.stream())

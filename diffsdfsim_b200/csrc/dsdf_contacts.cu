@@ -8,8 +8,8 @@
 //   _frank_wolfe                                contacts.py:39-94
 //   _compute_contacts                           contacts.py:161-214
 //   _filter_contacts (scipy Qhull on the host)  contacts.py:97-158
-// Kernels: overlap_kernel (CTA per world x pair), candidate_kernel (all faces, warp-ballot compaction),
-// refine_kernel (CTA per world: FW with the reference's pair-global early exit, contact geometry, filter),
+// Kernels: contacts_kernel (one CTA per world, everything fused: cell-culled vertex/face scans with warp-ballot
+// compaction into shared memory, FW with the reference's pair-global early exit, contact geometry, filter) and
 // contact_geometry_bwd_kernel (forward-mode duals w.r.t. the two poses).
 #include "dsdf_dense.cuh"
 #include "dsdf_sdf.cuh"
@@ -22,6 +22,11 @@ struct BodyGeom {                 // mirrors dsdf_body_geom in include/dsdf_b200
     const int* faces;             // (nfaces,3)
     const double* grid;           // res^3; world w at grid + w*gstride
     long long vstride, gstride;
+    // uniform cell index over the body-frame mesh (faces binned by centroid, vertices by position); has_cells = 0 when
+    // the vertices are per-world (the kernels then scan the whole mesh)
+    double cell_lo[3], cell_inv;
+    int cell_dims[3], has_cells;
+    const int *fcell_start, *fcell_items, *vcell_start, *vcell_items;
 };
 
 __device__ __forceinline__ void load_pose(const double* p, int w, int nb, int b, Q4<double>& q, V3<double>& x) {
@@ -46,115 +51,147 @@ __device__ __forceinline__ V3<double> to_b2(V3<double> v, Q4<double> q1, V3<doub
     return qapply(q2i, (qapply(q1, v) + x1) - x2);
 }
 
-// ------------------------------------------------------------------------------------------ broad phase + _overlap
-__global__ void __launch_bounds__(256)
-overlap_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs, const double* __restrict__ p,
-               const double* __restrict__ shape, const unsigned char* __restrict__ active, int nb, int npairs,
-               double body_eps, int* __restrict__ ovl) {
-    const int pair = blockIdx.x, w = blockIdx.y, tid = threadIdx.x;
-    if (active && !active[w]) return;
-    const int i = pairs[2 * pair], j = pairs[2 * pair + 1];
-    Q4<double> qi, qj; V3<double> xi, xj;
-    load_pose(p, w, nb, i, qi, xi);
-    load_pose(p, w, nb, j, qj, xj);
-    const double si = shape[((size_t)w * nb + i) * 4 + 3], sj = shape[((size_t)w * nb + j) * 4 + 3];
-    // AABB of the rotated cube of half side scale + eps (declared py3ode semantics)
-    M3<double> Ri = q2mat(qi), Rj = q2mat(qj);
-    bool hit = true;
+// ------------------------------------------------------------------------------------------ conservative spatial cull
+// A face can only become a candidate, and a vertex can only witness _overlap, if its position in b2's frame lies in
+// the cube |x| <= scale2 (outside it query_sdfs returns (scale, 0): contacts.py:52 then fails on |grad| > 1e-12;
+// contacts.py:34 tests exactly that cube).  The cube's pre-image in b1's body frame is an oriented box; its
+// axis-aligned bounds (inflated by a margin far above round-off) select the cells to visit.  Everything visited still
+// goes through the exact reference arithmetic, so the result sets are unchanged -- only skipped work differs.
+struct CellRange { int lo[3], hi[3]; bool empty; };
+
+__device__ __forceinline__ CellRange cube_cells(const BodyGeom& g1, Q4<double> q1, V3<double> x1, Q4<double> q2,
+                                                V3<double> x2, double scale2) {
+    CellRange r;
+    const double n1 = q1.w * q1.w + q1.x * q1.x + q1.y * q1.y + q1.z * q1.z;      // raw quaternion products scale by |q|^2
+    const double n2 = q2.w * q2.w + q2.x * q2.x + q2.y * q2.y + q2.z * q2.z;
+    const M3<double> R1 = q2mat(q1), R2 = q2mat(q2);
+    // x_local = R1' ((R2 x_b2) / n2 + x2 - x1) / n1
+    const V3<double> ctr = mat_applyT(R1, x2 - x1);
+    double c[3] = {ctr.x / n1, ctr.y / n1, ctr.z / n1};
+    double h[3];
 #pragma unroll
-    for (int a = 0; a < 3; ++a) {
-        const double hi = (fabs(Ri.m[3 * a]) + fabs(Ri.m[3 * a + 1]) + fabs(Ri.m[3 * a + 2])) * (si + body_eps);
-        const double hj = (fabs(Rj.m[3 * a]) + fabs(Rj.m[3 * a + 1]) + fabs(Rj.m[3 * a + 2])) * (sj + body_eps);
-        const double dc = a == 0 ? xi.x - xj.x : (a == 1 ? xi.y - xj.y : xi.z - xj.z);
-        hit = hit && (fabs(dc) <= hi + hj);
+    for (int i = 0; i < 3; ++i) {
+        double acc = 0.0;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            // (R1' R2)_{ik}
+            const double m = R1.m[i] * R2.m[k] + R1.m[3 + i] * R2.m[3 + k] + R1.m[6 + i] * R2.m[6 + k];
+            acc += fabs(m);
+        }
+        h[i] = acc * scale2 / (n1 * n2);
     }
-    int result = 0;
-    if (hit) {
-        // any vertex of i inside j's cube AND any vertex of j inside i's cube
-        const BodyGeom gi = geom[i], gj = geom[j];
-        const Q4<double> qii = qinv(qi), qji = qinv(qj);
-        int found_ij = 0, found_ji = 0;
-        for (int base = 0; base < gi.nverts && !found_ij; base += 256 * 4) {
+    const double margin = 1e-6 * (1.0 + fabs(c[0]) + fabs(c[1]) + fabs(c[2]) + 2.0 * scale2);
+    r.empty = false;
+#pragma unroll
+    for (int i = 0; i < 3; ++i) {
+        const double a = (c[i] - h[i] - margin - g1.cell_lo[i]) * g1.cell_inv;
+        const double b = (c[i] + h[i] + margin - g1.cell_lo[i]) * g1.cell_inv;
+        if (b < 0.0 || a >= (double)g1.cell_dims[i]) r.empty = true;
+        r.lo[i] = a <= 0.0 ? 0 : (a >= (double)g1.cell_dims[i] ? g1.cell_dims[i] - 1 : (int)a);
+        r.hi[i] = b <= 0.0 ? 0 : (b >= (double)g1.cell_dims[i] ? g1.cell_dims[i] - 1 : (int)b);
+    }
+    return r;
+}
+
+// _overlap half (contacts.py:31,34): any vertex of b1 inside b2's cube.  Block-cooperative, early exit.
+__device__ int any_vertex_in_cube(const BodyGeom& g1, int w, Q4<double> q1, V3<double> x1, Q4<double> q2,
+                                  V3<double> x2, double s2) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
+    const Q4<double> q2i = qinv(q2);
+    if (!g1.has_cells) {
+        for (int base = 0; base < g1.nverts; base += 256 * 4) {
             int f = 0;
             for (int u = 0; u < 4; ++u) {
                 const int v = base + u * 256 + tid;
-                if (v < gi.nverts) {
-                    V3<double> t = to_b2(load_vert(gi, w, v), qi, xi, qji, xj);
-                    f |= (-sj <= t.x && t.x <= sj && -sj <= t.y && t.y <= sj && -sj <= t.z && t.z <= sj);
+                if (v < g1.nverts) {
+                    const V3<double> t = to_b2(load_vert(g1, w, v), q1, x1, q2i, x2);
+                    f |= (-s2 <= t.x && t.x <= s2 && -s2 <= t.y && t.y <= s2 && -s2 <= t.z && t.z <= s2);
                 }
             }
-            found_ij = __syncthreads_or(f);
+            if (__syncthreads_or(f)) return 1;
         }
-        if (found_ij) {
-            for (int base = 0; base < gj.nverts && !found_ji; base += 256 * 4) {
-                int f = 0;
-                for (int u = 0; u < 4; ++u) {
-                    const int v = base + u * 256 + tid;
-                    if (v < gj.nverts) {
-                        V3<double> t = to_b2(load_vert(gj, w, v), qj, xj, qii, xi);
-                        f |= (-si <= t.x && t.x <= si && -si <= t.y && t.y <= si && -si <= t.z && t.z <= si);
-                    }
-                }
-                found_ji = __syncthreads_or(f);
-            }
-        }
-        result = found_ij && found_ji;
+        return 0;
     }
-    if (tid == 0) ovl[(size_t)w * npairs + pair] = result;
+    const CellRange cr = cube_cells(g1, q1, x1, q2, x2, s2);
+    if (cr.empty) return 0;
+    const int nx = cr.hi[0] - cr.lo[0] + 1, ny = cr.hi[1] - cr.lo[1] + 1, nzc = cr.hi[2] - cr.lo[2] + 1;
+    const int ncell = nx * ny * nzc;
+    for (int base = 0; base < ncell; base += nw) {
+        int f = 0;
+        const int ci = base + warp;
+        if (ci < ncell) {
+            const int ix = cr.lo[0] + ci / (ny * nzc), iy = cr.lo[1] + (ci / nzc) % ny, iz = cr.lo[2] + ci % nzc;
+            const int cell = (ix * g1.cell_dims[1] + iy) * g1.cell_dims[2] + iz;
+            const int s = g1.vcell_start[cell], e = g1.vcell_start[cell + 1];
+            for (int k = s + lane; k < e; k += 32) {
+                const V3<double> t = to_b2(load_vert(g1, w, g1.vcell_items[k]), q1, x1, q2i, x2);
+                f |= (-s2 <= t.x && t.x <= s2 && -s2 <= t.y && t.y <= s2 && -s2 <= t.z && t.z <= s2);
+            }
+        }
+        if (__syncthreads_or(f)) return 1;
+    }
+    return 0;
 }
 
-// ------------------------------------------------------------------------------------------ centroid candidate pass
-// contacts.py:44-52: sdf(centroid) < max_i |centroid - v_i| + eps  and  |grad| > 1e-12
-enum { CAND_FPT = 4 };
-__global__ void __launch_bounds__(256)
-candidate_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs, const int* __restrict__ chunk_prefix,
-                 int ndirs, const double* __restrict__ p, const double* __restrict__ shape,
-                 const unsigned char* __restrict__ active, const int* __restrict__ ovl, int nb, int npairs,
-                 double eps, int capK, int* __restrict__ cand, int* __restrict__ ccnt) {
-    const int w = blockIdx.y, tid = threadIdx.x, lane = tid & 31;
-    if (active && !active[w]) return;
-    int d = 0;
-    while (d + 1 < ndirs && (int)blockIdx.x >= chunk_prefix[d + 1]) ++d;
-    const int chunk = blockIdx.x - chunk_prefix[d];
-    const int pair = d >> 1;
-    if (!ovl[(size_t)w * npairs + pair]) return;
-    const int i1 = (d & 1) ? pairs[2 * pair + 1] : pairs[2 * pair];
-    const int i2 = (d & 1) ? pairs[2 * pair] : pairs[2 * pair + 1];
-    const BodyGeom g1 = geom[i1];
-    const SdfShape s2 = body_shape(geom[i2], shape, w, nb, i2);
-    Q4<double> q1, q2; V3<double> x1, x2;
-    load_pose(p, w, nb, i1, q1, x1);
-    load_pose(p, w, nb, i2, q2, x2);
+// contacts.py:44-52 for one face: sdf(centroid) < max_i |centroid - v_i| + eps  and  |grad| > 1e-12
+__device__ __forceinline__ bool face_is_candidate(const BodyGeom& g1, int w, int f, const SdfShape& s2, Q4<double> q1,
+                                                  V3<double> x1, Q4<double> q2i, V3<double> x2, double eps) {
+    const int ia = g1.faces[3 * f], ib = g1.faces[3 * f + 1], ic = g1.faces[3 * f + 2];
+    const V3<double> a = to_b2(load_vert(g1, w, ia), q1, x1, q2i, x2);
+    const V3<double> b = to_b2(load_vert(g1, w, ib), q1, x1, q2i, x2);
+    const V3<double> c = to_b2(load_vert(g1, w, ic), q1, x1, q2i, x2);
+    const V3<double> ctr = v3<double>((a.x + b.x + c.x) / 3, (a.y + b.y + c.y) / 3, (a.z + b.z + c.z) / 3);
+    const SdfOut<double> o = sdf_query<double>(s2, ctr, true);
+    double rad = norm3(ctr - a);
+    rad = fmax(rad, norm3(ctr - b));
+    rad = fmax(rad, norm3(ctr - c));
+    return (o.d < rad + eps) && (norm3(o.n) > 1e-12);
+}
+
+// Centroid candidate pass of one search direction into the shared list ids[0..capK) (unsorted); returns the count
+// (which may exceed capK: overflow).  s_cnt: one shared int.
+__device__ int gather_candidates(const BodyGeom& g1, int w, const SdfShape& s2, Q4<double> q1, V3<double> x1,
+                                 Q4<double> q2, V3<double> x2, double eps, int capK, int* ids, int* s_cnt) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const Q4<double> q2i = qinv(q2);
-    int* my_cand = cand + ((size_t)w * ndirs + d) * capK;
-    int* my_cnt = ccnt + (size_t)w * ndirs + d;
-#pragma unroll 1
-    for (int u = 0; u < CAND_FPT; ++u) {
-        const int f = (chunk * CAND_FPT + u) * 256 + tid;
-        bool is_cand = false;
-        if (f < g1.nfaces) {
-            const int ia = g1.faces[3 * f], ib = g1.faces[3 * f + 1], ic = g1.faces[3 * f + 2];
-            const V3<double> a = to_b2(load_vert(g1, w, ia), q1, x1, q2i, x2);
-            const V3<double> b = to_b2(load_vert(g1, w, ib), q1, x1, q2i, x2);
-            const V3<double> c = to_b2(load_vert(g1, w, ic), q1, x1, q2i, x2);
-            const V3<double> ctr = v3<double>((a.x + b.x + c.x) / 3, (a.y + b.y + c.y) / 3, (a.z + b.z + c.z) / 3);
-            const SdfOut<double> o = sdf_query<double>(s2, ctr, true);
-            double rad = norm3(ctr - a);
-            rad = fmax(rad, norm3(ctr - b));
-            rad = fmax(rad, norm3(ctr - c));
-            is_cand = (o.d < rad + eps) && (norm3(o.n) > 1e-12);
-        }
+    if (tid == 0) *s_cnt = 0;
+    __syncthreads();
+    auto push = [&](bool is_cand, int f) {
         const unsigned m = __ballot_sync(DSDF_FULL, is_cand);
         if (m) {
             int base = 0;
-            if (lane == 0) base = atomicAdd(my_cnt, __popc(m));
+            if (lane == 0) base = atomicAdd(s_cnt, __popc(m));
             base = __shfl_sync(DSDF_FULL, base, 0);
             if (is_cand) {
                 const int slot = base + __popc(m & ((1u << lane) - 1));
-                if (slot < capK) my_cand[slot] = f;
+                if (slot < capK) ids[slot] = f;
+            }
+        }
+    };
+    if (!g1.has_cells) {
+        for (int base = 0; base < g1.nfaces; base += blockDim.x) {
+            const int f = base + tid;
+            push(f < g1.nfaces && face_is_candidate(g1, w, f, s2, q1, x1, q2i, x2, eps), f);
+        }
+    } else {
+        const CellRange cr = cube_cells(g1, q1, x1, q2, x2, s2.scale);
+        if (!cr.empty) {
+            const int nx = cr.hi[0] - cr.lo[0] + 1, ny = cr.hi[1] - cr.lo[1] + 1, nzc = cr.hi[2] - cr.lo[2] + 1;
+            const int ncell = nx * ny * nzc;
+            for (int ci = warp; ci < ncell; ci += nw) {
+                const int ix = cr.lo[0] + ci / (ny * nzc), iy = cr.lo[1] + (ci / nzc) % ny, iz = cr.lo[2] + ci % nzc;
+                const int cell = (ix * g1.cell_dims[1] + iy) * g1.cell_dims[2] + iz;
+                const int s = g1.fcell_start[cell], e = g1.fcell_start[cell + 1];
+                for (int k0 = s; k0 < e; k0 += 32) {
+                    const int k = k0 + lane;
+                    const int f = k < e ? g1.fcell_items[k] : 0;
+                    push(k < e && face_is_candidate(g1, w, f, s2, q1, x1, q2i, x2, eps), f);
+                }
             }
         }
     }
+    __syncthreads();
+    return *s_cnt;
 }
 
 // ------------------------------------------------------------------------------------------ contact geometry
@@ -296,17 +333,17 @@ struct DirResult { int count; int valid; };
 
 // One search direction (mesh body i1 -> SDF body i2) for world w.  On return the first `count` slots of
 // GEO (=P rows 0..8 + X row 0), ABC and ID hold the pre-filter contacts in ascending face order.
+// ids: the candidate list already sitting (unsorted) in sm.ID[0..min(ncand,capK)).
 __device__ DirResult search_direction(const RefineSmem& sm, int capK, const BodyGeom& g1, const SdfShape& s1,
                                       const SdfShape& s2, Q4<double> q1, V3<double> x1, Q4<double> q2, V3<double> x2,
-                                      int w, const int* cand, int ncand, double eps, double tol, double fd_eps,
-                                      bool detach_b2) {
+                                      int w, int ncand, double eps, double tol, double fd_eps, bool detach_b2) {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int K = min(ncand, capK);
     DirResult r; r.count = 0; r.valid = 1;
     if (K == 0) return r;
     int n2 = 1;
     while (n2 < K) n2 <<= 1;
-    for (int i = tid; i < n2; i += nt) sm.ID[i] = i < K ? cand[i] : 0x7fffffff;
+    for (int i = K + tid; i < n2; i += nt) sm.ID[i] = 0x7fffffff;
     __syncthreads();
     bitonic_sort_int(sm.ID, n2);
     const Q4<double> q2i = qinv(q2);
@@ -654,16 +691,19 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
     return status;
 }
 
+// One CTA per world: broad phase, _overlap, and both search directions of every body pair, fused.
 __global__ void __launch_bounds__(256)
-refine_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs, int ndirs,
-              const double* __restrict__ p, const double* __restrict__ shape, const unsigned char* __restrict__ active,
-              const int* __restrict__ ovl, int nb, int npairs, double eps, double tol, double fd_eps, int detach_b2,
-              int capK, const int* __restrict__ cand, const int* __restrict__ ccnt, int maxc,
-              int* __restrict__ count, int* __restrict__ cbody, int* __restrict__ cface, double* __restrict__ cabc,
-              double* __restrict__ cgeo, int* __restrict__ wstatus, int* __restrict__ pre_ids, int* __restrict__ pre_cnt) {
+contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs, int npairs,
+                const double* __restrict__ p, const double* __restrict__ shape, const unsigned char* __restrict__ active,
+                int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
+                int capK, int maxc,
+                int* __restrict__ count, int* __restrict__ cbody, int* __restrict__ cface, double* __restrict__ cabc,
+                double* __restrict__ cgeo, int* __restrict__ wstatus, int* __restrict__ pre_ids, int* __restrict__ pre_cnt) {
     extern __shared__ double smraw[];
+    __shared__ int s_cnt;
     const int w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
     if (active && !active[w]) return;
+    const int ndirs = 2 * npairs;
     RefineSmem sm;
     sm.P = smraw; sm.X = sm.P + 9 * (size_t)capK; sm.ABC = sm.X + 3 * (size_t)capK; sm.HK = sm.ABC + 3 * (size_t)capK;
     sm.red = sm.HK + 2 * (size_t)capK;
@@ -671,24 +711,38 @@ refine_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs, 
     sm.SC = sm.ID + capK; sm.CL = sm.SC + capK; sm.HI = sm.CL + capK; sm.KEEP = sm.HI + capK;
     int nout = 0, status = 0;
     for (int pair = 0; pair < npairs; ++pair) {
-        if (!ovl[(size_t)w * npairs + pair]) {
+        const int bi = pairs[2 * pair], bj = pairs[2 * pair + 1];
+        Q4<double> qi, qj; V3<double> xi, xj;
+        load_pose(p, w, nb, bi, qi, xi);
+        load_pose(p, w, nb, bj, qj, xj);
+        const double si = shape[((size_t)w * nb + bi) * 4 + 3], sj = shape[((size_t)w * nb + bj) * 4 + 3];
+        // broad phase: AABB of the rotated cube of half side scale + eps (declared py3ode semantics)
+        const M3<double> Ri = q2mat(qi), Rj = q2mat(qj);
+        bool hit = true;
+#pragma unroll
+        for (int a = 0; a < 3; ++a) {
+            const double hi = (fabs(Ri.m[3 * a]) + fabs(Ri.m[3 * a + 1]) + fabs(Ri.m[3 * a + 2])) * (si + body_eps);
+            const double hj = (fabs(Rj.m[3 * a]) + fabs(Rj.m[3 * a + 1]) + fabs(Rj.m[3 * a + 2])) * (sj + body_eps);
+            const double dc = a == 0 ? xi.x - xj.x : (a == 1 ? xi.y - xj.y : xi.z - xj.z);
+            hit = hit && (fabs(dc) <= hi + hj);
+        }
+        int ov = 0;
+        if (hit) ov = any_vertex_in_cube(geom[bi], w, qi, xi, qj, xj, sj) && any_vertex_in_cube(geom[bj], w, qj, xj, qi, xi, si);
+        if (!ov) {
             if (pre_cnt && tid == 0) { pre_cnt[(size_t)w * ndirs + 2 * pair] = -1; pre_cnt[(size_t)w * ndirs + 2 * pair + 1] = -1; }
             continue;
         }
         for (int rev = 0; rev < 2; ++rev) {
             const int d = 2 * pair + rev;
-            const int i1 = rev ? pairs[2 * pair + 1] : pairs[2 * pair];
-            const int i2 = rev ? pairs[2 * pair] : pairs[2 * pair + 1];
+            const int i1 = rev ? bj : bi, i2 = rev ? bi : bj;
             const BodyGeom g1 = geom[i1];
             const SdfShape s1 = body_shape(g1, shape, w, nb, i1);
             const SdfShape s2 = body_shape(geom[i2], shape, w, nb, i2);
-            Q4<double> q1, q2; V3<double> x1, x2;
-            load_pose(p, w, nb, i1, q1, x1);
-            load_pose(p, w, nb, i2, q2, x2);
-            const int ncand = ccnt[(size_t)w * ndirs + d];
+            const Q4<double> q1 = rev ? qj : qi, q2 = rev ? qi : qj;
+            const V3<double> x1 = rev ? xj : xi, x2 = rev ? xi : xj;
+            const int ncand = gather_candidates(g1, w, s2, q1, x1, q2, x2, eps, capK, sm.ID, &s_cnt);
             if (ncand > capK) status |= 1;
-            DirResult r = search_direction(sm, capK, g1, s1, s2, q1, x1, q2, x2, w,
-                                           cand + ((size_t)w * ndirs + d) * capK, ncand, eps, tol, fd_eps, detach_b2 != 0);
+            DirResult r = search_direction(sm, capK, g1, s1, s2, q1, x1, q2, x2, w, ncand, eps, tol, fd_eps, detach_b2 != 0);
             if (pre_cnt) {
                 if (tid == 0) pre_cnt[(size_t)w * ndirs + d] = r.count;
                 for (int k = tid; k < r.count; k += nt) pre_ids[((size_t)w * ndirs + d) * capK + k] = sm.ID[k];
@@ -726,7 +780,6 @@ refine_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs, 
     if (tid == 0) { count[w] = nout; wstatus[w] = status; }
 }
 
-// ------------------------------------------------------------------------------------------ geometry VJP w.r.t. poses
 // One CTA per world; thread (body, component) accumulates over that world's contacts sequentially (deterministic).
 __global__ void __launch_bounds__(128)
 contact_geometry_bwd_kernel(const BodyGeom* __restrict__ geom, const double* __restrict__ p,
@@ -774,43 +827,23 @@ using namespace dsdf;
 
 extern "C" {
 
-size_t dsdf_contacts_workspace_bytes(int W, int npairs, int capK) {
-    const size_t ndirs = 2 * (size_t)npairs;
-    return ((size_t)W * npairs + (size_t)W * ndirs + (size_t)W * ndirs * capK + 16) * sizeof(int);
-}
-
-int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, const int32_t* chunk_prefix, int total_chunks,
-                         int npairs, const double* p, const double* shape, const unsigned char* active,
+int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, int npairs, const double* p,
+                         const double* shape, const unsigned char* active,
                          int W, int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
                          int capK, int maxc, int32_t* count, int32_t* cbody, int32_t* cface, double* cabc, double* cgeo,
-                         int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, void* ws, void* stream) {
+                         int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, void* stream) {
     if (W <= 0 || nb <= 0 || npairs < 0 || capK < 32 || capK > 1024 || maxc <= 0) return -1;
+    static_assert(sizeof(BodyGeom) == sizeof(dsdf_body_geom), "BodyGeom must mirror dsdf_body_geom");
     cudaStream_t st = (cudaStream_t)stream;
-    if (npairs == 0) {
-        cudaMemsetAsync(count, 0, sizeof(int) * W, st);   // note: inactive worlds are also zeroed in this trivial case
-        cudaMemsetAsync(wstatus, 0, sizeof(int) * W, st);
-        return (int)cudaGetLastError();
-    }
-    const int ndirs = 2 * npairs;
-    int* ovl = (int*)ws;
-    int* ccnt = ovl + (size_t)W * npairs;
-    int* cand = ccnt + (size_t)W * ndirs;
     const size_t smem = refine_smem_bytes(capK);
     if (smem > 227 * 1024) return -2;
-    cudaMemsetAsync(ccnt, 0, sizeof(int) * (size_t)W * ndirs, st);
-    const BodyGeom* G = reinterpret_cast<const BodyGeom*>(geom);
-    overlap_kernel<<<dim3(npairs, W), 256, 0, st>>>(G, pairs, p, shape, active, nb, npairs, body_eps, ovl);
-    if (total_chunks > 0)
-        candidate_kernel<<<dim3(total_chunks, W), 256, 0, st>>>(G, pairs, chunk_prefix, ndirs, p, shape, active, ovl, nb,
-                                                              npairs, eps, capK, cand, ccnt);
-    cudaError_t e = cudaFuncSetAttribute(refine_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = cudaFuncSetAttribute(contacts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    refine_kernel<<<W, 256, smem, st>>>(G, pairs, ndirs, p, shape, active, ovl, nb, npairs, eps, tol, fd_eps, detach_b2,
-                                        capK, cand, ccnt, maxc, count, cbody, cface, cabc, cgeo, wstatus, pre_ids, pre_cnt);
+    contacts_kernel<<<W, 256, smem, st>>>(reinterpret_cast<const BodyGeom*>(geom), pairs, npairs, p, shape, active, nb,
+                                          eps, tol, fd_eps, body_eps, detach_b2, capK, maxc, count, cbody, cface, cabc,
+                                          cgeo, wstatus, pre_ids, pre_cnt);
     return (int)cudaGetLastError();
 }
-
-int dsdf_contact_chunks_per_face_count(int nfaces) { return (nfaces + 256 * CAND_FPT - 1) / (256 * CAND_FPT); }
 
 int dsdf_contact_geometry_backward(const dsdf_body_geom* geom, const double* p, const double* shape, int W, int nb,
                                    double fd_eps, int detach_b2, int maxc, const int32_t* count, const int32_t* cbody,

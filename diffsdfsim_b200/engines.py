@@ -24,7 +24,7 @@ def _assemble(L, p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody, geo
     h = torch.empty(W, ni, dtype=F64, device=dev)
     Fm = torch.empty(W, ni, ni, dtype=F64, device=dev)
     nin = torch.empty(W, dtype=torch.int32, device=dev)
-    rc = L.dsdf_dynamics_assemble(_lib.ptr(p), _lib.ptr(v), _lib.ptr(mass), _lib.ptr(Ibody), _lib.ptr(fric),
+    rc = _lib.call('dsdf_dynamics_assemble', _lib.ptr(p), _lib.ptr(v), _lib.ptr(mass), _lib.ptr(Ibody), _lib.ptr(fric),
                                   _lib.ptr(rest), _lib.ptr(f), _lib.ptr(dt), _lib.ptr(active), _lib.ptr(count),
                                   _lib.ptr(cbody), _lib.ptr(geo), W, nb, maxc, fd, _lib.ptr(Q), _lib.ptr(pv),
                                   _lib.ptr(G), _lib.ptr(h), _lib.ptr(Fm), _lib.ptr(nin), _lib.stream())
@@ -79,8 +79,8 @@ class _Dynamics(torch.autograd.Function):
         gmass, gI = torch.empty_like(mass), torch.empty_like(Ibody)
         gfric, grest, gf = torch.empty_like(fric), torch.empty_like(rest), torch.empty_like(f)
         gdt, ggeo = torch.empty(W, dtype=F64, device=dev), torch.empty_like(geo)
-        rc = L.dsdf_dynamics_assemble_backward(
-            _lib.ptr(p), _lib.ptr(v), _lib.ptr(mass), _lib.ptr(Ibody), _lib.ptr(fric), _lib.ptr(rest), _lib.ptr(f),
+        rc = _lib.call(
+            'dsdf_dynamics_assemble_backward', _lib.ptr(p), _lib.ptr(v), _lib.ptr(mass), _lib.ptr(Ibody), _lib.ptr(fric), _lib.ptr(rest), _lib.ptr(f),
             _lib.ptr(dt), _lib.ptr(active), _lib.ptr(count), _lib.ptr(cbody), _lib.ptr(geo), W, nb, maxc, fd,
             int(cfg['stop_contact_grad']), int(cfg['stop_friction_grad']), _lib.ptr(Q), _lib.ptr(G), _lib.ptr(dQ),
             _lib.ptr(dp), _lib.ptr(dG), _lib.ptr(dh), _lib.ptr(dF), _lib.ptr(gp), _lib.ptr(gv), _lib.ptr(gmass),
@@ -89,6 +89,70 @@ class _Dynamics(torch.autograd.Function):
         if gpass is not None:
             gv = gv + gpass
         return gp, gv, gmass, gI, gfric, grest, gf, gdt, ggeo, None, None, None, None, None, None
+
+
+class _DynamicsFused(torch.autograd.Function):
+    """dsdf_dynamics_solve / dsdf_dynamics_solve_backward: one warp per world, structure-exploiting KKT."""
+
+    @staticmethod
+    def forward(ctx, p, v, mass, Ibody, fric, rest, f, dt, geo, count, cbody, eq_rows, active, cfg):
+        _lib.lib()
+        _lib.require_cuda(p, v)
+        c = lambda t: t.contiguous()
+        p, v, mass, Ibody, fric, rest, f, dt, geo = [c(t) for t in (p, v, mass, Ibody, fric, rest, f, dt, geo)]
+        W, nb = p.shape[0], p.shape[1]
+        maxc, fd = geo.shape[1], cfg['fric_dirs']
+        neq = eq_rows.shape[0]
+        dev = p.device
+        x = torch.empty(W, 6 * nb, dtype=F64, device=dev)
+        nu = torch.empty(W, neq, dtype=F64, device=dev)
+        lam = torch.empty(W, maxc * (2 + fd), dtype=F64, device=dev)
+        s = torch.empty_like(lam)
+        status = torch.zeros(W, dtype=torch.int32, device=dev)
+        iters = torch.zeros(W, dtype=torch.int32, device=dev)
+        rc = _lib.call('dsdf_dynamics_solve', _lib.ptr(p), _lib.ptr(v), _lib.ptr(mass), _lib.ptr(Ibody),
+                       _lib.ptr(fric), _lib.ptr(rest), _lib.ptr(f), _lib.ptr(dt), _lib.ptr(active), _lib.ptr(count),
+                       _lib.ptr(cbody), _lib.ptr(geo), _lib.ptr(eq_rows), W, nb, neq, maxc, cfg['nc_smem'], fd,
+                       1e-12, 3, cfg['max_iter'], _lib.ptr(x), _lib.ptr(nu), _lib.ptr(lam), _lib.ptr(s),
+                       _lib.ptr(status), _lib.ptr(iters), _lib.stream())
+        _lib.check(rc, 'dsdf_dynamics_solve')
+        new_v = (-x).reshape(W, nb, 6)
+        if active is not None:
+            new_v = torch.where(active.bool().reshape(W, 1, 1), new_v, v)
+        ctx.save_for_backward(p, v, mass, Ibody, fric, rest, f, dt, geo, count, cbody, eq_rows, x, lam, s,
+                              active if active is not None else p.new_empty(0))
+        ctx.cfg = cfg
+        cfg['last_iters'] = iters
+        ctx.mark_non_differentiable(status)
+        return new_v, status
+
+    @staticmethod
+    def backward(ctx, gv_new, _gstatus):
+        (p, v, mass, Ibody, fric, rest, f, dt, geo, count, cbody, eq_rows, x, lam, s, active) = ctx.saved_tensors
+        active = active if active.numel() else None
+        cfg = ctx.cfg
+        W, nb = p.shape[0], p.shape[1]
+        maxc, fd = geo.shape[1], cfg['fric_dirs']
+        gz = (-gv_new).reshape(W, 6 * nb).contiguous()
+        gpass = None
+        if active is not None:
+            am = active.bool().reshape(W, 1)
+            gpass = torch.where(am, torch.zeros_like(gz), -gz).reshape(W, nb, 6)
+        gp, gv = torch.empty_like(p), torch.empty_like(v)
+        gmass, gI = torch.empty_like(mass), torch.empty_like(Ibody)
+        gfric, grest, gf = torch.empty_like(fric), torch.empty_like(rest), torch.empty_like(f)
+        gdt, ggeo = torch.empty(W, dtype=F64, device=p.device), torch.empty_like(geo)
+        rc = _lib.call('dsdf_dynamics_solve_backward', _lib.ptr(p), _lib.ptr(v), _lib.ptr(mass), _lib.ptr(Ibody),
+                       _lib.ptr(fric), _lib.ptr(rest), _lib.ptr(f), _lib.ptr(dt), _lib.ptr(active), _lib.ptr(count),
+                       _lib.ptr(cbody), _lib.ptr(geo), _lib.ptr(eq_rows), W, nb, eq_rows.shape[0], maxc,
+                       cfg['nc_smem'], fd, int(cfg['stop_contact_grad']), int(cfg['stop_friction_grad']),
+                       _lib.ptr(x), _lib.ptr(lam), _lib.ptr(s), _lib.ptr(gz), _lib.ptr(gp), _lib.ptr(gv),
+                       _lib.ptr(gmass), _lib.ptr(gI), _lib.ptr(gfric), _lib.ptr(grest), _lib.ptr(gf), _lib.ptr(gdt),
+                       _lib.ptr(ggeo), _lib.stream())
+        _lib.check(rc, 'dsdf_dynamics_solve_backward')
+        if gpass is not None:
+            gv = gv + gpass
+        return gp, gv, gmass, gI, gfric, grest, gf, gdt, ggeo, None, None, None, None, None
 
 
 class Engine:
@@ -101,6 +165,8 @@ class Engine:
 class PdipmEngine(Engine):
     """Primal-dual interior-point LCP engine (engines.py:22-83) over all worlds at once."""
 
+    dense = False    # True: assemble dense matrices and run the general LCP kernels (dsdf_lcp_*) instead
+
     def __init__(self, max_iter=10):
         self.max_iter = max_iter
         self.last_status = None
@@ -111,15 +177,25 @@ class PdipmEngine(Engine):
         f = world.apply_forces(world.t)
         cfg = dict(fric_dirs=world.fric_dirs, max_iter=self.max_iter, stop_contact_grad=world.stop_contact_grad,
                    stop_friction_grad=world.stop_friction_grad,
-                   ni_smem=max(world.max_nc, 1) * (2 + world.fric_dirs))
-        new_v, status = _Dynamics.apply(st.p, st.v, st.mass, st.Ibody, st.fric, st.rest, f, dt, world.contact_geo,
-                                        world.contact_set.count, world.contact_set.body, world.A, world.b, active, cfg)
+                   ni_smem=max(world.max_nc, 1) * (2 + world.fric_dirs), nc_smem=max(world.max_nc, 1))
+        cs = world.contact_set
+        if self.dense:
+            new_v, status = _Dynamics.apply(st.p, st.v, st.mass, st.Ibody, st.fric, st.rest, f, dt, world.contact_geo,
+                                            cs.count, cs.body, world.A, world.b, active, cfg)
+        else:
+            new_v, status = _DynamicsFused.apply(st.p, st.v, st.mass, st.Ibody, st.fric, st.rest, f, dt,
+                                                 world.contact_geo, cs.count, cs.body, world.eq_rows, active, cfg)
         self.last_status = status
         return new_v
 
     def post_stabilization(self, world):
         raise NotImplementedError('post-stabilisation (engines.py:85-121) is off by default in the reference '
                                   '(utils.py:64) and listed under "next" in SURVEY.md s8f')
+
+
+class DensePdipmEngine(PdipmEngine):
+    """Same engine through the dense LCP kernels (the LCPFunction path); limited to ~15 contacts per world."""
+    dense = True
 
 
 B200Engine = PdipmEngine

@@ -46,7 +46,7 @@ def lcp_solve_raw(Q, p, G, h, A, b, F, nineq_w=None, eps=1e-12, not_improved_lim
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     iters = torch.zeros(B, dtype=torch.int32, device=dev)
     ws = torch.empty(L.dsdf_lcp_workspace_bytes(B, nz, neq, ni) // 8 + 1, dtype=F64, device=dev)
-    rc = L.dsdf_lcp_forward(_lib.ptr(Q), _lib.ptr(p), _lib.ptr(G), _lib.ptr(h),
+    rc = _lib.call('dsdf_lcp_forward', _lib.ptr(Q), _lib.ptr(p), _lib.ptr(G), _lib.ptr(h),
                             _lib.ptr(A) if neq else None, _lib.ptr(b) if neq else None, _lib.ptr(F),
                             _lib.ptr(nineq_w), B, nz, neq, ni, int(nineq_smem), eps, not_improved_lim, max_iter,
                             int(check_spd),
@@ -68,7 +68,7 @@ def lcp_backward_raw(Q, G, A, F, x, nu, lam, s, gz, nineq_w=None, need=(True,) *
     dF = mk(need[6], B, ni, ni)
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     ws = torch.empty(L.dsdf_lcp_workspace_bytes(B, nz, neq, ni) // 8 + 1, dtype=F64, device=dev)
-    rc = L.dsdf_lcp_backward(_lib.ptr(Q), _lib.ptr(G), _lib.ptr(A) if neq else None, _lib.ptr(F), _lib.ptr(nineq_w),
+    rc = _lib.call('dsdf_lcp_backward', _lib.ptr(Q), _lib.ptr(G), _lib.ptr(A) if neq else None, _lib.ptr(F), _lib.ptr(nineq_w),
                              _lib.ptr(x), _lib.ptr(nu), _lib.ptr(lam), _lib.ptr(s), _lib.ptr(gz.contiguous()),
                              B, nz, neq, ni, int(nineq_smem), _lib.ptr(dQ), _lib.ptr(dp), _lib.ptr(dG), _lib.ptr(dh), _lib.ptr(dA),
                              _lib.ptr(db), _lib.ptr(dF), _lib.ptr(status), _lib.ptr(ws), _lib.stream())

@@ -28,7 +28,7 @@ class _SdfQuery(torch.autograd.Function):
             stride = res ** 3 if grid.dim() == 4 else 0
         sdf = torch.empty(W, N, dtype=F64, device=pts.device)
         d = torch.empty(W, N, 3, dtype=F64, device=pts.device) if want_dir else None
-        rc = L.dsdf_sdf_query(kind, _lib.ptr(shape), _lib.ptr(grid) if kind == 3 else None, res, stride,
+        rc = _lib.call('dsdf_sdf_query', kind, _lib.ptr(shape), _lib.ptr(grid) if kind == 3 else None, res, stride,
                               _lib.ptr(pts), W, N, int(want_dir), _lib.ptr(sdf), _lib.ptr(d), _lib.stream())
         _lib.check(rc, 'dsdf_sdf_query')
         ctx.save_for_backward(pts, shape, grid if kind == 3 else pts.new_empty(0))
@@ -46,7 +46,7 @@ class _SdfQuery(torch.autograd.Function):
         W, N = pts.shape[0], pts.shape[1]
         gpts = torch.empty_like(pts)
         gdir = _c(gdir) if (want_dir and gdir is not None and gdir.numel()) else None
-        rc = L.dsdf_sdf_query_backward(kind, _lib.ptr(shape), _lib.ptr(grid) if kind == 3 else None, res, stride,
+        rc = _lib.call('dsdf_sdf_query_backward', kind, _lib.ptr(shape), _lib.ptr(grid) if kind == 3 else None, res, stride,
                                        _lib.ptr(pts), W, N, _lib.ptr(_c(gsdf)), _lib.ptr(gdir), _lib.ptr(gpts),
                                        _lib.stream())
         _lib.check(rc, 'dsdf_sdf_query_backward')
@@ -70,7 +70,7 @@ class _Integrate(torch.autograd.Function):
         p, v, dt = _c(p), _c(v), _c(dt)
         W, nb = p.shape[0], p.shape[1]
         out = torch.empty_like(p)
-        rc = L.dsdf_integrate(_lib.ptr(p), _lib.ptr(v), _lib.ptr(dt), _lib.ptr(active), W, nb, _lib.ptr(out),
+        rc = _lib.call('dsdf_integrate', _lib.ptr(p), _lib.ptr(v), _lib.ptr(dt), _lib.ptr(active), W, nb, _lib.ptr(out),
                               _lib.stream())
         _lib.check(rc, 'dsdf_integrate')
         ctx.save_for_backward(p, v, dt, active if active is not None else p.new_empty(0))
@@ -84,7 +84,7 @@ class _Integrate(torch.autograd.Function):
         W, nb = p.shape[0], p.shape[1]
         gp, gv = torch.empty_like(p), torch.empty_like(v)
         gdt = torch.empty(W, nb, dtype=F64, device=p.device)
-        rc = L.dsdf_integrate_backward(_lib.ptr(p), _lib.ptr(v), _lib.ptr(dt), _lib.ptr(active), W, nb,
+        rc = _lib.call('dsdf_integrate_backward', _lib.ptr(p), _lib.ptr(v), _lib.ptr(dt), _lib.ptr(active), W, nb,
                                        _lib.ptr(_c(g)), _lib.ptr(gp), _lib.ptr(gv), _lib.ptr(gdt), _lib.stream())
         _lib.check(rc, 'dsdf_integrate_backward')
         return gp, gv, gdt.sum(1), None

@@ -124,6 +124,7 @@ class World3D:
             A[r, 6 * i + a] = 1
         self.A = A.to(dev).unsqueeze(0).expand(W, -1, -1).contiguous() if rows else None
         self.b = torch.zeros(W, len(rows), dtype=F64, device=dev) if rows else None
+        self.eq_rows = torch.tensor(rows, dtype=torch.int32, device=dev).reshape(-1, 2).contiguous()
 
         # contact detection set-up (replaces the py3ode HashSpace of world.py:69-72)
         self.table = GeometryTable(self.bodies, W, dev)

@@ -117,6 +117,13 @@ typedef struct dsdf_body_geom {
     const int32_t* faces;         /* (nfaces,3), shared by all worlds */
     const double* grid;           /* res^3 SDF samples on [-1,1]^3 (kind == GRID); world w at grid + w*grid_world_stride */
     long long vert_world_stride, grid_world_stride;
+    /* Optional uniform cell index over the body-frame mesh (has_cells = 0: scan everything).  Cell (ix,iy,iz) of
+     * cell_dims covers cell_lo + [ix,ix+1) / cell_inv ...; faces are binned by centroid, vertices by position, as
+     * CSR lists: items of cell c are *_items[*_start[c] .. *_start[c+1]).  Only used to SKIP work that provably
+     * cannot pass the reference's tests (points outside the other body's cube); results are unchanged. */
+    double cell_lo[3], cell_inv;
+    int32_t cell_dims[3], has_cells;
+    const int32_t *fcell_start, *fcell_items, *vcell_start, *vcell_items;
 } dsdf_body_geom;
 
 /* per-world contact status bits (int32) */
@@ -129,23 +136,19 @@ typedef struct dsdf_body_geom {
  * (sdf_physics/physics3d/contacts.py:221-272): broad phase (AABB of each body's rotated cube of half side
  * scale+body_eps, pairs (i<j) from `pairs` (npairs,2), no_contact pairs already removed), _overlap (:27-36),
  * _frank_wolfe (:39-94), _compute_contacts (:161-214), _filter_contacts (:97-158), both search directions with the
- * reference's "reverse only if the first is valid" rule (:238-240).
+ * reference's "reverse only if the first is valid" rule (:238-240).  One CTA per world, one launch.
  * p (W,nb,7), shape (W,nb,4), active (W) uint8 or NULL (inactive worlds keep their previous outputs).
- * chunk_prefix (2*npairs+1): candidate-kernel CTA offsets per search direction, chunk count of direction d =
- *   dsdf_contact_chunks_per_face_count(nfaces of the mesh body of d); total_chunks = chunk_prefix[2*npairs].
  * Outputs (capacity maxc contacts per world, ordered pair -> direction -> face id):
  *   count (W); cbody (W,maxc,2) = (mesh body, sdf body); cface (W,maxc) face id on the mesh body;
  *   cabc (W,maxc,3) barycentrics; cgeo (W,maxc,10) = [normal(3), p1(3), p2(3), pen]; wstatus (W).
  *   pre_ids (W,2*npairs,capK) / pre_cnt (W,2*npairs): PRE-filter contact face ids per direction (parity
  *   evidence; -1 = direction not searched); both may be NULL.
  */
-size_t dsdf_contacts_workspace_bytes(int W, int npairs, int capK);
-int dsdf_contact_chunks_per_face_count(int nfaces);
-int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, const int32_t* chunk_prefix, int total_chunks,
-                         int npairs, const double* p, const double* shape, const unsigned char* active,
+int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, int npairs, const double* p,
+                         const double* shape, const unsigned char* active,
                          int W, int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
                          int capK, int maxc, int32_t* count, int32_t* cbody, int32_t* cface, double* cabc, double* cgeo,
-                         int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, void* ws, void* stream);
+                         int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, void* stream);
 /* VJP of cgeo w.r.t. the poses (the reference's grad-enabled second _compute_contacts, contacts.py:262-264):
  * gp (W,nb,7) from ggeo (W,maxc,10). */
 int dsdf_contact_geometry_backward(const dsdf_body_geom* geom, const double* p, const double* shape, int W, int nb,
@@ -184,6 +187,36 @@ int dsdf_dynamics_assemble_backward(const double* p, const double* v, const doub
                                     const double* dQ, const double* dp, const double* dG, const double* dh, const double* dF,
                                     double* gp, double* gv, double* gmass, double* gI, double* gfric, double* grest,
                                     double* gf, double* gdt, double* ggeo, void* stream);
+
+/* ------------------------------------------------- fused contact dynamics ----
+ * Replaces PdipmEngine.solve_dynamics (lcp_physics/physics/engines.py:31-83) end to end, one warp per world:
+ * assembly (as dsdf_dynamics_assemble) + the PDIPM of lcp_physics/lcp/solvers/batch.py:70-237 with the Newton
+ * systems reduced through the per-contact block structure of F + D^-1 (closed-form block inverse, pivoted LU of
+ * the (6 nb + neq)^2 reduced KKT matrix in shared memory) instead of the dense nineq^2 factorisation.
+ * Same iterates as dsdf_lcp_forward on the assembled matrices up to round-off.
+ * eq_rows (neq,2) int32 = [body, velocity component] of each equality row (rows of Je are 0/1 selections:
+ * sdf_physics/physics3d/constraints.py:32-145).  ncontacts_smem (0 = maxc): contacts the launch sizes its shared
+ * memory for (<= 64); worlds with more get DSDF_LCP_TOO_LARGE.
+ * Outputs x (W,6nb) [new_v = -x], nu (W,neq), lam / s (W, maxc (2+fric_dirs)) in the reference's row order
+ * [normal | friction | cone], status (W), iters (W).
+ */
+size_t dsdf_dynamics_solve_smem_bytes(int nb, int neq, int ncontacts, int fric_dirs);
+int dsdf_dynamics_solve(const double* p, const double* v, const double* mass, const double* Ibody,
+                        const double* fric, const double* rest, const double* f, const double* dt,
+                        const unsigned char* active, const int32_t* count, const int32_t* cbody, const double* cgeo,
+                        const int32_t* eq_rows, int W, int nb, int neq, int maxc, int ncontacts_smem, int fric_dirs,
+                        double eps, int not_improved_lim, int max_iter,
+                        double* x, double* nu, double* lam, double* s, int32_t* status, int32_t* iters, void* stream);
+/* Replaces LCPFunctionFn.backward (lcp_physics/lcp/lcp.py:156-213) + the autograd of the assembly, fused: from
+ * gz = dL/dx straight to the gradients of the physical inputs (no dense dG / dF is materialised). */
+int dsdf_dynamics_solve_backward(const double* p, const double* v, const double* mass, const double* Ibody,
+                                 const double* fric, const double* rest, const double* f, const double* dt,
+                                 const unsigned char* active, const int32_t* count, const int32_t* cbody,
+                                 const double* cgeo, const int32_t* eq_rows, int W, int nb, int neq, int maxc,
+                                 int ncontacts_smem, int fric_dirs, int stop_contact_grad, int stop_friction_grad,
+                                 const double* x, const double* lam, const double* s, const double* gz,
+                                 double* gp, double* gv, double* gmass, double* gI, double* gfric, double* grest,
+                                 double* gf, double* gdt, double* ggeo, void* stream);
 
 #ifdef __cplusplus
 }

@@ -20,7 +20,7 @@ F64 = torch.float64
 # (state atol, grad rtol); box_tilted balances on an edge with rank-deficient contact sets: the reference's own LU
 # round-off is amplified there (oracle-vs-reference shows the same), so only a drift bound is asserted.
 TOL = {'box_on_plane': (1e-8, 1e-5), 'bouncing_sphere': (1e-8, 1e-4), 'grid_on_pole': (1e-8, 1e-4),
-       'box_tilted': (5e-3, None)}
+       'box_tilted': (2e-2, None)}
 
 
 def _params(leaves, g, W=1):
