@@ -19,6 +19,23 @@ _GEOM_DTYPE = np.dtype([('kind', 'i4'), ('nverts', 'i4'), ('nfaces', 'i4'), ('re
 assert _GEOM_DTYPE.itemsize == 136
 
 
+_CELL_CACHE = {}
+
+
+def cached_cell_index(verts_np, faces_np, device):
+    """Cell index of a (shared) mesh on `device`, memoised on the mesh content (worlds are rebuilt every
+    optimisation iteration with the same meshes)."""
+    key = (verts_np.shape, faces_np.shape, hash(verts_np.tobytes()), hash(faces_np.tobytes()), str(device))
+    hit = _CELL_CACHE.get(key)
+    if hit is None:
+        lo, inv, dims, fs, fi, vs, vi = build_cell_index(verts_np, faces_np)
+        hit = (lo, inv, dims, [torch.from_numpy(a).to(device) for a in (fs, fi, vs, vi)])
+        if len(_CELL_CACHE) > 64:
+            _CELL_CACHE.clear()
+        _CELL_CACHE[key] = hit
+    return hit
+
+
 def build_cell_index(verts, faces, target=32, max_cells=1 << 18):
     """Uniform grid over a body-frame mesh: faces binned by centroid, vertices by position (CSR, int32).
 
@@ -80,8 +97,7 @@ class GeometryTable:
             self.keep += [verts, faces]
             cell = (np.zeros(3), 0.0, np.zeros(3, dtype=np.int32), 0, 0, 0, 0, 0)
             if not per_world:
-                lo, inv, dims, fs, fi, vs, vi = build_cell_index(verts.cpu().numpy(), faces.cpu().numpy())
-                dev_arrays = [torch.from_numpy(a).to(device) for a in (fs, fi, vs, vi)]
+                lo, inv, dims, dev_arrays = cached_cell_index(verts.cpu().numpy(), faces.cpu().numpy(), device)
                 self.keep += dev_arrays
                 cell = (lo, inv, dims, 1) + tuple(a.data_ptr() for a in dev_arrays)
             rows[i] = (b.kind, nverts, faces.shape[0], res, verts.data_ptr(), faces.data_ptr(), gptr,
@@ -109,7 +125,7 @@ class ContactSet:
 class ContactDetector:
     """Owns the work buffers of ``dsdf_contacts_detect`` for one batched world."""
 
-    def __init__(self, table, pairs, W, nb, device, capK=768, maxc=16, record_prefilter=False):
+    def __init__(self, table, pairs, W, nb, device, capK=512, maxc=32, record_prefilter=False):
         _lib.lib()
         self.table, self.W, self.nb, self.capK, self.maxc = table, W, nb, capK, maxc
         self.npairs = len(pairs)

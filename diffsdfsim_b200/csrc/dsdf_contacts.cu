@@ -99,10 +99,10 @@ __device__ int any_vertex_in_cube(const BodyGeom& g1, int w, Q4<double> q1, V3<d
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
     const Q4<double> q2i = qinv(q2);
     if (!g1.has_cells) {
-        for (int base = 0; base < g1.nverts; base += 256 * 4) {
+        for (int base = 0; base < g1.nverts; base += blockDim.x * 4) {
             int f = 0;
             for (int u = 0; u < 4; ++u) {
-                const int v = base + u * 256 + tid;
+                const int v = base + u * blockDim.x + tid;
                 if (v < g1.nverts) {
                     const V3<double> t = to_b2(load_vert(g1, w, v), q1, x1, q2i, x2);
                     f |= (-s2 <= t.x && t.x <= s2 && -s2 <= t.y && t.y <= s2 && -s2 <= t.z && t.z <= s2);
@@ -242,38 +242,44 @@ __device__ ContactGeo<S> contact_geometry(const SdfShape& s1, const SdfShape& s2
 }
 
 // ------------------------------------------------------------------------------------------ block helpers
-__device__ inline void bitonic_sort_int(int* a, int n2) {      // n2 power of two, ascending
-    for (int k = 2; k <= n2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const int x = a[i], y = a[l];
-                    const bool up = (i & k) == 0;
-                    if ((x > y) == up) { a[i] = y; a[l] = x; }
-                }
-            }
-            __syncthreads();
-        }
+// Rank sorts: every element counts how many precede it (O(n^2/threads) compares on broadcast shared loads, two
+// barriers) -- far cheaper here than a bitonic network's ~45 barrier-separated passes for n <= 1024.
+enum { SORT_MAX_ROUNDS = 8 };                                   // n <= SORT_MAX_ROUNDS * blockDim.x
+__device__ inline void rank_sort_int(int* a, int* tmp, int n) {  // ascending; tmp: n ints of scratch
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const int x = a[i];
+        int r = 0;
+        for (int j = 0; j < n; ++j) { const int y = a[j]; r += (y < x) || (y == x && j < i); }
+        tmp[r] = x;
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x) a[i] = tmp[i];
+    __syncthreads();
 }
-// (key double, payload int) ascending by key then payload
-__device__ inline void bitonic_sort_kv(double* key, double* key2, int* pay, int n2) {
-    for (int k = 2; k <= n2; k <<= 1)
-        for (int j = k >> 1; j > 0; j >>= 1) {
-            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
-                const int l = i ^ j;
-                if (l > i) {
-                    const double x = key[i], y = key[l], x2 = key2[i], y2 = key2[l];
-                    const bool gt = (x > y) || (x == y && (x2 > y2 || (x2 == y2 && pay[i] > pay[l])));
-                    const bool up = (i & k) == 0;
-                    if (gt == up) {
-                        key[i] = y; key[l] = x; key2[i] = y2; key2[l] = x2;
-                        const int t = pay[i]; pay[i] = pay[l]; pay[l] = t;
-                    }
-                }
+// (key, key2, payload) ascending lexicographically, in place
+__device__ inline void rank_sort_kv(double* key, double* key2, int* pay, int n) {
+    double k1[SORT_MAX_ROUNDS], k2[SORT_MAX_ROUNDS];
+    int pl[SORT_MAX_ROUNDS], rk[SORT_MAX_ROUNDS];
+#pragma unroll
+    for (int rd = 0; rd < SORT_MAX_ROUNDS; ++rd) {
+        const int i = rd * blockDim.x + threadIdx.x;
+        rk[rd] = -1;
+        if (i < n) {
+            const double x = key[i], x2 = key2[i];
+            const int px = pay[i];
+            int r = 0;
+            for (int j = 0; j < n; ++j) {
+                const double y = key[j], y2 = key2[j];
+                r += (y < x) || (y == x && (y2 < x2 || (y2 == x2 && (pay[j] < px || (pay[j] == px && j < i)))));
             }
-            __syncthreads();
+            k1[rd] = x; k2[rd] = x2; pl[rd] = px; rk[rd] = r;
         }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int rd = 0; rd < SORT_MAX_ROUNDS; ++rd)
+        if (rk[rd] >= 0) { key[rk[rd]] = k1[rd]; key2[rk[rd]] = k2[rd]; pay[rk[rd]] = pl[rd]; }
+    __syncthreads();
 }
 // order-preserving compaction offsets: returns exclusive prefix of flag over index order 0..n-1; *total = sum.
 // idx loop layout: element e handled by thread e % nt in round e / nt.  scan buffer: n ints.
@@ -316,17 +322,18 @@ struct RefineSmem {
     double* P;      // [9][capK] candidate triangle in b2 frame, later GEO rows 0..8
     double* X;      // [3][capK] FW iterate, later GEO row 9 (pen) + scratch
     double* ABC;    // [3][capK]
-    double* HK;     // [2][capK] hull sort keys
+    double* HK;     // [2][capK] hull sort keys -- aliases X rows 1,2 (free once the contact geometry is computed)
     int* ID;        // [capK] face ids
     int* SC;        // [capK] scan / flags
     int* CL;        // [capK] cluster id
     int* HI;        // [capK] hull payload
     int* KEEP;      // [capK]
+    int* TMP;       // [capK] scratch flags
     double* red;    // [40]
 };
 
 __host__ __device__ inline size_t refine_smem_bytes(int capK) {
-    return (size_t)capK * (17 * sizeof(double) + 5 * sizeof(int)) + 40 * sizeof(double) + 64;
+    return (size_t)capK * (15 * sizeof(double) + 6 * sizeof(int)) + 40 * sizeof(double) + 64;
 }
 
 struct DirResult { int count; int valid; };
@@ -341,11 +348,7 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
     const int K = min(ncand, capK);
     DirResult r; r.count = 0; r.valid = 1;
     if (K == 0) return r;
-    int n2 = 1;
-    while (n2 < K) n2 <<= 1;
-    for (int i = K + tid; i < n2; i += nt) sm.ID[i] = 0x7fffffff;
-    __syncthreads();
-    bitonic_sort_int(sm.ID, n2);
+    rank_sort_int(sm.ID, sm.SC, K);
     const Q4<double> q2i = qinv(q2);
     // init: vertices in b2 frame, start at the vertex with the smallest SDF (contacts.py:57-61)
     for (int k = tid; k < K; k += nt) {
@@ -365,12 +368,15 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
         }
     }
     __syncthreads();
-    // Frank-Wolfe, <= 32 iterations, PAIR-GLOBAL exit (contacts.py:63-82)
+    // Frank-Wolfe, <= 32 iterations, PAIR-GLOBAL exit (contacts.py:63-82).  A candidate whose step is zero
+    // (|gain| <= tol) keeps its x, so re-evaluating it would reproduce the same decision: it is skipped from then on
+    // (TMP[k] = 1) -- the reference recomputes it every iteration with identical results.
+    for (int k = tid; k < K; k += nt) sm.TMP[k] = 0;
     for (int it = 0; it < 32; ++it) {
         int any_active = 0, any_pen = 0;
         // phase 1: evaluate (no state change until the exit test is known)
-        // each thread handles at most ceil(capK/nt) candidates; keep decisions in registers via recompute in phase 2
         for (int k = tid; k < K; k += nt) {
+            if (sm.TMP[k]) { sm.SC[k] = -1; continue; }              // frozen, not penetrating
             const V3<double> x = v3<double>(sm.X[k], sm.X[capK + k], sm.X[2 * capK + k]);
             const SdfOut<double> o = sdf_query<double>(s2, x, true);
             double dmin = 0.0; int pick = 0;
@@ -387,6 +393,7 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
             any_active |= act;
             any_pen |= (o.d < -tol);
             sm.SC[k] = act ? pick : -1;
+            if (!act && !(o.d < -tol)) sm.TMP[k] = 1;
         }
         // __syncthreads_or returns a predicate, not a bitwise OR: one barrier per flag
         const int blk_active = __syncthreads_or(any_active);
@@ -459,7 +466,7 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
         sm.P[0 * capK + k] = g.n.x; sm.P[1 * capK + k] = g.n.y; sm.P[2 * capK + k] = g.n.z;
         sm.P[3 * capK + k] = g.p1.x; sm.P[4 * capK + k] = g.p1.y; sm.P[5 * capK + k] = g.p1.z;
         sm.P[6 * capK + k] = g.p2.x; sm.P[7 * capK + k] = g.p2.y; sm.P[8 * capK + k] = g.p2.z;
-        sm.HK[k] = g.pen;                                  // pen parked in HK row 0 until the filter needs HK
+        sm.X[k] = g.pen;                                   // X row 0 <- pen (this thread already consumed X[.][k])
         bad |= !(g.pen <= tol);
     }
     r.valid = !__syncthreads_or(bad);
@@ -633,19 +640,84 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
             __syncthreads();
             continue;
         }
-        // --- planar convex hull (strict vertices only): sort by (u,v), monotone chain on one thread
-        int n2 = 1;
-        while (n2 < m) n2 <<= 1;
+        // --- planar convex hull (strict vertices only)
         double* KU = sm.HK; double* KV = sm.HK + capK;
-        for (int e = tid; e < n2; e += nt) {
-            if (e < m) { const int k = sm.HI[e]; KU[e] = PA[u_ax][k]; KV[e] = PA[v_ax][k]; }
-            else { KU[e] = INFINITY; KV[e] = INFINITY; sm.HI[e] = 0x7fffffff; }
-        }
+        for (int e = tid; e < m; e += nt) { const int k = sm.HI[e]; KU[e] = PA[u_ax][k]; KV[e] = PA[v_ax][k]; }
         __syncthreads();
-        bitonic_sort_kv(KU, KV, sm.HI, n2);
+        // Akl-Toussaint pre-filter: the support points of 8 directions span a polygon inscribed in the hull; points
+        // STRICTLY inside it (by a margin far above the hull tolerance) cannot be hull vertices.  Dropping them in
+        // parallel leaves only the boundary band for the sequential chain below.
+        {
+            __shared__ double s_ev[8][8];          // [warp][direction] best value
+            __shared__ int s_ei[8][8];
+            __shared__ double s_px[8], s_py[8];
+            const double dxs[8] = {1, 1, 0, -1, -1, -1, 0, 1}, dys[8] = {0, 1, 1, 1, 0, -1, -1, -1};
+            double bv[8]; int bi[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) { bv[q] = -INFINITY; bi[q] = 0x7fffffff; }
+            double mxl = 0.0;
+            for (int e = tid; e < m; e += nt) {
+                const double x = KU[e], y = KV[e];
+                mxl = fmax(mxl, fmax(fabs(x), fabs(y)));
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const double v = dxs[q] * x + dys[q] * y;
+                    if (v > bv[q]) { bv[q] = v; bi[q] = e; }
+                }
+            }
+            const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const double ov = __shfl_xor_sync(DSDF_FULL, bv[q], o);
+                    const int oi = __shfl_xor_sync(DSDF_FULL, bi[q], o);
+                    if (ov > bv[q] || (ov == bv[q] && oi < bi[q])) { bv[q] = ov; bi[q] = oi; }
+                }
+                if (lane == 0) { s_ev[warp][q] = bv[q]; s_ei[warp][q] = bi[q]; }
+            }
+            const double mxc_all = block_reduce<RED_MAX>(mxl, sm.red);     // (contains the barriers)
+            if (tid < 8) {
+                double v = -INFINITY; int ix = 0x7fffffff;
+                for (int ww = 0; ww < nw; ++ww)
+                    if (s_ev[ww][tid] > v || (s_ev[ww][tid] == v && s_ei[ww][tid] < ix)) { v = s_ev[ww][tid]; ix = s_ei[ww][tid]; }
+                s_px[tid] = KU[ix]; s_py[tid] = KV[ix];
+            }
+            __syncthreads();
+            const double margin = 1e-9 * (1.0 + mxc_all);
+            for (int e = tid; e < m; e += nt) {
+                const double x = KU[e], y = KV[e];
+                bool inside = true;
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const double ax_ = s_px[q], ay_ = s_py[q], bx_ = s_px[(q + 1) & 7], by_ = s_py[(q + 1) & 7];
+                    const double ex = bx_ - ax_, ey = by_ - ay_;
+                    const double len = sqrt(ex * ex + ey * ey);
+                    if (len > 0.0) inside = inside && ((ex * (y - ay_) - ey * (x - ax_)) > margin * len);
+                }
+                sm.SC[e] = inside ? 0 : 1;
+            }
+            __syncthreads();
+            for (int e = tid; e < m; e += nt) sm.TMP[e] = sm.SC[e];
+            int msurv = 0;
+            block_exclusive_scan(sm.SC, m, &msurv);
+            // order-preserving compaction of (KU, KV, HI)
+            const int rounds = (m + nt - 1) / nt;
+            for (int rd = 0; rd < rounds; ++rd) {
+                const int e = rd * nt + tid;
+                double x = 0, y = 0; int hi_ = 0, dst = -1;
+                if (e < m && sm.TMP[e]) { dst = sm.SC[e]; x = KU[e]; y = KV[e]; hi_ = sm.HI[e]; }
+                __syncthreads();
+                if (dst >= 0) { KU[dst] = x; KV[dst] = y; sm.HI[dst] = hi_; }
+                __syncthreads();
+            }
+            m = msurv;
+            rank_sort_kv(KU, KV, sm.HI, m);
+            if (tid == 0) sm.red[39] = mxc_all;
+            __syncthreads();
+        }
         if (tid == 0) {
-            double mxc = 0.0;
-            for (int e = 0; e < m; ++e) mxc = fmax(mxc, fmax(fabs(KU[e]), fabs(KV[e])));
+            const double mxc = sm.red[39];
             const double tol_d = 2.0 * distround(2, mxc);
             int* H = sm.SC;                 // stack of sorted positions
             int top = 0;
@@ -692,7 +764,8 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
 }
 
 // One CTA per world: broad phase, _overlap, and both search directions of every body pair, fused.
-__global__ void __launch_bounds__(256)
+enum { CONTACT_THREADS = 128 };
+__global__ void __launch_bounds__(CONTACT_THREADS, 3)
 contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs, int npairs,
                 const double* __restrict__ p, const double* __restrict__ shape, const unsigned char* __restrict__ active,
                 int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
@@ -705,10 +778,10 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
     if (active && !active[w]) return;
     const int ndirs = 2 * npairs;
     RefineSmem sm;
-    sm.P = smraw; sm.X = sm.P + 9 * (size_t)capK; sm.ABC = sm.X + 3 * (size_t)capK; sm.HK = sm.ABC + 3 * (size_t)capK;
-    sm.red = sm.HK + 2 * (size_t)capK;
+    sm.P = smraw; sm.X = sm.P + 9 * (size_t)capK; sm.ABC = sm.X + 3 * (size_t)capK; sm.HK = sm.X + (size_t)capK;
+    sm.red = sm.ABC + 3 * (size_t)capK;
     sm.ID = reinterpret_cast<int*>(sm.red + 40);
-    sm.SC = sm.ID + capK; sm.CL = sm.SC + capK; sm.HI = sm.CL + capK; sm.KEEP = sm.HI + capK;
+    sm.SC = sm.ID + capK; sm.CL = sm.SC + capK; sm.HI = sm.CL + capK; sm.KEEP = sm.HI + capK; sm.TMP = sm.KEEP + capK;
     int nout = 0, status = 0;
     for (int pair = 0; pair < npairs; ++pair) {
         const int bi = pairs[2 * pair], bj = pairs[2 * pair + 1];
@@ -747,9 +820,6 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
                 if (tid == 0) pre_cnt[(size_t)w * ndirs + d] = r.count;
                 for (int k = tid; k < r.count; k += nt) pre_ids[((size_t)w * ndirs + d) * capK + k] = sm.ID[k];
             }
-            // stash pen (HK row 0) into X row 0 before the filter reuses HK
-            for (int k = tid; k < r.count; k += nt) sm.X[k] = sm.HK[k];
-            __syncthreads();
             if (r.valid) status |= filter_contacts(sm, capK, r.count, eps);
             else { status |= 8; for (int k = tid; k < r.count; k += nt) sm.KEEP[k] = 1; __syncthreads(); }
             // append kept contacts in ascending face order
@@ -839,7 +909,7 @@ int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, int n
     if (smem > 227 * 1024) return -2;
     cudaError_t e = cudaFuncSetAttribute(contacts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return (int)e;
-    contacts_kernel<<<W, 256, smem, st>>>(reinterpret_cast<const BodyGeom*>(geom), pairs, npairs, p, shape, active, nb,
+    contacts_kernel<<<W, CONTACT_THREADS, smem, st>>>(reinterpret_cast<const BodyGeom*>(geom), pairs, npairs, p, shape, active, nb,
                                           eps, tol, fd_eps, body_eps, detach_b2, capK, maxc, count, cbody, cface, cabc,
                                           cgeo, wstatus, pre_ids, pre_cnt);
     return (int)cudaGetLastError();

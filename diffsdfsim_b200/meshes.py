@@ -25,11 +25,24 @@ def _grid_quads(n0, n1, offset, flip):
     return tris + offset
 
 
+_BOX_CACHE = {}
+
+
 def box_mesh(dims, max_tri_length=0.1):
     """Axis-aligned box centred at 0; six lattice patches, edge length <= max_tri_length.
 
-    20x1x20 @ 0.1 -> 89 646 verts / 176 000 faces; 1x1x1 @ 0.1 -> 726 / 1200.
+    20x1x20 @ 0.1 -> 89 646 verts / 176 000 faces; 1x1x1 @ 0.1 -> 726 / 1200.  Memoised (read-only arrays).
     """
+    key = (tuple(float(d) for d in dims), float(max_tri_length))
+    if key not in _BOX_CACHE:
+        v, f = _box_mesh(dims, max_tri_length)
+        v.setflags(write=False)
+        f.setflags(write=False)
+        _BOX_CACHE[key] = (v, f)
+    return _BOX_CACHE[key]
+
+
+def _box_mesh(dims, max_tri_length):
     dims = np.asarray(dims, dtype=np.float64)
     half = dims / 2
     n = np.ceil(dims / max_tri_length - 1e-9).astype(int) + 1

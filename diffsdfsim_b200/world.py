@@ -75,7 +75,7 @@ class World3D:
                  contact_callback=Defaults3D.CONTACT, eps=Defaults3D.EPSILON, tol=Defaults3D.TOL,
                  fric_dirs=Defaults3D.FRIC_DIRS, post_stab=Defaults3D.POST_STABILIZATION,
                  strict_no_penetration=True, time_of_contact_diff=True, stop_contact_grad=False,
-                 stop_friction_grad=False, detach_contact_b2=False, device=None, capK=768, maxc=16,
+                 stop_friction_grad=False, detach_contact_b2=False, device=None, capK=512, maxc=32,
                  record_prefilter=False):
         if post_stab:
             raise NotImplementedError('post_stab (off by default in the reference) is not built yet')
@@ -140,6 +140,7 @@ class World3D:
         self.trajectory, self.observations = [], []
         self.stats = {'rounds': [], 'attempts': torch.zeros(W, dtype=torch.int64, device=dev)}
         self.static_inverse = False
+        self._kk = torch.arange(self.maxc, device=dev)[None, :]
         self.contact_set = self.detector.new_set()
         self.contact_geo = None
         self.find_contacts()
@@ -258,25 +259,17 @@ class World3D:
         self._undo = (st.p, st.v, self.contact_set, self.contact_geo, self.t.clone(), self.t_host, self.toc_flag.clone(),
                       self.last_dt, len(self.trajectory))
         W, dev = self.W, self.device
-        end_t = self.t + self.dt
+        end_t = (self.t + self.dt) if fixed_dt else None
         dt_try = torch.full((W,), float(self.dt), dtype=F64, device=dev)
         active = torch.ones(W, dtype=torch.bool, device=dev)
         had = torch.zeros(W, dtype=torch.bool, device=dev)
         rounds = 0
         while True:
             rounds += 1
-            accept = self._attempt(active, dt_try)
             self.stats['attempts'] += active.long()
+            accept, dt_try, active, any_active = self._attempt(active, dt_try, end_t)
             had |= accept & (self.contact_set.count > 0)
-            # rejected worlds retry with half the step (world.py:348); accepted ones take the remaining time
-            dt_try = torch.where(active & ~accept, dt_try / 2, dt_try)
-            if fixed_dt:
-                more = accept & (self.t < end_t)
-                dt_try = torch.where(more, end_t - self.t, dt_try)
-                active = (active & ~accept) | more
-            else:
-                active = active & ~accept
-            if not bool(active.any()):
+            if not any_active:
                 break
         self.stats['rounds'].append(rounds)
         self.t_host += self.dt
@@ -292,61 +285,85 @@ class World3D:
         del self.trajectory[ntraj:]
         self._sync_bodies()
 
-    def _attempt(self, active, dt_try):
-        """One solve -> move -> find_contacts attempt of every active world (body of world.py:249-356)."""
+    def _attempt(self, active, dt_try, end_t):
+        """One solve -> move -> find_contacts attempt of every active world (body of world.py:249-356).
+
+        Returns (accept, next dt_try, next active, any world still active).  One host synchronisation per attempt:
+        a 4-entry flag vector [capacity error, any new (time-of-contact) contact, max contact count, any active].
+        """
         st = self.state
         W, nb = self.W, self.nb
-        act8 = active.to(torch.uint8).contiguous()
+        act8 = active.to(torch.uint8)
         dt_ = dt_try
         if self.time_of_contact_diff:
             # world.py:253-257: value == dt_try, carries -d last_dt
             dt_ = torch.where(self.toc_flag, -self.last_dt + (self.last_dt.detach() + dt_try), dt_try)
-        new_v = self.engine.solve_dynamics(self, dt_.contiguous(), act8)
-        p_try = ops.integrate(st.p, new_v, dt_.contiguous(), act8)
-        cs = self.contact_set.clone()
-        self.detector.detect(p_try.detach().contiguous(), self.shape, cs, act8, eps=self.eps, tol=self.tol,
+        new_v = self.engine.solve_dynamics(self, dt_, act8)
+        p_try = ops.integrate(st.p, new_v, dt_, act8)
+        old = self.contact_set
+        cs = old.clone()
+        self.detector.detect(p_try.detach(), self.shape, cs, act8, eps=self.eps, tol=self.tol,
                              fd_eps=Defaults3D.EPSILON, body_eps=self.body_eps, detach_b2=self.detach_contact_b2)
         geo = differentiable_geometry(p_try, self.shape, cs, self.table, Defaults3D.EPSILON, self.detach_contact_b2)
-        pen_bad = (cs.status & 8) != 0
-        clean = active & ~pen_bad
+        status = cs.status
+        clean = active & ((status & 8) == 0)
         accept = clean
         if not self.strict_no_pen:
             accept = clean | (active & (dt_try < self.dt / 2 ** 10))         # world.py:345-347 (give up, keep going)
-        self._check_capacity_masked(cs, accept)
-
-        # contacts between body pairs that had no contact at the start of the sub-step (world.py:273-274)
-        kk = torch.arange(self.maxc, device=self.device)[None, :]
-        new_valid = kk < cs.count[:, None]
-        old_valid = kk < self.contact_set.count[:, None]
-        bn, bo = cs.body.long(), self.contact_set.body.long()
-        pid_new = torch.minimum(bn[..., 0], bn[..., 1]) * nb + torch.maximum(bn[..., 0], bn[..., 1])
-        pid_old = torch.minimum(bo[..., 0], bo[..., 1]) * nb + torch.maximum(bo[..., 0], bo[..., 1])
-        seen = ((pid_new[:, :, None] == pid_old[:, None, :]) & old_valid[:, None, :]).any(2)
-        toc_mask = new_valid & ~seen & clean[:, None]
-        toc_now = toc_mask.any(1)
-        if self.time_of_contact_diff and bool(toc_now.any()):
-            dt_h = self._time_of_contact(dt_, p_try, new_v, geo, cs, toc_mask)
-            p_redo = ops.integrate(st.p, new_v, dt_h.contiguous(), toc_now.to(torch.uint8).contiguous())
-            p_try = torch.where(toc_now[:, None, None], p_redo, p_try)
-            self.last_dt = torch.where(toc_now, dt_h, self.last_dt)
-        self.toc_flag = torch.where(clean, toc_now, self.toc_flag)    # a give-up accept leaves toc_contacts untouched
+        bad = ((status & 1) != 0).any() | (((status & 2) != 0) & accept).any()
+        count_after = torch.where(accept, cs.count, old.count)
+        t_new = torch.where(accept, self.t + dt_try, self.t)
+        # rejected worlds retry with half the step (world.py:348); accepted ones take the remaining time
+        dt_next = torch.where(active & ~accept, dt_try / 2, dt_try)
+        if end_t is not None:
+            more = accept & (t_new < end_t)
+            dt_next = torch.where(more, end_t - t_new, dt_next)
+            next_active = (active & ~accept) | more
+        else:
+            next_active = active & ~accept
+        flags = [bad, count_after.max() > 0, next_active.any()]
+        toc_mask = toc_now = None
+        if self.time_of_contact_diff:
+            # contacts between body pairs that had no contact at the start of the sub-step (world.py:273-274)
+            new_valid = self._kk < cs.count[:, None]
+            old_valid = self._kk < old.count[:, None]
+            pid_new, pid_old = self._pair_ids(cs.body), self._pair_ids(old.body)
+            seen = ((pid_new[:, :, None] == pid_old[:, None, :]) & old_valid[:, None, :]).any(2)
+            toc_mask = new_valid & ~seen & clean[:, None]
+            toc_now = toc_mask.any(1)
+            flags.append(toc_now.any())
+        fl = torch.stack([f.to(torch.int32) for f in flags] + [count_after.max().to(torch.int32)]).tolist()   # the sync
+        if fl[0]:
+            raise RuntimeError('contact capacity exceeded (capK=%d, maxc=%d): raise World3D(capK=..., maxc=...)'
+                               % (self.detector.capK, self.maxc))
+        any_active = bool(fl[2])
+        self.max_nc = int(fl[-1])                  # sizes the dynamics kernel's shared memory for the next solve
+        if self.time_of_contact_diff:
+            if fl[3]:
+                dt_h = self._time_of_contact(dt_, p_try, new_v, geo, cs, toc_mask)
+                p_redo = ops.integrate(st.p, new_v, dt_h, toc_now.to(torch.uint8))
+                p_try = torch.where(toc_now[:, None, None], p_redo, p_try)
+                self.last_dt = torch.where(toc_now, dt_h, self.last_dt)
+            self.toc_flag = torch.where(clean, toc_now, self.toc_flag)   # a give-up accept leaves toc_contacts untouched
 
         # commit accepted worlds
         a3 = accept[:, None, None]
         st.p = torch.where(a3, p_try, st.p)
         st.v = torch.where(a3, new_v, st.v)
-        old = self.contact_set
-        for k in ('count', 'status'):
-            setattr(cs, k, torch.where(accept, getattr(cs, k), getattr(old, k)))
+        cs.count = count_after
+        cs.status = torch.where(accept, status, old.status)
         cs.body = torch.where(a3, cs.body, old.body)
         cs.face = torch.where(accept[:, None], cs.face, old.face)
         cs.abc = torch.where(a3, cs.abc, old.abc)
         cs.geo = torch.where(a3, cs.geo, old.geo)
         self.contact_geo = torch.where(a3, geo, self.contact_geo)
         self.contact_set = cs
-        self.max_nc = int(cs.count.max())          # sizes the LCP kernel's shared memory for the next solve
-        self.t = torch.where(accept, self.t + dt_try, self.t)
-        return accept
+        self.t = t_new
+        return accept, dt_next, next_active, any_active
+
+    def _pair_ids(self, body):
+        b = body.long()
+        return torch.minimum(b[..., 0], b[..., 1]) * self.nb + torch.maximum(b[..., 0], b[..., 1])
 
     def _check_capacity_masked(self, cs, accept):
         st = cs.status
