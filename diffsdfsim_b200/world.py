@@ -373,27 +373,34 @@ class World3D:
                                % (self.detector.capK, self.maxc))
 
     def _time_of_contact(self, dt_, p_try, new_v, geo, cs, toc_mask):
-        """Gather of world.py:275-327 for all worlds (padded to maxc) + the H function."""
+        """Gather of world.py:275-327 (padded to maxc) + the H function, evaluated only for the worlds that have a new
+        contact (a handful per step); every other world keeps its dt_ (H is the identity in value)."""
         st = self.state
-        W, C = self.W, self.maxc
-        i1 = cs.body[..., 0].long().clamp(0, self.nb - 1)
-        i2 = cs.body[..., 1].long().clamp(0, self.nb - 1)
+        C = self.maxc
+        idx = toc_mask.any(1).nonzero().squeeze(1)                # host sync; this branch is rare
+        T = idx.numel()
+        sel = lambda x: x.index_select(0, idx)
+        body = sel(cs.body)
+        i1 = body[..., 0].long().clamp(0, self.nb - 1)
+        i2 = body[..., 1].long().clamp(0, self.nb - 1)
 
-        def per_contact(x, idx):
-            return torch.gather(x, 1, idx[..., None].expand(W, C, x.shape[-1]))
+        def per_contact(x, ii):
+            return torch.gather(x, 1, ii[..., None].expand(T, C, x.shape[-1]))
 
-        v1, v2 = per_contact(new_v, i1), per_contact(new_v, i2)
-        pp1, pp2 = per_contact(p_try, i1), per_contact(p_try, i2)
+        new_v_s, p_try_s, geo_s, dt_s = sel(new_v), sel(p_try), sel(geo), sel(dt_)
+        v1, v2 = per_contact(new_v_s, i1), per_contact(new_v_s, i2)
+        pp1, pp2 = per_contact(p_try_s, i1), per_contact(p_try_s, i2)
         f = self.apply_forces(self.t)
-        acc = f / st.mass[..., None]
+        acc = sel(f) / sel(st.mass)[..., None]
         a1, a2 = per_contact(acc, i1), per_contact(acc, i2)
-        h = dt_[:, None, None]
+        h = dt_s[:, None, None]
         x1 = pp1[..., 4:] - h * v1[..., 3:]
         x2 = pp2[..., 4:] - h * v2[..., 3:]
         R1 = so3_exponential_map(-h * v1[..., :3]) @ quaternion_to_matrix(pp1[..., :4])
         R2 = so3_exponential_map(-h * v2[..., :3]) @ quaternion_to_matrix(pp2[..., :4])
-        n, c1, c2 = geo[..., 0:3], geo[..., 3:6], geo[..., 6:9]
+        n, c1, c2 = geo_s[..., 0:3], geo_s[..., 3:6], geo_s[..., 6:9]
         c1 = (R1.transpose(-1, -2) @ c1[..., None])[..., 0]
         c2 = (R2.transpose(-1, -2) @ c2[..., None])[..., 0]
         n2 = (R2.transpose(-1, -2) @ n[..., None])[..., 0]
-        return TimeOfContact.apply(dt_, toc_mask.to(F64), c1, c2, v1, v2, x1, x2, R1, R2, n2, a1, a2)
+        dt_h = TimeOfContact.apply(dt_s, sel(toc_mask).to(F64), c1, c2, v1, v2, x1, x2, R1, R2, n2, a1, a2)
+        return dt_.index_copy(0, idx, dt_h)
