@@ -38,9 +38,10 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--worlds', type=int, default=4096, help='worlds per GPU')
     ap.add_argument('--sim-steps', type=int, default=30)
-    ap.add_argument('--cpu-worlds', type=int, default=2, help='worlds of the bounded CPU sample')
-    ap.add_argument('--cpu-sim-steps', type=int, default=8)
+    ap.add_argument('--cpu-worlds', type=int, default=0, help='worlds of the bounded CPU sample (0 = one per core)')
+    ap.add_argument('--cpu-sim-steps', type=int, default=0, help='0 = --sim-steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-sdf-query', action='store_true', help='skip the SDF-query HBM-roofline microbenchmark')
     return ap.parse_args()
 
 
@@ -106,15 +107,12 @@ def gpu_iteration(spec, params_dev, sim_steps, device):
 
 def run_ours(args):
     import torch.distributed as dist
-    from diffsdfsim_b200 import _lib, scenes
-    rank = int(os.environ.get('RANK', 0))
-    local = int(os.environ.get('LOCAL_RANK', 0))
-    world_size = int(os.environ.get('WORLD_SIZE', 1))
+    from diffsdfsim_b200 import _lib, scenes, distributed as D
+    rank, local, world_size = D.env_rank()
     assert torch.cuda.is_available(), 'bench.py --impl ours needs a CUDA device (no CPU fallback)'
     torch.cuda.set_device(local)
     device = torch.device('cuda', local)
-    if world_size > 1:
-        dist.init_process_group('nccl', device_id=device)
+    D.init(device)
     _lib.lib()
     W = args.worlds
     spec = scenes.box_on_plane(steps=args.sim_steps)
@@ -126,12 +124,8 @@ def run_ours(args):
     d2h = h2d + 8
 
     def allreduce(loss, grads):
-        # shared-parameter reduction of batched system identification: loss and the summed gradients
-        if world_size > 1:
-            buf = torch.stack([loss] + [g.sum() for g in grads.values()])
-            dist.all_reduce(buf)
-            return buf[0]
-        return loss
+        # shared-parameter reduction of batched system identification: loss and the summed gradients (ONE all-reduce)
+        return D.reduce_loss_and_shared_grads(loss, [g.sum(0) for g in grads.values()])[0]
 
     def barrier():
         if world_size > 1:
@@ -175,10 +169,10 @@ def run_ours(args):
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     sampler.stop_flag = True
-    t = torch.tensor([ms, ms_e2e], dtype=torch.float64, device=device)
-    if world_size > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms, ms_e2e = float(t[0]), float(t[1])
+    ms, ms_e2e = D.max_over_ranks([ms, ms_e2e], device)
+    sdfq = None
+    if rank == 0 and not args.no_sdf_query:
+        sdfq = sdf_query_roofline(device)
     units = W * args.sim_steps * args.steps * world_size
     if rank != 0:
         return None
@@ -201,7 +195,57 @@ def run_ours(args):
         'roofline': roof,
         'kernel_ms_per_step': {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
     }
+    if sdfq is not None:
+        line['sdf_query'] = sdfq
     return line
+
+
+def sdf_query_roofline(device, W=256, R=64, N=1 << 17, reps=5):
+    """HBM roofline of the stand-alone SDF query operator (dsdf_sdf_query) on config-4 shaped data: W per-world R^3 f64
+    grids (W*R^3*8 = 512 MiB, larger than the 126 MB L2) and N surface-ordered query points per world with value +
+    direction out.  Algorithmic bytes per launch = W * (N * (24 in + 8 + 24 out) + R^3 * 8 grid, every voxel touched)."""
+    from diffsdfsim_b200 import ops
+    peaks, which = measured_peaks()
+    g = torch.Generator(device='cpu').manual_seed(0)
+    t = torch.linspace(-1, 1, R, dtype=torch.float64)
+    X, Y, Z = torch.meshgrid(t, t, t, indexing='ij')
+    base = (X * X + Y * Y + Z * Z).sqrt() - 0.6
+    grid = (base[None] + 0.01 * torch.rand(W, 1, 1, 1, generator=g, dtype=torch.float64)).to(device).contiguous()
+    # points: a jittered lattice in scan order (coherent like mesh vertices emitted by marching cubes)
+    n1 = int(round(N ** (1 / 3)))
+    while n1 ** 3 < N:
+        n1 += 1
+    u = torch.linspace(-0.98, 0.98, n1, dtype=torch.float64)
+    P = torch.stack(torch.meshgrid(u, u, u, indexing='ij'), -1).reshape(-1, 3)[:N]
+    pts = (P[None] + 0.005 * torch.rand(W, N, 3, generator=g, dtype=torch.float64)).to(device).contiguous()
+    shape = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=torch.float64, device=device).expand(W, 4).contiguous()
+    with torch.no_grad():
+        for _ in range(3):
+            ops.sdf_query('grid', shape, pts, grid=grid, want_dir=True)
+    torch.cuda.synchronize()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    with torch.no_grad():
+        for a, b in ev:
+            a.record()
+            ops.sdf_query('grid', shape, pts, grid=grid, want_dir=True)
+            b.record()
+    torch.cuda.synchronize()
+    ms = sum(a.elapsed_time(b) for a, b in ev) / reps
+    alg = W * (N * 56 + R ** 3 * 8)
+    ach = alg / 1e9 / (ms / 1e3)
+    return {'kernel': 'dsdf_sdf_query (grid, per-world %d^3 f64 grids, W=%d, N=%d pts/world, value+direction)' % (R, W, N),
+            'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
+            'peak_source': which, 'avg_launch_ms': ms, 'algorithmic_bytes_per_launch': alg,
+            'l2_policy': 'inputs (%.2f GB) larger than L2' % (alg / 1e9), 'traffic': ncu_traffic('sdf_query_kernel')}
+
+
+def ncu_traffic(kernel):
+    """dram bytes (read + write) per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json)."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as fh:
+            return json.load(fh).get(kernel)
+    except Exception:
+        return None
 
 
 def roofline(name, stat, W, spec, peaks, which, attempts):
@@ -220,7 +264,7 @@ def roofline(name, stat, W, spec, peaks, which, attempts):
         shared = 176000 * 12 + 89646 * 24 + 1200 * 12 + 726 * 24
         alg = per_world * W + shared
         return {'kernel': name, 'bound': 'hbm', 'achieved': alg / 1e9 / (avg_ms / 1e3), 'peak': peaks['hbm_gbs'],
-                'unit': 'GB/s', 'frac': alg / 1e9 / (avg_ms / 1e3) / peaks['hbm_gbs'], 'traffic': None,
+                'unit': 'GB/s', 'frac': alg / 1e9 / (avg_ms / 1e3) / peaks['hbm_gbs'], 'traffic': ncu_traffic('contacts_kernel'),
                 'peak_source': which, 'avg_launch_ms': avg_ms, 'algorithmic_bytes_per_launch': alg}
     else:
         per_world = 8 * (nz * nz + ni * nz)
@@ -231,56 +275,95 @@ def roofline(name, stat, W, spec, peaks, which, attempts):
             'algorithmic_bytes_per_launch': alg}
 
 
-def cpu_sample(n_worlds, sim_steps, seed=0):
-    """The oracle port (oracle/, CPU float64, one world at a time like the reference) on a bounded sample."""
+def _cpu_world(job):
+    """One world of the bounded CPU sample: the oracle port (oracle/, CPU float64) -- `sim_steps` World.step + backward."""
+    w, sim_steps, seed = job
+    import warnings
+    warnings.filterwarnings('ignore')
+    torch.set_num_threads(1)
     from oracle.scenes import build as build_oracle
     from diffsdfsim_b200 import scenes
-    torch.set_num_threads(os.cpu_count() or 1)
     spec = scenes.box_on_plane(steps=sim_steps)
-    host = make_params(n_worlds, torch.device('cpu'), seed)
+    host = make_params(w + 1, torch.device('cpu'), seed)
     t0 = time.time()
-    for w in range(n_worlds):
-        leaves = dict(mass=host['mass'][w].clone().requires_grad_(True),
-                      fric_coeff=host['fric_coeff'][w].clone().requires_grad_(True),
-                      push=host['push'][w].clone().requires_grad_(True))
-        ow = build_oracle(spec, leaves)
-        loss = 0.
-        for _ in range(sim_steps):
-            ow.step()
-            loss = loss + (ow.bodies[-1].pos ** 2).sum()
-        loss.backward()
+    leaves = dict(mass=host['mass'][w].clone().requires_grad_(True),
+                  fric_coeff=host['fric_coeff'][w].clone().requires_grad_(True),
+                  push=host['push'][w].clone().requires_grad_(True))
+    ow = build_oracle(spec, leaves)
+    loss = 0.
+    for _ in range(sim_steps):
+        ow.step()
+        loss = loss + (ow.bodies[-1].pos ** 2).sum()
+    loss.backward()
+    return time.time() - t0
+
+
+_POOL = None
+
+
+def cpu_pool():
+    """One worker process per host core (worlds are independent: this is all the parallelism the CPU path has)."""
+    global _POOL
+    if _POOL is None:
+        import multiprocessing as mp
+        _POOL = mp.get_context('spawn').Pool(os.cpu_count() or 1)
+        _POOL.map(_cpu_world, [(0, 1, 0)] * (os.cpu_count() or 1))      # import + warm every worker
+    return _POOL
+
+
+def cpu_sample(n_worlds, sim_steps, seed=0):
+    """world-steps/s of the CPU path on `n_worlds` worlds spread over all host cores, and the wall seconds it took."""
+    pool = cpu_pool()
+    t0 = time.time()
+    pool.map(_cpu_world, [(w, sim_steps, seed) for w in range(n_worlds)], chunksize=1)
     dt = time.time() - t0
     return n_worlds * sim_steps / dt, dt
 
 
+def cpu_sizes(args):
+    cores = os.cpu_count() or 1
+    return (args.cpu_worlds or cores), (args.cpu_sim_steps or args.sim_steps), cores
+
+
 def run_reference(args):
     """The reference's CPU implementation of the path: here the oracle port (the reference is pure Python/torch with
-    un-vendored dependencies and cannot travel to the GPU box)."""
-    rank = int(os.environ.get('RANK', 0))
+    un-vendored dependencies and cannot travel to the GPU box), one world per host core at a time."""
+    from diffsdfsim_b200 import distributed as D
+    rank, _, _ = D.env_rank()
     if rank != 0:
         return None
-    vals = []
+    nw, ns, cores = cpu_sizes(args)
+    cpu_pool()
     for _ in range(args.warmup):
-        cpu_sample(1, 2)
+        cpu_sample(cores, 1)
     t0 = time.time()
     for k in range(args.steps):
-        v, _ = cpu_sample(args.cpu_worlds, args.cpu_sim_steps, seed=k)
-        vals.append(v)
+        cpu_sample(nw, ns, seed=k)
     total = time.time() - t0
-    units = args.cpu_worlds * args.cpu_sim_steps * args.steps
+    units = nw * ns * args.steps
     value = units / total
-    sample = '%d worlds x %d World.step + backward per bench step (same scene, same meshes), sequential worlds' % (
-        args.cpu_worlds, args.cpu_sim_steps)
+    sample = ('%d worlds x %d World.step + backward per bench step (same scene, meshes and parameters '
+              'distribution as the 4096-world workload), one world per process on %d cores' % (nw, ns, cores))
     return {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus,
             'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': total / args.steps * 1e3,
             'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f64', 'data': 'synthetic',
-            'config': {'workload': 'box_on_plane sysid (bounded CPU sample of the 4096-world workload)',
+            'config': {'workload': 'box_on_plane sysid (bounded CPU sample of the %d-world workload)' % args.worlds,
                        'worlds_per_gpu': args.worlds, 'sim_steps': args.sim_steps},
-            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port', 'sample': sample},
+            'cpu_baseline': {'value': value, 'unit': UNIT, 'cores': cores, 'kind': 'port', 'sample': sample},
             'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
 
 
+def close_pool():
+    global _POOL
+    if _POOL is not None:
+        _POOL.close()
+        _POOL.join()
+        _POOL = None
+
+
 def main():
+    import atexit
+    atexit.register(close_pool)
     args = parse()
     if args.impl == 'reference':
         line = run_reference(args)
@@ -291,10 +374,11 @@ def main():
     if line is None:
         return
     if args.gpus == 1 and not args.no_cpu_baseline:
-        v, secs = cpu_sample(args.cpu_worlds, args.cpu_sim_steps)
-        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': os.cpu_count(), 'kind': 'port',
-                                'sample': '%d worlds x %d World.step + backward, sequential worlds, %.1f s of CPU work'
-                                          % (args.cpu_worlds, args.cpu_sim_steps, secs)}
+        nw, ns, cores = cpu_sizes(args)
+        v, secs = cpu_sample(nw, ns)
+        line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                                'sample': '%d worlds x %d World.step + backward, one world per process on %d cores, '
+                                          '%.1f s wall' % (nw, ns, cores, secs)}
     print(json.dumps(line))
 
 

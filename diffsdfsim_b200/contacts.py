@@ -111,14 +111,35 @@ class GeometryTable:
 
 
 class ContactSet:
-    """Contacts of all worlds after one detection pass (padded to ``maxc`` per world)."""
-    __slots__ = ('count', 'body', 'face', 'abc', 'geo', 'status', 'pre_ids', 'pre_cnt')
+    """Contacts of all worlds after one detection pass (padded to ``maxc`` per world).
+
+    All six arrays live in ONE flat allocation (segments 8-byte aligned) so that a copy of the whole set is a single
+    device-to-device copy: count (W) i32 | status (W) i32 | body (W,maxc,2) i32 | face (W,maxc) i32 |
+    abc (W,maxc,3) f64 | geo (W,maxc,10) f64.
+    """
+    __slots__ = ('flat', 'W', 'maxc', 'count', 'status', 'body', 'face', 'abc', 'geo', 'pre_ids', 'pre_cnt')
+
+    def __init__(self, W, maxc, device, flat=None):
+        self.W, self.maxc = W, maxc
+        Wp = (W + 1) // 2 * 2                       # keep every segment 8-byte aligned
+        sizes = [4 * Wp, 4 * Wp, 8 * W * maxc, 4 * Wp * maxc, 24 * W * maxc, 80 * W * maxc]
+        offs = [0]
+        for n in sizes:
+            offs.append(offs[-1] + n)
+        self.flat = torch.zeros(offs[-1], dtype=torch.uint8, device=device) if flat is None else flat
+        seg = lambda i, dt: self.flat[offs[i]:offs[i + 1]].view(dt)
+        self.count = seg(0, torch.int32)[:W]
+        self.status = seg(1, torch.int32)[:W]
+        self.body = seg(2, torch.int32).view(W, maxc, 2)
+        self.face = seg(3, torch.int32)[:W * maxc].view(W, maxc)
+        self.abc = seg(4, F64).view(W, maxc, 3)
+        self.geo = seg(5, F64).view(W, maxc, 10)
+        self.pre_ids = self.pre_cnt = None
 
     def clone(self):
-        c = ContactSet()
-        for k in self.__slots__:
-            v = getattr(self, k, None)
-            setattr(c, k, v.clone() if isinstance(v, torch.Tensor) else v)
+        c = ContactSet(self.W, self.maxc, self.flat.device, self.flat.clone())
+        if self.pre_ids is not None:
+            c.pre_ids, c.pre_cnt = self.pre_ids.clone(), self.pre_cnt.clone()
         return c
 
 
@@ -134,18 +155,10 @@ class ContactDetector:
         self.record_prefilter = record_prefilter
 
     def new_set(self):
-        c, W, m, d = ContactSet(), self.W, self.maxc, self.device
-        c.count = torch.zeros(W, dtype=torch.int32, device=d)
-        c.body = torch.zeros(W, m, 2, dtype=torch.int32, device=d)
-        c.face = torch.zeros(W, m, dtype=torch.int32, device=d)
-        c.abc = torch.zeros(W, m, 3, dtype=F64, device=d)
-        c.geo = torch.zeros(W, m, 10, dtype=F64, device=d)
-        c.status = torch.zeros(W, dtype=torch.int32, device=d)
+        c, W, d = ContactSet(self.W, self.maxc, self.device), self.W, self.device
         if self.record_prefilter:
             c.pre_ids = torch.zeros(W, max(2 * self.npairs, 1), self.capK, dtype=torch.int32, device=d)
             c.pre_cnt = torch.zeros(W, max(2 * self.npairs, 1), dtype=torch.int32, device=d)
-        else:
-            c.pre_ids = c.pre_cnt = None
         return c
 
     def detect(self, p, shape, out, active=None, eps=1e-3, tol=1e-8, fd_eps=1e-3, body_eps=1e-3, detach_b2=False):

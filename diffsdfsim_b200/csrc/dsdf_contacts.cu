@@ -67,7 +67,7 @@ __device__ __forceinline__ CellRange cube_cells(const BodyGeom& g1, Q4<double> q
     const M3<double> R1 = q2mat(q1), R2 = q2mat(q2);
     // x_local = R1' ((R2 x_b2) / n2 + x2 - x1) / n1
     const V3<double> ctr = mat_applyT(R1, x2 - x1);
-    double c[3] = {ctr.x / n1, ctr.y / n1, ctr.z / n1};
+    double c[3] = {fdiv(ctr.x, n1), fdiv(ctr.y, n1), fdiv(ctr.z, n1)};
     double h[3];
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
@@ -140,7 +140,7 @@ __device__ __forceinline__ bool face_is_candidate(const BodyGeom& g1, int w, int
     const V3<double> a = to_b2(load_vert(g1, w, ia), q1, x1, q2i, x2);
     const V3<double> b = to_b2(load_vert(g1, w, ib), q1, x1, q2i, x2);
     const V3<double> c = to_b2(load_vert(g1, w, ic), q1, x1, q2i, x2);
-    const V3<double> ctr = v3<double>((a.x + b.x + c.x) / 3, (a.y + b.y + c.y) / 3, (a.z + b.z + c.z) / 3);
+    const V3<double> ctr = v3<double>(fdiv(a.x + b.x + c.x, 3.0), fdiv(a.y + b.y + c.y, 3.0), fdiv(a.z + b.z + c.z, 3.0));
     const SdfOut<double> o = sdf_query<double>(s2, ctr, true);
     double rad = norm3(ctr - a);
     rad = fmax(rad, norm3(ctr - b));
@@ -245,11 +245,15 @@ __device__ ContactGeo<S> contact_geometry(const SdfShape& s1, const SdfShape& s2
 // Rank sorts: every element counts how many precede it (O(n^2/threads) compares on broadcast shared loads, two
 // barriers) -- far cheaper here than a bitonic network's ~45 barrier-separated passes for n <= 1024.
 enum { SORT_MAX_ROUNDS = 8 };                                   // n <= SORT_MAX_ROUNDS * blockDim.x
-__device__ inline void rank_sort_int(int* a, int* tmp, int n) {  // ascending; tmp: n ints of scratch
+__device__ inline void rank_sort_int(int* a, int* tmp, int n) {  // ascending; DISTINCT values; a 16-byte aligned
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int x = a[i];
-        int r = 0;
-        for (int j = 0; j < n; ++j) { const int y = a[j]; r += (y < x) || (y == x && j < i); }
+        int r = 0, j = 0;
+        for (; j + 4 <= n; j += 4) {                           // broadcast 128-bit shared loads
+            const int4 y = *reinterpret_cast<const int4*>(a + j);
+            r += (y.x < x) + (y.y < x) + (y.z < x) + (y.w < x);
+        }
+        for (; j < n; ++j) r += a[j] < x;
         tmp[r] = x;
     }
     __syncthreads();
@@ -491,7 +495,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
     const double* PX = sm.P + 3 * capK; const double* PY = sm.P + 4 * capK; const double* PZ = sm.P + 5 * capK;
     // zero normals are dropped; CL = -1 unassigned, -2 dropped
     for (int k = tid; k < n; k += nt) {
-        const double nn = sqrt(NX[k] * NX[k] + NY[k] * NY[k] + NZ[k] * NZ[k]);
+        const double nn = fsqrt(NX[k] * NX[k] + NY[k] * NY[k] + NZ[k] * NZ[k]);
         sm.CL[k] = nn > 1e-12 ? -1 : -2;
         sm.KEEP[k] = 0;
     }
@@ -574,7 +578,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
         for (int e = tid; e < m; e += nt) {
             const int k = sm.HI[e];
             const V3<double> AP = v3<double>(PX[k], PY[k], PZ[k]) - A;
-            const double dl = lab > 0 ? norm3(cross(AB, AP)) / lab : norm3(AP);
+            const double dl = lab > 0 ? fdiv(norm3(cross(AB, AP)), lab) : norm3(AP);
             far = fmax(far, dl);
         }
         far = block_reduce<RED_MAX>(far, sm.red);
@@ -584,7 +588,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
         for (int e = tid; e < m; e += nt) {
             const int k = sm.HI[e];
             const V3<double> AP = v3<double>(PX[k], PY[k], PZ[k]) - A;
-            const double dl = lab > 0 ? norm3(cross(AB, AP)) / lab : norm3(AP);
+            const double dl = lab > 0 ? fdiv(norm3(cross(AB, AP)), lab) : norm3(AP);
             if (dl == far) atomicMin(&s_far, e);
         }
         __syncthreads();
@@ -597,7 +601,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
             double th = 0.0;
             for (int e = tid; e < m; e += nt) {
                 const int k = sm.HI[e];
-                th = fmax(th, fabs(dot(nrm, v3<double>(PX[k], PY[k], PZ[k]) - A)) / ln);
+                th = fmax(th, fdiv(fabs(dot(nrm, v3<double>(PX[k], PY[k], PZ[k]) - A)), ln));
             }
             th = block_reduce<RED_MAX>(th, sm.red);
             flat3 = !(th > 4.0 * distround(3, mx));
@@ -618,13 +622,13 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
             // extremes along the larger-variance remaining axis define the reference line
             const int ke_lo = sm.HI[e_lo], ke_hi = sm.HI[e_hi];
             const double ax_ = PA[u_ax][ke_lo], ay_ = PA[v_ax][ke_lo], bx_ = PA[u_ax][ke_hi], by_ = PA[v_ax][ke_hi];
-            const double l2 = sqrt((bx_ - ax_) * (bx_ - ax_) + (by_ - ay_) * (by_ - ay_));
+            const double l2 = fsqrt((bx_ - ax_) * (bx_ - ax_) + (by_ - ay_) * (by_ - ay_));
             double fd2 = 0.0, mx2 = 0.0;
             for (int e = tid; e < m; e += nt) {
                 const int k = sm.HI[e];
                 const double px = PA[u_ax][k], py = PA[v_ax][k];
                 const double cr = (bx_ - ax_) * (py - ay_) - (by_ - ay_) * (px - ax_);
-                fd2 = fmax(fd2, l2 > 0 ? fabs(cr) / l2 : sqrt((px - ax_) * (px - ax_) + (py - ay_) * (py - ay_)));
+                fd2 = fmax(fd2, l2 > 0 ? fdiv(fabs(cr), l2) : fsqrt((px - ax_) * (px - ax_) + (py - ay_) * (py - ay_)));
                 mx2 = fmax(mx2, fmax(fabs(px), fabs(py)));
             }
             fd2 = block_reduce<RED_MAX>(fd2, sm.red);
@@ -692,7 +696,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
                 for (int q = 0; q < 8; ++q) {
                     const double ax_ = s_px[q], ay_ = s_py[q], bx_ = s_px[(q + 1) & 7], by_ = s_py[(q + 1) & 7];
                     const double ex = bx_ - ax_, ey = by_ - ay_;
-                    const double len = sqrt(ex * ex + ey * ey);
+                    const double len = fsqrt(ex * ex + ey * ey);
                     if (len > 0.0) inside = inside && ((ex * (y - ay_) - ey * (x - ax_)) > margin * len);
                 }
                 sm.SC[e] = inside ? 0 : 1;
@@ -735,7 +739,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
                     const int a = H[top - 2], b = H[top - 1];
                     const double ex = KU[e] - KU[a], ey = KV[e] - KV[a];
                     const double cr = (KU[b] - KU[a]) * ey - (KV[b] - KV[a]) * ex;   // > 0: left turn keeps b
-                    const double len = sqrt(ex * ex + ey * ey);
+                    const double len = fsqrt(ex * ex + ey * ey);
                     if (cr > tol_d * len) break;
                     --top;
                 }
@@ -747,7 +751,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
                     const int a = H[top - 2], b = H[top - 1];
                     const double ex = KU[e] - KU[a], ey = KV[e] - KV[a];
                     const double cr = (KU[b] - KU[a]) * ey - (KV[b] - KV[a]) * ex;
-                    const double len = sqrt(ex * ex + ey * ey);
+                    const double len = fsqrt(ex * ex + ey * ey);
                     if (cr > tol_d * len) break;
                     --top;
                 }
@@ -912,7 +916,7 @@ int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, int n
                          int W, int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
                          int capK, int maxc, int32_t* count, int32_t* cbody, int32_t* cface, double* cabc, double* cgeo,
                          int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, void* stream) {
-    if (W <= 0 || nb <= 0 || npairs < 0 || capK < 32 || capK > 1024 || maxc <= 0) return -1;
+    if (W <= 0 || nb <= 0 || npairs < 0 || capK < 32 || capK > 1024 || (capK & 3) || maxc <= 0) return -1;
     static_assert(sizeof(BodyGeom) == sizeof(dsdf_body_geom), "BodyGeom must mirror dsdf_body_geom");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = refine_smem_bytes(capK);

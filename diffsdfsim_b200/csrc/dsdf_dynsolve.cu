@@ -11,8 +11,11 @@
 //        B_c = [[a_n, 0, 0], [0, diag(a_f), 1], [mu_c, -1', a_g]],   a = 1/d = s/z > 0
 // with a closed-form inverse, so we eliminate the multipliers instead and factor the (nz+neq)^2 matrix
 //        K = [[Q + sum_c G_c' B_c^-1 G_c, A'], [A, 0]]
-// by pivoted LU in shared memory (18 x 18 for the box-on-plane scene instead of 100 x 100).  Same Newton systems,
-// same iterates up to round-off; verified against the dense kernels and the oracle in tests/test_dynsolve_gpu.py.
+// The equality rows of the engine are 0/1 selections of single velocity components with b = 0 (pinned bodies, axis
+// locks: sdf_physics/physics3d/constraints.py:32-145), so x_P = 0 on the pinned set P throughout and K reduces once
+// more: pivoted LU of the FREE block M~_FF only ((6 nb - neq)^2: 6 x 6 for the box-on-plane scene instead of
+// 100 x 100), multipliers dy = r_P - M~_PF dx_F from the pinned rows.  Same Newton systems, same iterates up to
+// round-off; verified against the dense kernels and the oracle in tests/test_dynsolve_gpu.py.
 #include "dsdf_math.cuh"
 #include "dsdf_dense.cuh"
 #include "../../include/dsdf_b200.h"
@@ -58,25 +61,26 @@ template <class S> __device__ __forceinline__ M3<S> winertia(Q4<S> q, const S* I
 }
 
 struct DynSmem {
-    int C, per, R, nz, neq, nq, ldK, nb;
+    int C, per, R, nz, neq, nq, nF, ldF, nb;
     size_t oG, oYG, oA, oDen, oV, oK, oQ, oS, oI, bytes;
 };
 enum { DV_S = 0, DV_Z, DV_H, DV_RZ, DV_T, DV_DSA, DV_DZA, DV_DS, DV_DZ, DV_BS, DV_BZ, DV_D, DV_COUNT };
-enum { DS_XY = 0, DS_RXY, DS_DXYA, DS_DXY, DS_BXY, DS_P, DS_RHS, DS_COUNT };
+enum { DS_XY = 0, DS_RXY, DS_DXYA, DS_DXY, DS_BXY, DS_P, DS_RHS, DS_TF, DS_XF, DS_COUNT };
 
 __host__ __device__ inline DynSmem dyn_layout(int nb, int neq, int C, int fd) {
     DynSmem L;
-    L.C = C; L.per = 2 + fd; L.R = C * L.per; L.nz = 6 * nb; L.neq = neq; L.nq = L.nz + neq; L.ldK = L.nq | 1; L.nb = nb;
+    L.C = C; L.per = 2 + fd; L.R = C * L.per; L.nz = 6 * nb; L.neq = neq; L.nq = L.nz + neq; L.nb = nb;
+    L.nF = L.nz - neq; L.ldF = L.nF | 1;
     size_t o = 0;
     L.oG = o;   o += (size_t)C * (1 + fd) * 12;
     L.oYG = o;  o += (size_t)C * 12;
     L.oA = o;   o += L.R;                 // a = 1/d
     L.oDen = o; o += C;
     L.oV = o;   o += (size_t)DV_COUNT * L.R;
-    L.oK = o;   o += (size_t)L.nq * L.ldK;
+    L.oK = o;   o += (size_t)L.nz * L.ldF;      // rows [0,nF): M~_FF (LU in place); rows [nF,nz): M~_PF
     L.oQ = o;   o += (size_t)nb * 36;
     L.oS = o;   o += (size_t)DS_COUNT * L.nq;
-    L.oI = o;   o += (size_t)(2 * C + 2 * neq + L.nq + 8 + 1) / 2 + 1;
+    L.oI = o;   o += (size_t)(2 * C + 2 * neq + L.nq + 2 * L.nz + 8 + 1) / 2 + 1;
     L.bytes = o * sizeof(double);
     return L;
 }
@@ -85,7 +89,7 @@ struct DynCtx {
     DynSmem L;
     int nc, ni;                     // active contacts / rows of this world
     double *G, *YG, *a, *den, *V, *K, *Qb, *Sv;
-    int *cb, *eq, *perm, *ib;
+    int *cb, *eq, *perm, *fidx, *fpos;   // fidx[jf] = free dof; fpos[I] = jf (free) or -(m+1) (pinned by row m)
     __device__ double* vec(int k) const { return V + (size_t)k * L.R; }
     __device__ double* sv(int k) const { return Sv + (size_t)k * L.nq; }
     __device__ int gidx(int c, int k) const { return 6 * cb[2 * c + (k >= 6)] + (k % 6); }
@@ -144,6 +148,15 @@ __device__ void dyn_load(DynCtx& c, int w, const double* p, const double* v, con
     c.nc = min(min(count[w], maxc), L.C);
     c.ni = c.nc * L.per;
     for (int i = lane; i < 2 * L.neq; i += 32) c.eq[i] = eq_rows[i];
+    for (int i = lane; i < nz; i += 32) c.fpos[i] = 0;
+    __syncwarp();
+    for (int m = lane; m < L.neq; m += 32) c.fpos[6 * c.eq[2 * m] + c.eq[2 * m + 1]] = -(m + 1);
+    __syncwarp();
+    if (lane == 0) {
+        int jf = 0;
+        for (int i = 0; i < nz; ++i) if (c.fpos[i] == 0) { c.fidx[jf] = i; c.fpos[i] = jf++; }
+    }
+    __syncwarp();
     for (int b = lane; b < nb; b += 32) {
         const double* pb = p + ((size_t)w * nb + b) * 7;
         M3<double> Iw = winertia<double>(q4<double>(pb[0], pb[1], pb[2], pb[3]), Ibody + ((size_t)w * nb + b) * 9);
@@ -249,7 +262,7 @@ __device__ __forceinline__ void block_solve(const DynCtx& c, const double* mu, d
 __device__ int dyn_factor(DynCtx& c, const double* d, const double* mu, int fd) {
     const int lane = threadIdx.x & 31;
     const DynSmem& L = c.L;
-    const int per = L.per, nz = L.nz, nq = L.nq, ld = L.ldK;
+    const int per = L.per, nz = L.nz, nF = L.nF, ld = L.ldF;
     // a = 1/d is B's diagonal (batch.py:496); the kernel keeps 1/a and 1/den so the hot loops multiply
     for (int r = lane; r < c.ni; r += 32) c.a[r] = 1.0 / (1.0 / d[r]);
     __syncwarp();
@@ -268,11 +281,10 @@ __device__ int dyn_factor(DynCtx& c, const double* d, const double* mu, int fd) 
         for (int q = 1; q <= fd; ++q) acc += Gc[12 * q] * ac[q];
         c.YG[e] = acc * c.den[cc];
     }
-    for (int e = lane; e < nq * nq; e += 32) c.K[(e / nq) * ld + e % nq] = 0.0;
     __syncwarp();
-    // M~ entries: thread per (I,J)
-    for (int e = lane; e < nz * nz; e += 32) {
-        const int I = e / nz, J = e % nz, bI = I / 6, bJ = J / 6;
+    // M~ entries (I, J free): thread per entry; free rows land in the LU block, pinned rows below it
+    for (int e = lane; e < nz * nF; e += 32) {
+        const int I = e / nF, jf = e % nF, J = c.fidx[jf], bI = I / 6, bJ = J / 6;
         double acc = bI == bJ ? c.Qb[36 * bI + 6 * (I % 6) + (J % 6)] : 0.0;
         for (int cc = 0; cc < c.nc; ++cc) {
             const int i1 = c.cb[2 * cc], i2 = c.cb[2 * cc + 1];
@@ -286,15 +298,32 @@ __device__ int dyn_factor(DynCtx& c, const double* d, const double* mu, int fd) 
             for (int q = 1; q <= fd; ++q) a2 += Gc[12 * q + ki] * ((Gc[12 * q + kj] - yg) * ac[q]);
             acc += a2;
         }
-        c.K[I * ld + J] = acc;
-    }
-    for (int m = lane; m < L.neq; m += 32) {
-        const int col = 6 * c.eq[2 * m] + c.eq[2 * m + 1];
-        c.K[(nz + m) * ld + col] = 1.0;
-        c.K[col * ld + nz + m] = 1.0;
+        const int fp = c.fpos[I];
+        const int row = fp >= 0 ? fp : nF + (-fp - 1);
+        c.K[row * ld + jf] = acc;
     }
     __syncwarp();
-    return warp_lu(c.K, ld, nq, c.perm);
+    return warp_lu(c.K, ld, nF, c.perm);
+}
+
+// [[M~, A'], [A, 0]] [dx; dy] = rhs with A a 0/1 selection of the pinned components and rhs_y = 0 (b = 0, x_P = 0):
+// dx_P = rhs_y (= 0), dx_F = (M~_FF)^-1 rhs_F, dy = rhs_P - M~_PF dx_F.
+__device__ inline void kkt_solve(DynCtx& c, const double* rhs, double* dxy) {
+    const int lane = threadIdx.x & 31;
+    const DynSmem& L = c.L;
+    const int nz = L.nz, nF = L.nF, ld = L.ldF;
+    double *tF = c.sv(DS_TF), *xF = c.sv(DS_XF);
+    for (int jf = lane; jf < nF; jf += 32) tF[jf] = rhs[c.fidx[jf]];
+    __syncwarp();
+    warp_lu_solve(c.K, ld, nF, c.perm, tF, xF);
+    for (int I = lane; I < nz; I += 32) { const int fp = c.fpos[I]; dxy[I] = fp >= 0 ? xF[fp] : rhs[nz + (-fp - 1)]; }
+    for (int m = lane; m < L.neq; m += 32) {
+        const double* row = c.K + (size_t)(nF + m) * ld;
+        double acc = rhs[6 * c.eq[2 * m] + c.eq[2 * m + 1]];
+        for (int jf = 0; jf < nF; ++jf) acc -= row[jf] * xF[jf];
+        dxy[nz + m] = acc;
+    }
+    __syncwarp();
 }
 
 // KKT solve (batch.py:380-410 semantics).  rxy = [rx; ry] (NULL = 0), rs (NULL = 0), rz (NULL = 0).
@@ -317,7 +346,7 @@ __device__ void dyn_solve(DynCtx& c, const double* d, const double* mu, int fd, 
         rhs[I] = acc;
     }
     __syncwarp();
-    warp_lu_solve(c.K, L.ldK, nq, c.perm, rhs, dxy);
+    kkt_solve(c, rhs, dxy);
     for (int r = lane; r < c.ni; r += 32) dz[r] = Gx_row(c, dxy, r, fd) + dz[r];   // G dx + t
     __syncwarp();
     block_solve(c, mu, dz, fd);
@@ -342,7 +371,7 @@ __device__ inline DynCtx dyn_ctx(double* sm, const DynSmem& L) {
     c.G = sm + L.oG; c.YG = sm + L.oYG; c.a = sm + L.oA; c.den = sm + L.oDen; c.V = sm + L.oV; c.K = sm + L.oK;
     c.Qb = sm + L.oQ; c.Sv = sm + L.oS;
     int* ib = reinterpret_cast<int*>(sm + L.oI);
-    c.cb = ib; c.eq = ib + 2 * L.C; c.perm = c.eq + 2 * L.neq; c.ib = c.perm + L.nq;
+    c.cb = ib; c.eq = ib + 2 * L.C; c.perm = c.eq + 2 * L.neq; c.fidx = c.perm + L.nq; c.fpos = c.fidx + L.nz;
     c.nc = c.ni = 0;
     return c;
 }
@@ -359,16 +388,19 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
                    const int* __restrict__ count, const int* __restrict__ cbody, const double* __restrict__ cgeo,
                    const int* __restrict__ eq_rows, int nb, int neq, int maxc, int C, int fd,
                    double eps, int not_improved_lim, int max_iter,
-                   double* __restrict__ xo, double* __restrict__ nuo, double* __restrict__ lamo, double* __restrict__ so,
-                   int* __restrict__ status_o, int* __restrict__ iters_o) {
+                   double* __restrict__ xo, double* __restrict__ nvo, double* __restrict__ nuo, double* __restrict__ lamo,
+                   double* __restrict__ so, int* __restrict__ status_o, int* __restrict__ iters_o) {
     extern __shared__ double smd[];
     const int w = blockIdx.x, lane = threadIdx.x & 31;
-    if (active && !active[w]) return;
     const DynSmem L = dyn_layout(nb, neq, C, fd);
-    DynCtx c = dyn_ctx(smd, L);
     const int nz = L.nz, nq = L.nq, per = L.per;
+    if (active && !active[w]) {               // inactive world: velocity passes through
+        if (nvo) for (int i = lane; i < nz; i += 32) nvo[(size_t)w * nz + i] = v[(size_t)w * nz + i];
+        return;
+    }
+    DynCtx c = dyn_ctx(smd, L);
     if (count[w] > C) {                       // more contacts than this launch's shared memory holds
-        for (int i = lane; i < nz; i += 32) xo[(size_t)w * nz + i] = NAN;
+        for (int i = lane; i < nz; i += 32) { xo[(size_t)w * nz + i] = NAN; if (nvo) nvo[(size_t)w * nz + i] = NAN; }
         if (lane == 0) { status_o[w] = DSDF_LCP_TOO_LARGE; if (iters_o) iters_o[w] = 0; }
         return;
     }
@@ -407,8 +439,8 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
                 double acc;
                 if (I < nz) {
                     const int b = I / 6, k = I % 6;
-                    double ay = 0.0;
-                    for (int m = 0; m < L.neq; ++m) if (6 * c.eq[2 * m] + c.eq[2 * m + 1] == I) ay += xy[nz + m];
+                    const int fp = c.fpos[I];
+                    const double ay = fp < 0 ? xy[nz + (-fp - 1)] : 0.0;
                     double qx = 0.0;
                     for (int j = 0; j < 6; ++j) qx += xy[6 * b + j] * c.Qb[36 * b + 6 * k + j];
                     acc = ay + Gtw_row(c, z, I, fd) + qx + pv[I];
@@ -467,7 +499,10 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
     }
     __syncwarp();
     const int niCap = maxc * per;
-    for (int i = lane; i < nz; i += 32) xo[(size_t)w * nz + i] = have_best ? bxy[i] : NAN;
+    for (int i = lane; i < nz; i += 32) {
+        xo[(size_t)w * nz + i] = have_best ? bxy[i] : NAN;
+        if (nvo) nvo[(size_t)w * nz + i] = have_best ? -bxy[i] : NAN;       // engines.py:81-82
+    }
     for (int m = lane; m < L.neq; m += 32) nuo[(size_t)w * L.neq + m] = have_best ? bxy[nz + m] : NAN;
     for (int r = lane; r < niCap; r += 32) { lamo[(size_t)w * niCap + r] = 0.0; so[(size_t)w * niCap + r] = 0.0; }
     __syncwarp();
@@ -489,7 +524,7 @@ dyn_backward_kernel(const double* __restrict__ p, const double* __restrict__ v, 
                     const int* __restrict__ eq_rows, int nb, int neq, int maxc, int C, int fd,
                     int stop_contact_grad, int stop_friction_grad,
                     const double* __restrict__ xs, const double* __restrict__ lams, const double* __restrict__ ss,
-                    const double* __restrict__ gz,
+                    const double* __restrict__ gnv,
                     double* __restrict__ gp, double* __restrict__ gv, double* __restrict__ gmass, double* __restrict__ gI,
                     double* __restrict__ gfric, double* __restrict__ grest, double* __restrict__ gf,
                     double* __restrict__ gdt, double* __restrict__ ggeo) {
@@ -498,10 +533,14 @@ dyn_backward_kernel(const double* __restrict__ p, const double* __restrict__ v, 
     const DynSmem L = dyn_layout(nb, neq, C, fd);
     DynCtx c = dyn_ctx(smd, L);
     const int nz = L.nz, nq = L.nq, per = L.per, niCap = maxc * per;
-    const bool on = !(active && !active[w]) && count[w] <= C;
+    const bool masked = active && !active[w];
+    const bool on = !masked && count[w] <= C;
     if (!on) {
         for (int i = lane; i < nb * 7; i += 32) gp[(size_t)w * nb * 7 + i] = 0.0;
-        for (int i = lane; i < nz; i += 32) { gv[(size_t)w * nz + i] = 0.0; gf[(size_t)w * nz + i] = 0.0; }
+        for (int i = lane; i < nz; i += 32) {               // inactive world: new_v = v
+            gv[(size_t)w * nz + i] = masked ? gnv[(size_t)w * nz + i] : 0.0;
+            gf[(size_t)w * nz + i] = 0.0;
+        }
         for (int i = lane; i < nb; i += 32) {
             gmass[(size_t)w * nb + i] = 0.0; gfric[(size_t)w * nb + i] = 0.0; grest[(size_t)w * nb + i] = 0.0;
         }
@@ -517,7 +556,7 @@ dyn_backward_kernel(const double* __restrict__ p, const double* __restrict__ v, 
     const double* vw = v + (size_t)w * nz;
     double *lam = c.vec(DV_Z), *d = c.vec(DV_D), *dl = c.vec(DV_DZ), *ds = c.vec(DV_DS);
     double *g = c.sv(DS_RXY), *dxy = c.sv(DS_DXY), *zh = c.sv(DS_XY);
-    for (int i = lane; i < nq; i += 32) { g[i] = i < nz ? gz[(size_t)w * nz + i] : 0.0; zh[i] = i < nz ? xs[(size_t)w * nz + i] : 0.0; }
+    for (int i = lane; i < nq; i += 32) { g[i] = i < nz ? -gnv[(size_t)w * nz + i] : 0.0; zh[i] = i < nz ? xs[(size_t)w * nz + i] : 0.0; }
     for (int r = lane; r < ni; r += 32) {
         const int rr = ref_row(r / per, r % per, nc, fd);
         lam[r] = lams[(size_t)w * niCap + rr];
@@ -638,7 +677,8 @@ int dsdf_dynamics_solve(const double* p, const double* v, const double* mass, co
                         const unsigned char* active, const int32_t* count, const int32_t* cbody, const double* cgeo,
                         const int32_t* eq_rows, int W, int nb, int neq, int maxc, int ncontacts_smem, int fric_dirs,
                         double eps, int not_improved_lim, int max_iter,
-                        double* x, double* nu, double* lam, double* s, int32_t* status, int32_t* iters, void* stream) {
+                        double* x, double* new_v, double* nu, double* lam, double* s, int32_t* status, int32_t* iters,
+                        void* stream) {
     size_t smem;
     int C = ncontacts_smem;
     int rc = dyn_check(W, nb, neq, maxc, &C, fric_dirs, &smem);
@@ -647,7 +687,7 @@ int dsdf_dynamics_solve(const double* p, const double* v, const double* mass, co
     if (e != cudaSuccess) return (int)e;
     dyn_forward_kernel<<<W, 32, smem, (cudaStream_t)stream>>>(p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody,
                                                               cgeo, eq_rows, nb, neq, maxc, C, fric_dirs, eps,
-                                                              not_improved_lim, max_iter, x, nu, lam, s, status, iters);
+                                                              not_improved_lim, max_iter, x, new_v, nu, lam, s, status, iters);
     return (int)cudaGetLastError();
 }
 
@@ -656,7 +696,7 @@ int dsdf_dynamics_solve_backward(const double* p, const double* v, const double*
                                  const unsigned char* active, const int32_t* count, const int32_t* cbody,
                                  const double* cgeo, const int32_t* eq_rows, int W, int nb, int neq, int maxc,
                                  int ncontacts_smem, int fric_dirs, int stop_contact_grad, int stop_friction_grad,
-                                 const double* x, const double* lam, const double* s, const double* gz,
+                                 const double* x, const double* lam, const double* s, const double* g_new_v,
                                  double* gp, double* gv, double* gmass, double* gI, double* gfric, double* grest,
                                  double* gf, double* gdt, double* ggeo, void* stream) {
     size_t smem;
@@ -667,7 +707,7 @@ int dsdf_dynamics_solve_backward(const double* p, const double* v, const double*
     if (e != cudaSuccess) return (int)e;
     dyn_backward_kernel<<<W, 32, smem, (cudaStream_t)stream>>>(p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody,
                                                                cgeo, eq_rows, nb, neq, maxc, C, fric_dirs,
-                                                               stop_contact_grad, stop_friction_grad, x, lam, s, gz, gp,
+                                                               stop_contact_grad, stop_friction_grad, x, lam, s, g_new_v, gp,
                                                                gv, gmass, gI, gfric, grest, gf, gdt, ggeo);
     return (int)cudaGetLastError();
 }

@@ -20,11 +20,18 @@ struct Dual {
     __host__ __device__ Dual(double a, double b) : v(a), d(b) {}
 };
 #define HD __host__ __device__ __forceinline__
+// IEEE-exact division / square root with the zero operand peeled off.  The hardware sequences (MUFU.RCP64H / RSQ64H +
+// Newton steps) fall into a ~100-instruction slow path whenever the numerator (radicand) is zero or denormal, and the
+// whole warp waits for it; exact zeros are everywhere in contact geometry (axis-aligned normals, points on coordinate
+// planes, clamped box distances).  0 / b = +-0 and sqrt(+-0) = +-0 exactly, so the shortcut changes no bit.
+HD double fdiv(double a, double b) { return (a == 0.0 && b != 0.0 && b == b) ? (b > 0.0 ? a : -a) : a / b; }
+HD double fsqrt(double a) { return a == 0.0 ? a : sqrt(a); }
 HD Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
 HD Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
 HD Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
 HD Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, a.d * b.v + a.v * b.d); }
-HD Dual operator/(Dual a, Dual b) { double q = a.v / b.v; return Dual(q, (a.d - q * b.d) / b.v); }
+HD Dual operator/(Dual a, Dual b) { double q = fdiv(a.v, b.v); return Dual(q, fdiv(a.d - q * b.d, b.v)); }
+HD Dual fdiv(Dual a, Dual b) { return a / b; }
 HD Dual& operator+=(Dual& a, Dual b) { a = a + b; return a; }
 HD Dual& operator-=(Dual& a, Dual b) { a = a - b; return a; }
 HD Dual& operator*=(Dual& a, Dual b) { a = a * b; return a; }
@@ -38,8 +45,8 @@ HD void set_tangent(Dual& a, double d) { a.d = d; }
 HD bool needs_tan(double) { return false; }
 HD bool needs_tan(Dual) { return true; }
 
-HD double dsqrt(double a) { return sqrt(a); }
-HD Dual dsqrt(Dual a) { double s = sqrt(a.v); return Dual(s, a.d / (2.0 * s)); }
+HD double dsqrt(double a) { return fsqrt(a); }
+HD Dual dsqrt(Dual a) { double s = fsqrt(a.v); return Dual(s, a.d / (2.0 * s)); }
 HD double dsin(double a) { return sin(a); }
 HD Dual dsin(Dual a) { return Dual(sin(a.v), cos(a.v) * a.d); }
 HD double dcos(double a) { return cos(a); }
@@ -76,27 +83,27 @@ template <class S> HD V3<S> cross(V3<S> a, V3<S> b) {
     return v3<S>(a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x);
 }
 // torch .norm(): derivative x/|x|, 0 at the origin
-HD double norm3(V3<double> a) { return sqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
+HD double norm3(V3<double> a) { return fsqrt(a.x * a.x + a.y * a.y + a.z * a.z); }
 HD Dual norm3(V3<Dual> a) {
-    double n = sqrt(a.x.v * a.x.v + a.y.v * a.y.v + a.z.v * a.z.v);
-    double d = n > 0.0 ? (a.x.v * a.x.d + a.y.v * a.y.d + a.z.v * a.z.d) / n : 0.0;
+    double n = fsqrt(a.x.v * a.x.v + a.y.v * a.y.v + a.z.v * a.z.v);
+    double d = n > 0.0 ? fdiv(a.x.v * a.x.d + a.y.v * a.y.d + a.z.v * a.z.d, n) : 0.0;
     return Dual(n, d);
 }
-HD double norm2(double a, double b) { return sqrt(a * a + b * b); }
+HD double norm2(double a, double b) { return fsqrt(a * a + b * b); }
 HD Dual norm2(Dual a, Dual b) {
-    double n = sqrt(a.v * a.v + b.v * b.v);
-    return Dual(n, n > 0.0 ? (a.v * a.d + b.v * b.d) / n : 0.0);
+    double n = fsqrt(a.v * a.v + b.v * b.v);
+    return Dual(n, n > 0.0 ? fdiv(a.v * a.d + b.v * b.d, n) : 0.0);
 }
 // F.normalize(v, dim): v / max(|v|, 1e-12); the clamp has zero gradient when it is active
 template <class S> HD V3<S> normalize3(V3<S> a) {
     S n = norm3(a);
     if (val(n) < 1e-12) n = cst(n, 1e-12);
-    return v3<S>(a.x / n, a.y / n, a.z / n);
+    return v3<S>(fdiv(a.x, n), fdiv(a.y, n), fdiv(a.z, n));
 }
 template <class S> HD void normalize2(S& a, S& b) {
     S n = norm2(a, b);
     if (val(n) < 1e-12) n = cst(n, 1e-12);
-    a = a / n; b = b / n;
+    a = fdiv(a, n); b = fdiv(b, n);
 }
 
 // ------------------------------------------------------------------ quaternions (w,x,y,z)
@@ -181,7 +188,7 @@ template <class S> HD Q4<S> mat2q(const M3<S>& R) {
     else if (best == 1) { c0 = m21 - m12; c1 = qa[1] * qa[1]; c2 = m10 + m01; c3 = m02 + m20; }
     else if (best == 2) { c0 = m02 - m20; c1 = m10 + m01; c2 = qa[2] * qa[2]; c3 = m12 + m21; }
     else { c0 = m10 - m01; c1 = m20 + m02; c2 = m21 + m12; c3 = qa[3] * qa[3]; }
-    return q4<S>(c0 / den, c1 / den, c2 / den, c3 / den);
+    return q4<S>(fdiv(c0, den), fdiv(c1, den), fdiv(c2, den), fdiv(c3, den));
 }
 
 #undef HD

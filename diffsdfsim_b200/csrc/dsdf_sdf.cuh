@@ -75,7 +75,7 @@ __device__ __forceinline__ double grid_cd(const double* g, int R, int i, int j, 
     if (c <= 0 || c >= R - 1) return 0.0;
     const size_t st = axis == 0 ? (size_t)R * R : (axis == 1 ? (size_t)R : 1);
     const size_t o = ((size_t)i * R + j) * R + k;
-    return (g[o + st] - g[o - st]) / 2.0;
+    return (g[o + st] - g[o - st]) * 0.5;      // exact: division by 2
 }
 __device__ __forceinline__ bool grid_eval_raw(const double* g, int R, double ux, double uy, double uz, bool want_n,
                                               double& value, double n[3]) {
@@ -127,7 +127,7 @@ __device__ __forceinline__ SdfOut<S> sdf_query(const SdfShape& sh, V3<S> p, bool
     const bool inside = fabs(val(p.x)) <= sc && fabs(val(p.y)) <= sc && fabs(val(p.z)) <= sc;
     if (!inside) { o.d = cst(p.x, 1.0 * sc); return o; }
     S scs = cst(p.x, sc);
-    V3<S> u = v3<S>(p.x / scs, p.y / scs, p.z / scs);
+    V3<S> u = v3<S>(fdiv(p.x, scs), fdiv(p.y, scs), fdiv(p.z, scs));
     S value;
     V3<S> dir = o.n;
     if (sh.kind == DSDF_SDF_BOX) box_eval<S>(u, sh.a, sh.b, sh.c, want_n, value, dir);

@@ -92,7 +92,10 @@ class _Dynamics(torch.autograd.Function):
 
 
 class _DynamicsFused(torch.autograd.Function):
-    """dsdf_dynamics_solve / dsdf_dynamics_solve_backward: one warp per world, structure-exploiting KKT."""
+    """dsdf_dynamics_solve / dsdf_dynamics_solve_backward: one warp per world, structure-exploiting KKT.
+
+    The kernels write new_v (= -x, inactive worlds: v) and consume dL/dnew_v directly: no torch arithmetic around them.
+    """
 
     @staticmethod
     def forward(ctx, p, v, mass, Ibody, fric, rest, f, dt, geo, count, cbody, eq_rows, active, cfg):
@@ -105,6 +108,7 @@ class _DynamicsFused(torch.autograd.Function):
         neq = eq_rows.shape[0]
         dev = p.device
         x = torch.empty(W, 6 * nb, dtype=F64, device=dev)
+        new_v = torch.empty(W, nb, 6, dtype=F64, device=dev)
         nu = torch.empty(W, neq, dtype=F64, device=dev)
         lam = torch.empty(W, maxc * (2 + fd), dtype=F64, device=dev)
         s = torch.empty_like(lam)
@@ -113,12 +117,9 @@ class _DynamicsFused(torch.autograd.Function):
         rc = _lib.call('dsdf_dynamics_solve', _lib.ptr(p), _lib.ptr(v), _lib.ptr(mass), _lib.ptr(Ibody),
                        _lib.ptr(fric), _lib.ptr(rest), _lib.ptr(f), _lib.ptr(dt), _lib.ptr(active), _lib.ptr(count),
                        _lib.ptr(cbody), _lib.ptr(geo), _lib.ptr(eq_rows), W, nb, neq, maxc, cfg['nc_smem'], fd,
-                       1e-12, 3, cfg['max_iter'], _lib.ptr(x), _lib.ptr(nu), _lib.ptr(lam), _lib.ptr(s),
-                       _lib.ptr(status), _lib.ptr(iters), _lib.stream())
+                       1e-12, 3, cfg['max_iter'], _lib.ptr(x), _lib.ptr(new_v), _lib.ptr(nu), _lib.ptr(lam),
+                       _lib.ptr(s), _lib.ptr(status), _lib.ptr(iters), _lib.stream())
         _lib.check(rc, 'dsdf_dynamics_solve')
-        new_v = (-x).reshape(W, nb, 6)
-        if active is not None:
-            new_v = torch.where(active.bool().reshape(W, 1, 1), new_v, v)
         ctx.save_for_backward(p, v, mass, Ibody, fric, rest, f, dt, geo, count, cbody, eq_rows, x, lam, s,
                               active if active is not None else p.new_empty(0))
         ctx.cfg = cfg
@@ -133,11 +134,7 @@ class _DynamicsFused(torch.autograd.Function):
         cfg = ctx.cfg
         W, nb = p.shape[0], p.shape[1]
         maxc, fd = geo.shape[1], cfg['fric_dirs']
-        gz = (-gv_new).reshape(W, 6 * nb).contiguous()
-        gpass = None
-        if active is not None:
-            am = active.bool().reshape(W, 1)
-            gpass = torch.where(am, torch.zeros_like(gz), -gz).reshape(W, nb, 6)
+        gnv = gv_new.contiguous()
         gp, gv = torch.empty_like(p), torch.empty_like(v)
         gmass, gI = torch.empty_like(mass), torch.empty_like(Ibody)
         gfric, grest, gf = torch.empty_like(fric), torch.empty_like(rest), torch.empty_like(f)
@@ -146,12 +143,10 @@ class _DynamicsFused(torch.autograd.Function):
                        _lib.ptr(fric), _lib.ptr(rest), _lib.ptr(f), _lib.ptr(dt), _lib.ptr(active), _lib.ptr(count),
                        _lib.ptr(cbody), _lib.ptr(geo), _lib.ptr(eq_rows), W, nb, eq_rows.shape[0], maxc,
                        cfg['nc_smem'], fd, int(cfg['stop_contact_grad']), int(cfg['stop_friction_grad']),
-                       _lib.ptr(x), _lib.ptr(lam), _lib.ptr(s), _lib.ptr(gz), _lib.ptr(gp), _lib.ptr(gv),
+                       _lib.ptr(x), _lib.ptr(lam), _lib.ptr(s), _lib.ptr(gnv), _lib.ptr(gp), _lib.ptr(gv),
                        _lib.ptr(gmass), _lib.ptr(gI), _lib.ptr(gfric), _lib.ptr(grest), _lib.ptr(gf), _lib.ptr(gdt),
                        _lib.ptr(ggeo), _lib.stream())
         _lib.check(rc, 'dsdf_dynamics_solve_backward')
-        if gpass is not None:
-            gv = gv + gpass
         return gp, gv, gmass, gI, gfric, grest, gf, gdt, ggeo, None, None, None, None, None
 
 
@@ -174,7 +169,7 @@ class PdipmEngine(Engine):
     def solve_dynamics(self, world, dt, active=None):
         """dt: (W,) tensor (may carry grad).  Returns new_v (W,nb,6)."""
         st = world.state
-        f = world.apply_forces(world.t)
+        f = world.step_forces()
         cfg = dict(fric_dirs=world.fric_dirs, max_iter=self.max_iter, stop_contact_grad=world.stop_contact_grad,
                    stop_friction_grad=world.stop_friction_grad,
                    ni_smem=max(world.max_nc, 1) * (2 + world.fric_dirs), nc_smem=max(world.max_nc, 1))

@@ -12,7 +12,7 @@ import torch
 
 from . import contacts as contacts_module
 from . import engines as engines_module
-from . import ops
+from . import _lib, ops
 from .contacts import ContactDetector, GeometryTable, differentiable_geometry
 from .transforms import quaternion_to_matrix, so3_exponential_map
 from .utils import Defaults3D, default_device, get_instance
@@ -136,11 +136,12 @@ class World3D:
         self.t = torch.zeros(W, dtype=F64, device=dev)
         self.t_host = 0.0
         self.last_dt = torch.zeros(W, dtype=F64, device=dev)
-        self.toc_flag = torch.zeros(W, dtype=torch.bool, device=dev)
+        self.toc_flag = torch.zeros(W, dtype=torch.uint8, device=dev)
         self.trajectory, self.observations = [], []
         self.stats = {'rounds': [], 'attempts': torch.zeros(W, dtype=torch.int64, device=dev)}
         self.static_inverse = False
-        self._kk = torch.arange(self.maxc, device=dev)[None, :]
+        self._f_cache, self._any_toc_flag = None, False
+        self._f_vectorized = any(getattr(f, 'vectorized', False) for b in self.bodies for f in b.forces)
         self.contact_set = self.detector.new_set()
         self.contact_geo = None
         self.find_contacts()
@@ -206,7 +207,6 @@ class World3D:
 
     def lcp_matrices(self, dt=None):
         """(Q, p, G, h, A, b, F, nineq_w) exactly as handed to the LCP kernel (engines.py:56-79 layout)."""
-        from . import _lib
         st = self.state
         dtt = self._dt_tensor(self.dt if dt is None else dt)
         f = self.apply_forces(self.t)
@@ -253,124 +253,105 @@ class World3D:
         return cs
 
     # ------------------------------------------------------------------ stepping
+    def step_forces(self):
+        """Generalized forces of the current step.  Forces that only see the step's start time (the default, see
+        forces.py) are evaluated once per step and reused by every sub-step attempt."""
+        if self._f_cache is None or self._f_vectorized:
+            self._f_cache = self.apply_forces(self.t)
+        return self._f_cache
+
     def step(self, fixed_dt=False):
         """world.py:119-139.  Returns had_contacts: python bool for a single world, (W,) bool tensor otherwise."""
         st = self.state
-        self._undo = (st.p, st.v, self.contact_set, self.contact_geo, self.t.clone(), self.t_host, self.toc_flag.clone(),
-                      self.last_dt, len(self.trajectory))
+        self._undo = (st.p, st.v, self.contact_set, self.contact_geo, self.t, self.t_host, self.toc_flag.clone(),
+                      self.last_dt, len(self.trajectory), self._any_toc_flag)
         W, dev = self.W, self.device
+        self._f_cache = None
         end_t = (self.t + self.dt) if fixed_dt else None
         dt_try = torch.full((W,), float(self.dt), dtype=F64, device=dev)
-        active = torch.ones(W, dtype=torch.bool, device=dev)
+        active = torch.ones(W, dtype=torch.uint8, device=dev)
         had = torch.zeros(W, dtype=torch.bool, device=dev)
         rounds = 0
         while True:
             rounds += 1
-            self.stats['attempts'] += active.long()
+            self.stats['attempts'] += active
             accept, dt_try, active, any_active = self._attempt(active, dt_try, end_t)
-            had |= accept & (self.contact_set.count > 0)
+            had |= accept.bool() & (self.contact_set.count > 0)
             if not any_active:
                 break
         self.stats['rounds'].append(rounds)
         self.t_host += self.dt
         self._sync_bodies()
-        self.trajectory.append((self.t.clone() if self.batched else float(self.t[0]), self.get_p(), self.v,
+        self.trajectory.append((self.t if self.batched else float(self.t[0]), self.get_p(), self.v,
                                 self.contact_set, None))
         return had if self.batched else bool(had[0])
 
     def undo_step(self):
         """world.py:106-116."""
         st = self.state
-        (st.p, st.v, self.contact_set, self.contact_geo, self.t, self.t_host, self.toc_flag, self.last_dt, ntraj) = self._undo
+        (st.p, st.v, self.contact_set, self.contact_geo, self.t, self.t_host, self.toc_flag, self.last_dt, ntraj,
+         self._any_toc_flag) = self._undo
         del self.trajectory[ntraj:]
         self._sync_bodies()
 
     def _attempt(self, active, dt_try, end_t):
         """One solve -> move -> find_contacts attempt of every active world (body of world.py:249-356).
 
-        Returns (accept, next dt_try, next active, any world still active).  One host synchronisation per attempt:
-        a 4-entry flag vector [capacity error, any new (time-of-contact) contact, max contact count, any active].
+        ``active`` is a uint8 (W) mask.  Returns (accept, next dt_try, next active, any world still active).  The
+        per-world accept / halve / remaining-time / time-of-contact bookkeeping and the merge of the new contact set
+        with the previous one run in dsdf_attempt_commit; ONE host synchronisation per attempt reads its 4 flags
+        [capacity error, any world still active, any new (time-of-contact) contact, max contact count].
         """
         st = self.state
-        W, nb = self.W, self.nb
-        act8 = active.to(torch.uint8)
+        W, nb, dev = self.W, self.nb, self.device
+        toc = self.time_of_contact_diff
         dt_ = dt_try
-        if self.time_of_contact_diff:
+        if toc and self._any_toc_flag:
             # world.py:253-257: value == dt_try, carries -d last_dt
-            dt_ = torch.where(self.toc_flag, -self.last_dt + (self.last_dt.detach() + dt_try), dt_try)
-        new_v = self.engine.solve_dynamics(self, dt_, act8)
-        p_try = ops.integrate(st.p, new_v, dt_, act8)
+            dt_ = torch.where(self.toc_flag.bool(), -self.last_dt + (self.last_dt.detach() + dt_try), dt_try)
+        new_v = self.engine.solve_dynamics(self, dt_, active)
+        p_try = ops.integrate(st.p, new_v, dt_, active)
         old = self.contact_set
         cs = old.clone()
-        self.detector.detect(p_try.detach(), self.shape, cs, act8, eps=self.eps, tol=self.tol,
+        self.detector.detect(p_try.detach(), self.shape, cs, active, eps=self.eps, tol=self.tol,
                              fd_eps=Defaults3D.EPSILON, body_eps=self.body_eps, detach_b2=self.detach_contact_b2)
         geo = differentiable_geometry(p_try, self.shape, cs, self.table, Defaults3D.EPSILON, self.detach_contact_b2)
-        status = cs.status
-        clean = active & ((status & 8) == 0)
-        accept = clean
-        if not self.strict_no_pen:
-            accept = clean | (active & (dt_try < self.dt / 2 ** 10))         # world.py:345-347 (give up, keep going)
-        bad = ((status & 1) != 0).any() | (((status & 2) != 0) & accept).any()
-        count_after = torch.where(accept, cs.count, old.count)
-        t_new = torch.where(accept, self.t + dt_try, self.t)
-        # rejected worlds retry with half the step (world.py:348); accepted ones take the remaining time
-        dt_next = torch.where(active & ~accept, dt_try / 2, dt_try)
-        if end_t is not None:
-            more = accept & (t_new < end_t)
-            dt_next = torch.where(more, end_t - t_new, dt_next)
-            next_active = (active & ~accept) | more
-        else:
-            next_active = active & ~accept
-        flags = [bad, count_after.max() > 0, next_active.any()]
-        toc_mask = toc_now = None
-        if self.time_of_contact_diff:
-            # contacts between body pairs that had no contact at the start of the sub-step (world.py:273-274)
-            new_valid = self._kk < cs.count[:, None]
-            old_valid = self._kk < old.count[:, None]
-            pid_new, pid_old = self._pair_ids(cs.body), self._pair_ids(old.body)
-            seen = ((pid_new[:, :, None] == pid_old[:, None, :]) & old_valid[:, None, :]).any(2)
-            toc_mask = new_valid & ~seen & clean[:, None]
-            toc_now = toc_mask.any(1)
-            flags.append(toc_now.any())
-        fl = torch.stack([f.to(torch.int32) for f in flags] + [count_after.max().to(torch.int32)]).tolist()   # the sync
+        u8 = lambda *shape: torch.empty(*shape, dtype=torch.uint8, device=dev)
+        accept, active_next, toc_now, toc_mask = u8(W), u8(W), u8(W), u8(W, self.maxc)
+        t_new, dt_next = torch.empty_like(self.t), torch.empty_like(dt_try)
+        flags = torch.empty(4, dtype=torch.int32, device=dev)
+        toc_flag = self.toc_flag.clone() if toc else self.toc_flag
+        rc = _lib.call('dsdf_attempt_commit', W, nb, self.maxc, _lib.ptr(active), _lib.ptr(dt_try), _lib.ptr(self.t),
+                       _lib.ptr(end_t), float(self.dt), int(self.strict_no_pen), int(toc),
+                       _lib.ptr(old.count), _lib.ptr(old.status), _lib.ptr(old.body), _lib.ptr(old.face),
+                       _lib.ptr(old.abc), _lib.ptr(old.geo), _lib.ptr(cs.count), _lib.ptr(cs.status),
+                       _lib.ptr(cs.body), _lib.ptr(cs.face), _lib.ptr(cs.abc), _lib.ptr(cs.geo), _lib.ptr(toc_flag),
+                       _lib.ptr(accept), _lib.ptr(t_new), _lib.ptr(dt_next), _lib.ptr(active_next), _lib.ptr(toc_now),
+                       _lib.ptr(toc_mask), _lib.ptr(flags), _lib.stream())
+        _lib.check(rc, 'dsdf_attempt_commit')
+        fl = flags.tolist()                                              # the sync
         if fl[0]:
             raise RuntimeError('contact capacity exceeded (capK=%d, maxc=%d): raise World3D(capK=..., maxc=...)'
                                % (self.detector.capK, self.maxc))
-        any_active = bool(fl[2])
-        self.max_nc = int(fl[-1])                  # sizes the dynamics kernel's shared memory for the next solve
-        if self.time_of_contact_diff:
-            if fl[3]:
-                dt_h = self._time_of_contact(dt_, p_try, new_v, geo, cs, toc_mask)
-                p_redo = ops.integrate(st.p, new_v, dt_h, toc_now.to(torch.uint8))
-                p_try = torch.where(toc_now[:, None, None], p_redo, p_try)
-                self.last_dt = torch.where(toc_now, dt_h, self.last_dt)
-            self.toc_flag = torch.where(clean, toc_now, self.toc_flag)   # a give-up accept leaves toc_contacts untouched
+        self.max_nc = int(fl[3])                   # sizes the dynamics kernel's shared memory for the next solve
+        if toc:
+            if fl[2]:
+                dt_h = self._time_of_contact(dt_, p_try, new_v, geo, cs, toc_mask.bool())
+                p_redo = ops.integrate(st.p, new_v, dt_h, toc_now)
+                tn = toc_now.bool()
+                p_try = torch.where(tn[:, None, None], p_redo, p_try)
+                self.last_dt = torch.where(tn, dt_h, self.last_dt)
+                self._any_toc_flag = True
+            self.toc_flag = toc_flag
 
-        # commit accepted worlds
-        a3 = accept[:, None, None]
+        # commit accepted worlds (the non-differentiable part of the merge already happened in the kernel)
+        a3 = accept.bool()[:, None, None]
         st.p = torch.where(a3, p_try, st.p)
         st.v = torch.where(a3, new_v, st.v)
-        cs.count = count_after
-        cs.status = torch.where(accept, status, old.status)
-        cs.body = torch.where(a3, cs.body, old.body)
-        cs.face = torch.where(accept[:, None], cs.face, old.face)
-        cs.abc = torch.where(a3, cs.abc, old.abc)
-        cs.geo = torch.where(a3, cs.geo, old.geo)
         self.contact_geo = torch.where(a3, geo, self.contact_geo)
         self.contact_set = cs
         self.t = t_new
-        return accept, dt_next, next_active, any_active
-
-    def _pair_ids(self, body):
-        b = body.long()
-        return torch.minimum(b[..., 0], b[..., 1]) * self.nb + torch.maximum(b[..., 0], b[..., 1])
-
-    def _check_capacity_masked(self, cs, accept):
-        st = cs.status
-        bad = ((st & 1) != 0).any() | (((st & 2) != 0) & accept).any()
-        if bool(bad):
-            raise RuntimeError('contact capacity exceeded (capK=%d, maxc=%d): raise World3D(capK=..., maxc=...)'
-                               % (self.detector.capK, self.maxc))
+        return accept, dt_next, active_next, bool(fl[1])
 
     def _time_of_contact(self, dt_, p_try, new_v, geo, cs, toc_mask):
         """Gather of world.py:275-327 (padded to maxc) + the H function, evaluated only for the worlds that have a new

@@ -197,8 +197,9 @@ int dsdf_dynamics_assemble_backward(const double* p, const double* v, const doub
  * eq_rows (neq,2) int32 = [body, velocity component] of each equality row (rows of Je are 0/1 selections:
  * sdf_physics/physics3d/constraints.py:32-145).  ncontacts_smem (0 = maxc): contacts the launch sizes its shared
  * memory for (<= 64); worlds with more get DSDF_LCP_TOO_LARGE.
- * Outputs x (W,6nb) [new_v = -x], nu (W,neq), lam / s (W, maxc (2+fric_dirs)) in the reference's row order
- * [normal | friction | cone], status (W), iters (W).
+ * Outputs x (W,6nb), new_v (W,6nb) = -x (engines.py:81-82; inactive worlds: v passed through; may be NULL),
+ * nu (W,neq), lam / s (W, maxc (2+fric_dirs)) in the reference's row order [normal | friction | cone], status (W),
+ * iters (W).
  */
 size_t dsdf_dynamics_solve_smem_bytes(int nb, int neq, int ncontacts, int fric_dirs);
 int dsdf_dynamics_solve(const double* p, const double* v, const double* mass, const double* Ibody,
@@ -206,17 +207,40 @@ int dsdf_dynamics_solve(const double* p, const double* v, const double* mass, co
                         const unsigned char* active, const int32_t* count, const int32_t* cbody, const double* cgeo,
                         const int32_t* eq_rows, int W, int nb, int neq, int maxc, int ncontacts_smem, int fric_dirs,
                         double eps, int not_improved_lim, int max_iter,
-                        double* x, double* nu, double* lam, double* s, int32_t* status, int32_t* iters, void* stream);
+                        double* x, double* new_v, double* nu, double* lam, double* s, int32_t* status, int32_t* iters,
+                        void* stream);
 /* Replaces LCPFunctionFn.backward (lcp_physics/lcp/lcp.py:156-213) + the autograd of the assembly, fused: from
- * gz = dL/dx straight to the gradients of the physical inputs (no dense dG / dF is materialised). */
+ * g_new_v = dL/dnew_v (W,6nb) straight to the gradients of the physical inputs (no dense dG / dF is materialised).
+ * Inactive worlds pass g_new_v through to gv. */
 int dsdf_dynamics_solve_backward(const double* p, const double* v, const double* mass, const double* Ibody,
                                  const double* fric, const double* rest, const double* f, const double* dt,
                                  const unsigned char* active, const int32_t* count, const int32_t* cbody,
                                  const double* cgeo, const int32_t* eq_rows, int W, int nb, int neq, int maxc,
                                  int ncontacts_smem, int fric_dirs, int stop_contact_grad, int stop_friction_grad,
-                                 const double* x, const double* lam, const double* s, const double* gz,
+                                 const double* x, const double* lam, const double* s, const double* g_new_v,
                                  double* gp, double* gv, double* gmass, double* gI, double* gfric, double* grest,
                                  double* gf, double* gdt, double* ggeo, void* stream);
+
+/* ------------------------------------------------------ step bookkeeping ----
+ * Replaces the accept / reject / halve-dt / remaining-time / time-of-contact control flow of World.step_dt and
+ * World.step (lcp_physics/physics/world.py:119-139, 241-356) for all worlds after one attempt
+ * (solve -> move -> find_contacts).  One thread per world, no host round trip except the 4 flags.
+ * In:  active (W) uint8, dt_try (W), t (W), end_t (W) or NULL (fixed_dt = False), world_dt, strict (0/1),
+ *      toc_enabled (0/1); the previous contact set (*_o) and the freshly detected one (*_n, capacity maxc).
+ * Out: accept (W) uint8; t_out = t (+ dt_try if accepted); dt_next (halved on reject, remaining time after a short
+ *      accepted sub-step); active_next (W); toc_now (W) / toc_mask (W,maxc): contacts whose body pair had no contact
+ *      before (world.py:273-274); toc_flag (W) updated in place; *_n: worlds that did not accept get the previous set
+ *      back; flags[4] (device int32) = [capacity overflow, any world still active, any time-of-contact, max contact
+ *      count after the merge].
+ */
+int dsdf_attempt_commit(int W, int nb, int maxc, const unsigned char* active, const double* dt_try,
+                        const double* t, const double* end_t, double world_dt, int strict, int toc_enabled,
+                        const int32_t* count_o, const int32_t* status_o, const int32_t* body_o,
+                        const int32_t* face_o, const double* abc_o, const double* geo_o,
+                        int32_t* count_n, int32_t* status_n, int32_t* body_n, int32_t* face_n, double* abc_n,
+                        double* geo_n, unsigned char* toc_flag, unsigned char* accept, double* t_out,
+                        double* dt_next, unsigned char* active_next, unsigned char* toc_now,
+                        unsigned char* toc_mask, int32_t* flags, void* stream);
 
 #ifdef __cplusplus
 }
