@@ -16,6 +16,27 @@
 
 namespace dsdf {
 
+// Optional per-phase cycle counters (build with -DDSDF_PHASE_PROFILE; read back with dsdf_contacts_phase_cycles).
+enum { PH_OVERLAP = 0, PH_GATHER, PH_SORT_INIT, PH_FW, PH_PUSH_COMPACT, PH_GEOMETRY, PH_FILTER, PH_APPEND, PH_FW_ITERS, PH_CAND,
+       PH_PREFILTER, PH_COUNT };
+#ifdef DSDF_PHASE_PROFILE
+__device__ unsigned long long g_phase[PH_COUNT];
+__device__ __noinline__ void ph_mark(int k) {          // k < 0: (re)start the clock
+    __shared__ long long t0;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const long long t = clock64();
+        if (k >= 0) atomicAdd(&g_phase[k], (unsigned long long)(t - t0));
+        t0 = t;
+    }
+}
+#define PH_MARK(k) ph_mark(k)
+#define PH_ADD(k, v) do { if (threadIdx.x == 0) atomicAdd(&g_phase[k], (unsigned long long)(v)); } while (0)
+#else
+#define PH_MARK(k) do {} while (0)
+#define PH_ADD(k, v) do {} while (0)
+#endif
+
 struct BodyGeom {                 // mirrors dsdf_body_geom in include/dsdf_b200.h
     int kind, nverts, nfaces, res;
     const double* verts;          // (nverts,3) body frame; world w at verts + w*vstride
@@ -28,6 +49,12 @@ struct BodyGeom {                 // mirrors dsdf_body_geom in include/dsdf_b200
     int cell_dims[3], has_cells;
     const int *fcell_start, *fcell_items, *vcell_start, *vcell_items;
 };
+
+// One out-of-line copy of the SDF evaluation for the whole contact kernel: inlining it at ~30 call sites made the
+// kernel 575 KB of SASS, far beyond the instruction cache (ncu: 18 % of stall samples "no_instructions").
+__device__ __noinline__ SdfOut<double> sdf_q(SdfShape sh, V3<double> p, bool want_n) {
+    return sdf_query<double>(sh, p, want_n);
+}
 
 __device__ __forceinline__ void load_pose(const double* p, int w, int nb, int b, Q4<double>& q, V3<double>& x) {
     const double* s = p + ((size_t)w * nb + b) * 7;
@@ -141,7 +168,7 @@ __device__ __forceinline__ bool face_is_candidate(const BodyGeom& g1, int w, int
     const V3<double> b = to_b2(load_vert(g1, w, ib), q1, x1, q2i, x2);
     const V3<double> c = to_b2(load_vert(g1, w, ic), q1, x1, q2i, x2);
     const V3<double> ctr = v3<double>(fdiv(a.x + b.x + c.x, 3.0), fdiv(a.y + b.y + c.y, 3.0), fdiv(a.z + b.z + c.z, 3.0));
-    const SdfOut<double> o = sdf_query<double>(s2, ctr, true);
+    const SdfOut<double> o = sdf_q(s2, ctr, true);
     double rad = norm3(ctr - a);
     rad = fmax(rad, norm3(ctr - b));
     rad = fmax(rad, norm3(ctr - c));
@@ -197,6 +224,8 @@ __device__ int gather_candidates(const BodyGeom& g1, int w, const SdfShape& s2, 
 // ------------------------------------------------------------------------------------------ contact geometry
 template <class S> struct ContactGeo { V3<S> n, p1, p2; S pen; };
 
+__device__ __forceinline__ SdfOut<double> sdf_qs(const SdfShape& sh, V3<double> p, bool want_n) { return sdf_q(sh, p, want_n); }
+__device__ __forceinline__ SdfOut<Dual> sdf_qs(const SdfShape& sh, V3<Dual> p, bool want_n) { return sdf_query<Dual>(sh, p, want_n); }
 template <class S> __device__ __forceinline__ V3<S> lift(V3<double> a, S proto) {
     return v3<S>(cst(proto, a.x), cst(proto, a.y), cst(proto, a.z));
 }
@@ -208,8 +237,8 @@ __device__ __forceinline__ double laplacian_fd(const SdfShape& s, V3<double> c, 
 #pragma unroll
     for (int ax = 0; ax < 3; ++ax) {
         V3<double> sh = v3<double>(ax == 0 ? h : 0.0, ax == 1 ? h : 0.0, ax == 2 ? h : 0.0);
-        const double qp = sdf_query<double>(s, c + sh, false).d;
-        const double qm = sdf_query<double>(s, c - sh, false).d;
+        const double qp = sdf_q(s, c + sh, false).d;
+        const double qm = sdf_q(s, c - sh, false).d;
         acc = acc + ((qp - 2 * d0) + qm);
     }
     return acc;
@@ -221,13 +250,13 @@ __device__ ContactGeo<S> contact_geometry(const SdfShape& s1, const SdfShape& s2
                                           V3<double> c_tri, double fd_eps, bool detach_b2) {
     S proto = q1.w;
     V3<S> c1 = lift<S>(c_tri, proto);
-    SdfOut<S> o1 = sdf_query<S>(s1, c1, true);
+    SdfOut<S> o1 = sdf_qs(s1, c1, true);
     c1 = c1 - o1.n * o1.d;
-    o1 = sdf_query<S>(s1, c1, true);
+    o1 = sdf_qs(s1, c1, true);
     V3<S> cw = qapply(q1, c1) + x1;
     V3<S> c2 = qapply(qinv(q2), cw - x2);
     if (detach_b2) c2 = strip(c2);
-    SdfOut<S> o2 = sdf_query<S>(s2, c2, true);
+    SdfOut<S> o2 = sdf_qs(s2, c2, true);
     const V3<double> c1v = v3<double>(val(c1.x), val(c1.y), val(c1.z));
     const V3<double> c2v = v3<double>(val(c2.x), val(c2.y), val(c2.z));
     const double lap1 = laplacian_fd(s1, c1v, val(o1.d), fd_eps);
@@ -352,6 +381,8 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
     const int K = min(ncand, capK);
     DirResult r; r.count = 0; r.valid = 1;
     if (K == 0) return r;
+    PH_MARK(-1);
+    PH_ADD(PH_CAND, K);
     rank_sort_int(sm.ID, sm.SC, K);
     const Q4<double> q2i = qinv(q2);
     // init: vertices in b2 frame, start at the vertex with the smallest SDF (contacts.py:57-61)
@@ -362,7 +393,7 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
         for (int v = 0; v < 3; ++v) {
             const V3<double> t = to_b2(load_vert(g1, w, g1.faces[3 * f + v]), q1, x1, q2i, x2);
             sm.P[(3 * v + 0) * capK + k] = t.x; sm.P[(3 * v + 1) * capK + k] = t.y; sm.P[(3 * v + 2) * capK + k] = t.z;
-            const double d = sdf_query<double>(s2, t, false).d;
+            const double d = sdf_q(s2, t, false).d;
             if (v == 0 || d < best) { best = d; bi = v; }
         }
 #pragma unroll
@@ -376,13 +407,14 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
     // (|gain| <= tol) keeps its x, so re-evaluating it would reproduce the same decision: it is skipped from then on
     // (TMP[k] = 1) -- the reference recomputes it every iteration with identical results.
     for (int k = tid; k < K; k += nt) sm.TMP[k] = 0;
+    PH_MARK(PH_SORT_INIT);
     for (int it = 0; it < 32; ++it) {
         int any_active = 0, any_pen = 0;
         // phase 1: evaluate (no state change until the exit test is known)
         for (int k = tid; k < K; k += nt) {
             if (sm.TMP[k]) { sm.SC[k] = -1; continue; }              // frozen, not penetrating
             const V3<double> x = v3<double>(sm.X[k], sm.X[capK + k], sm.X[2 * capK + k]);
-            const SdfOut<double> o = sdf_query<double>(s2, x, true);
+            const SdfOut<double> o = sdf_q(s2, x, true);
             double dmin = 0.0; int pick = 0;
 #pragma unroll
             for (int v = 0; v < 3; ++v) {
@@ -402,6 +434,7 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
         // __syncthreads_or returns a predicate, not a bitwise OR: one barrier per flag
         const int blk_active = __syncthreads_or(any_active);
         const int blk_pen = __syncthreads_or(any_pen);
+        PH_ADD(PH_FW_ITERS, 1);
         if (!blk_active || blk_pen) break;
         const double gamma = 2.0 / (it + 2.0);
         for (int k = tid; k < K; k += nt) {
@@ -419,6 +452,7 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
         __syncthreads();
     }
     __syncthreads();
+    PH_MARK(PH_FW);
     // push onto b1's surface and final threshold (contacts.py:84-91)
     const Q4<double> rel = qmul(q2i, q1);
     for (int k = tid; k < K; k += nt) {
@@ -428,11 +462,11 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
         const double a = sm.ABC[k], b = sm.ABC[capK + k], c = sm.ABC[2 * capK + k];
         const V3<double> xb1 = v3<double>(va.x * a + vb.x * b + vc.x * c, va.y * a + vb.y * b + vc.y * c,
                                           va.z * a + vb.z * b + vc.z * c);
-        const SdfOut<double> o1 = sdf_query<double>(s1, xb1, true);
+        const SdfOut<double> o1 = sdf_q(s1, xb1, true);
         const V3<double> dir = qapply(rel, o1.n);
         const V3<double> x = v3<double>(sm.X[k] - o1.d * dir.x, sm.X[capK + k] - o1.d * dir.y,
                                         sm.X[2 * capK + k] - o1.d * dir.z);
-        const double d = sdf_query<double>(s2, x, false).d;
+        const double d = sdf_q(s2, x, false).d;
         sm.SC[k] = d <= eps ? 1 : 0;
         // stash the body-frame triangle point for the geometry pass
         sm.X[k] = xb1.x; sm.X[capK + k] = xb1.y; sm.X[2 * capK + k] = xb1.z;
@@ -462,6 +496,7 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
             __syncthreads();
         }
     }
+    PH_MARK(PH_PUSH_COMPACT);
     // contact geometry for every pre-filter contact (the reference's no_grad _compute_contacts)
     int bad = 0;
     for (int k = tid; k < total; k += nt) {
@@ -475,6 +510,8 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
     }
     r.valid = !__syncthreads_or(bad);
     r.count = total;
+    PH_ADD(PH_PREFILTER, total);
+    PH_MARK(PH_GEOMETRY);
     return r;
 }
 
@@ -769,7 +806,10 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
 
 // One CTA per world: broad phase, _overlap, and both search directions of every body pair, fused.
 enum { CONTACT_THREADS = 128 };
-__global__ void __launch_bounds__(CONTACT_THREADS, 3)
+#ifndef DSDF_CONTACT_MINBLOCKS
+#define DSDF_CONTACT_MINBLOCKS 3
+#endif
+__global__ void __launch_bounds__(CONTACT_THREADS, DSDF_CONTACT_MINBLOCKS)
 contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs, int npairs,
                 const double* __restrict__ p, const double* __restrict__ shape, const unsigned char* __restrict__ active,
                 int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
@@ -804,7 +844,9 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
             hit = hit && (fabs(dc) <= hi + hj);
         }
         int ov = 0;
+        PH_MARK(-1);
         if (hit) ov = any_vertex_in_cube(geom[bi], w, qi, xi, qj, xj, sj) && any_vertex_in_cube(geom[bj], w, qj, xj, qi, xi, si);
+        PH_MARK(PH_OVERLAP);
         if (!ov) {
             if (pre_cnt && tid == 0) { pre_cnt[(size_t)w * ndirs + 2 * pair] = -1; pre_cnt[(size_t)w * ndirs + 2 * pair + 1] = -1; }
             continue;
@@ -817,15 +859,19 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
             const SdfShape s2 = body_shape(geom[i2], shape, w, nb, i2);
             const Q4<double> q1 = rev ? qj : qi, q2 = rev ? qi : qj;
             const V3<double> x1 = rev ? xj : xi, x2 = rev ? xi : xj;
+            PH_MARK(-1);
             const int ncand = gather_candidates(g1, w, s2, q1, x1, q2, x2, eps, capK, sm.ID, &s_cnt);
+            PH_MARK(PH_GATHER);
             if (ncand > capK) status |= 1;
             DirResult r = search_direction(sm, capK, g1, s1, s2, q1, x1, q2, x2, w, ncand, eps, tol, fd_eps, detach_b2 != 0);
             if (pre_cnt) {
                 if (tid == 0) pre_cnt[(size_t)w * ndirs + d] = r.count;
                 for (int k = tid; k < r.count; k += nt) pre_ids[((size_t)w * ndirs + d) * capK + k] = sm.ID[k];
             }
+            PH_MARK(-1);
             if (r.valid) status |= filter_contacts(sm, capK, r.count, eps);
             else { status |= 8; for (int k = tid; k < r.count; k += nt) sm.KEEP[k] = 1; __syncthreads(); }
+            PH_MARK(PH_FILTER);
             // append kept contacts in ascending face order
             for (int k = tid; k < r.count; k += nt) sm.SC[k] = sm.KEEP[k];
             int nk = 0;
@@ -845,6 +891,7 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
             if (nout + nk > maxc) status |= 2;
             nout = min(nout + nk, maxc);
             __syncthreads();
+            PH_MARK(PH_APPEND);
             if (!r.valid) {                       // contacts.py:238-240: reverse direction only after a valid first one
                 if (rev == 0 && pre_cnt && tid == 0) pre_cnt[(size_t)w * ndirs + d + 1] = -1;
                 break;
@@ -927,6 +974,17 @@ int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, int n
                                           eps, tol, fd_eps, body_eps, detach_b2, capK, maxc, count, cbody, cface, cabc,
                                           cgeo, wstatus, pre_ids, pre_cnt);
     return (int)cudaGetLastError();
+}
+
+int dsdf_contacts_phase_cycles(unsigned long long* out8, int reset) {   /* out8: PH_COUNT = 11 counters */
+#ifdef DSDF_PHASE_PROFILE
+    if (out8 && cudaMemcpyFromSymbol(out8, g_phase, sizeof(unsigned long long) * PH_COUNT) != cudaSuccess) return 1;
+    if (reset) { unsigned long long z[PH_COUNT] = {0}; if (cudaMemcpyToSymbol(g_phase, z, sizeof(z)) != cudaSuccess) return 1; }
+    return 0;
+#else
+    (void)out8; (void)reset;
+    return -1;
+#endif
 }
 
 int dsdf_contact_geometry_backward(const dsdf_body_geom* geom, const double* p, const double* shape, int W, int nb,

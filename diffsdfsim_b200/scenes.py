@@ -92,6 +92,7 @@ def build_world(spec, device=None, params=None, **world_kw):
               strict_no_penetration=spec['strict_no_penetration'],
               time_of_contact_diff=spec['time_of_contact_diff'])
     kw.update(world_kw)
+    kw.setdefault('device', device)
     return World3D(bodies, cons, **kw)
 
 

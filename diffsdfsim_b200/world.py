@@ -81,8 +81,14 @@ class World3D:
             raise NotImplementedError('post_stab (off by default in the reference) is not built yet')
         self.engine = get_instance(engines_module, engine)
         self.contact_callback = get_instance(contacts_module, contact_callback)
-        self.device = torch.device(device) if device is not None else default_device()
         self.bodies = list(bodies)
+        if device is None:
+            # the device the bodies live on (first CUDA tensor found), else the default device
+            devs = [b.p.device for b in self.bodies if b.p.is_cuda] + [b.mass.device for b in self.bodies if b.mass.is_cuda]
+            device = devs[0] if devs else default_device()
+        self.device = torch.device(device)
+        if self.device.type == 'cuda' and self.device.index is None:
+            self.device = torch.device('cuda', torch.cuda.current_device())
         self.nb = len(self.bodies)
         self.W = max(b.batch() for b in self.bodies)
         self.batched = self.W > 1
@@ -144,7 +150,8 @@ class World3D:
         self._f_vectorized = any(getattr(f, 'vectorized', False) for b in self.bodies for f in b.forces)
         self.contact_set = self.detector.new_set()
         self.contact_geo = None
-        self.find_contacts()
+        with self._on_device():
+            self.find_contacts()
         if self.strict_no_pen:
             assert not bool(((self.contact_set.status & 8) != 0).any()), \
                 'Interpenetration at start:\n{}'.format(self.contacts_of(0))
@@ -253,6 +260,10 @@ class World3D:
         return cs
 
     # ------------------------------------------------------------------ stepping
+    def _on_device(self):
+        import contextlib
+        return torch.cuda.device(self.device) if self.device.type == 'cuda' else contextlib.nullcontext()
+
     def step_forces(self):
         """Generalized forces of the current step.  Forces that only see the step's start time (the default, see
         forces.py) are evaluated once per step and reused by every sub-step attempt."""
@@ -262,6 +273,10 @@ class World3D:
 
     def step(self, fixed_dt=False):
         """world.py:119-139.  Returns had_contacts: python bool for a single world, (W,) bool tensor otherwise."""
+        with self._on_device():                      # kernels launch on the world's device, whatever is current
+            return self._step(fixed_dt)
+
+    def _step(self, fixed_dt):
         st = self.state
         self._undo = (st.p, st.v, self.contact_set, self.contact_geo, self.t, self.t_host, self.toc_flag.clone(),
                       self.last_dt, len(self.trajectory), self._any_toc_flag)

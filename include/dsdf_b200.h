@@ -149,6 +149,10 @@ int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, int n
                          int W, int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
                          int capK, int maxc, int32_t* count, int32_t* cbody, int32_t* cface, double* cabc, double* cgeo,
                          int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, void* stream);
+/* Profiling aid: cumulative SM cycles (thread 0 of every CTA) per phase of the contact kernel
+ * [overlap, gather, sort+init, frank-wolfe, push+compact, geometry, filter, append]; returns -1 unless the library
+ * was built with -DDSDF_PHASE_PROFILE (DSDF_PHASE_PROFILE=1 python -m diffsdfsim_b200.build). Host pointer out8. */
+int dsdf_contacts_phase_cycles(unsigned long long* out8, int reset);
 /* VJP of cgeo w.r.t. the poses (the reference's grad-enabled second _compute_contacts, contacts.py:262-264):
  * gp (W,nb,7) from ggeo (W,maxc,10). */
 int dsdf_contact_geometry_backward(const dsdf_body_geom* geom, const double* p, const double* shape, int W, int nb,
