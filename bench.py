@@ -219,24 +219,33 @@ def sdf_query_roofline(device, W=256, R=64, N=1 << 17, reps=5):
     P = torch.stack(torch.meshgrid(u, u, u, indexing='ij'), -1).reshape(-1, 3)[:N]
     pts = (P[None] + 0.005 * torch.rand(W, N, 3, generator=g, dtype=torch.float64)).to(device).contiguous()
     shape = torch.tensor([0.0, 0.0, 0.0, 1.0], dtype=torch.float64, device=device).expand(W, 4).contiguous()
-    with torch.no_grad():
-        for _ in range(3):
-            ops.sdf_query('grid', shape, pts, grid=grid, want_dir=True)
-    torch.cuda.synchronize()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-    with torch.no_grad():
-        for a, b in ev:
-            a.record()
-            ops.sdf_query('grid', shape, pts, grid=grid, want_dir=True)
-            b.record()
-    torch.cuda.synchronize()
-    ms = sum(a.elapsed_time(b) for a, b in ev) / reps
+    def run(want_dir):
+        with torch.no_grad():
+            for _ in range(3):
+                ops.sdf_query('grid', shape, pts, grid=grid, want_dir=want_dir)
+            torch.cuda.synchronize()
+            ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+            for a, b in ev:
+                a.record()
+                ops.sdf_query('grid', shape, pts, grid=grid, want_dir=want_dir)
+                b.record()
+            torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in ev) / reps
+
+    ms = run(True)
     alg = W * (N * 56 + R ** 3 * 8)
     ach = alg / 1e9 / (ms / 1e3)
+    ms_v = run(False)                       # value only: 24 B in + 8 B out per point, 8 voxel reads, ~60 FP64 ops
+    alg_v = W * (N * 32 + R ** 3 * 8)
+    ach_v = alg_v / 1e9 / (ms_v / 1e3)
     return {'kernel': 'dsdf_sdf_query (grid, per-world %d^3 f64 grids, W=%d, N=%d pts/world, value+direction)' % (R, W, N),
             'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
             'peak_source': which, 'avg_launch_ms': ms, 'algorithmic_bytes_per_launch': alg,
-            'l2_policy': 'inputs (%.2f GB) larger than L2' % (alg / 1e9), 'traffic': ncu_traffic('sdf_query_kernel')}
+            'l2_policy': 'inputs (%.2f GB) larger than L2' % (alg / 1e9), 'traffic': ncu_traffic('sdf_query_grid_kernel'),
+            'note': 'value+direction costs ~200 FP64 instr/point = 2.8 instr/B, the FP64:HBM ridge of B200: the kernel is '
+                    'co-limited by the FP64 pipe (DESIGN.md s5)',
+            'value_only': {'achieved': ach_v, 'frac': ach_v / peaks['hbm_gbs'], 'avg_launch_ms': ms_v,
+                           'algorithmic_bytes_per_launch': alg_v}}
 
 
 def ncu_traffic(kernel):

@@ -16,11 +16,12 @@ OUT = os.path.join(HERE, 'libdsdf_b200.so')
 OBJ = os.path.join(HERE, 'csrc', '_build')
 NVCC = os.environ.get('NVCC', '/usr/local/cuda/bin/nvcc')
 FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
-         '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr']
+         '-Xcompiler', '-fPIC', '-Xptxas', '-v', '--expt-relaxed-constexpr'] + os.environ.get('DSDF_EXTRA_FLAGS', '').split()
 # Per-file extras.  The contact refinement makes round-off-level decisions (arg-min ties in Frank-Wolfe, which
 # body's normal to use on flat-flat contacts) that the reference takes with un-fused IEEE multiply/add (torch
 # element-wise ops): compile that file without FMA contraction so the same ties break the same way.
-EXTRA = {'dsdf_contacts.cu': ['-fmad=false'] + (['-DDSDF_PHASE_PROFILE'] if os.environ.get('DSDF_PHASE_PROFILE') else [])
+_NOFMA = ['-fmad=false']
+EXTRA = {'dsdf_contacts_bwd.cu': _NOFMA, 'dsdf_contacts.cu': _NOFMA + (['-DDSDF_PHASE_PROFILE'] if os.environ.get('DSDF_PHASE_PROFILE') else [])
          + (['-DDSDF_CONTACT_MINBLOCKS=' + os.environ['DSDF_CONTACT_MINBLOCKS']] if os.environ.get('DSDF_CONTACT_MINBLOCKS') else [])}
 
 

@@ -146,7 +146,7 @@ class ContactSet:
 class ContactDetector:
     """Owns the work buffers of ``dsdf_contacts_detect`` for one batched world."""
 
-    def __init__(self, table, pairs, W, nb, device, capK=512, maxc=32, record_prefilter=False):
+    def __init__(self, table, pairs, W, nb, device, capK=384, maxc=32, record_prefilter=False):
         _lib.lib()
         self.table, self.W, self.nb, self.capK, self.maxc = table, W, nb, capK, maxc
         self.npairs = len(pairs)

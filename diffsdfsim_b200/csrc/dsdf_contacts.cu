@@ -11,8 +11,8 @@
 // Kernels: contacts_kernel (one CTA per world, everything fused: cell-culled vertex/face scans with warp-ballot
 // compaction into shared memory, FW with the reference's pair-global early exit, contact geometry, filter) and
 // contact_geometry_bwd_kernel (forward-mode duals w.r.t. the two poses).
-#include "dsdf_dense.cuh"
-#include "dsdf_sdf.cuh"
+#define DSDF_OUTLINE_MATH
+#include "dsdf_contact_geo.cuh"
 
 namespace dsdf {
 
@@ -36,47 +36,6 @@ __device__ __noinline__ void ph_mark(int k) {          // k < 0: (re)start the c
 #define PH_MARK(k) do {} while (0)
 #define PH_ADD(k, v) do {} while (0)
 #endif
-
-struct BodyGeom {                 // mirrors dsdf_body_geom in include/dsdf_b200.h
-    int kind, nverts, nfaces, res;
-    const double* verts;          // (nverts,3) body frame; world w at verts + w*vstride
-    const int* faces;             // (nfaces,3)
-    const double* grid;           // res^3; world w at grid + w*gstride
-    long long vstride, gstride;
-    // uniform cell index over the body-frame mesh (faces binned by centroid, vertices by position); has_cells = 0 when
-    // the vertices are per-world (the kernels then scan the whole mesh)
-    double cell_lo[3], cell_inv;
-    int cell_dims[3], has_cells;
-    const int *fcell_start, *fcell_items, *vcell_start, *vcell_items;
-};
-
-// One out-of-line copy of the SDF evaluation for the whole contact kernel: inlining it at ~30 call sites made the
-// kernel 575 KB of SASS, far beyond the instruction cache (ncu: 18 % of stall samples "no_instructions").
-__device__ __noinline__ SdfOut<double> sdf_q(SdfShape sh, V3<double> p, bool want_n) {
-    return sdf_query<double>(sh, p, want_n);
-}
-
-__device__ __forceinline__ void load_pose(const double* p, int w, int nb, int b, Q4<double>& q, V3<double>& x) {
-    const double* s = p + ((size_t)w * nb + b) * 7;
-    q = q4<double>(s[0], s[1], s[2], s[3]);
-    x = v3<double>(s[4], s[5], s[6]);
-}
-__device__ __forceinline__ SdfShape body_shape(const BodyGeom& g, const double* shape, int w, int nb, int b) {
-    const double* s = shape + ((size_t)w * nb + b) * 4;
-    SdfShape sh;
-    sh.kind = g.kind; sh.a = s[0]; sh.b = s[1]; sh.c = s[2]; sh.scale = s[3];
-    sh.grid = g.grid ? g.grid + (size_t)w * g.gstride : nullptr;
-    sh.res = g.res;
-    return sh;
-}
-__device__ __forceinline__ V3<double> load_vert(const BodyGeom& g, int w, int vi) {
-    const double* v = g.verts + (size_t)w * g.vstride + (size_t)vi * 3;
-    return v3<double>(v[0], v[1], v[2]);
-}
-// vertex of b1 (body frame) -> world -> b2 frame, same operation order as contacts.py:42 / bodies.py:718
-__device__ __forceinline__ V3<double> to_b2(V3<double> v, Q4<double> q1, V3<double> x1, Q4<double> q2i, V3<double> x2) {
-    return qapply(q2i, (qapply(q1, v) + x1) - x2);
-}
 
 // ------------------------------------------------------------------------------------------ conservative spatial cull
 // A face can only become a candidate, and a vertex can only witness _overlap, if its position in b2's frame lies in
@@ -221,60 +180,11 @@ __device__ int gather_candidates(const BodyGeom& g1, int w, const SdfShape& s2, 
     return *s_cnt;
 }
 
-// ------------------------------------------------------------------------------------------ contact geometry
-template <class S> struct ContactGeo { V3<S> n, p1, p2; S pen; };
-
-__device__ __forceinline__ SdfOut<double> sdf_qs(const SdfShape& sh, V3<double> p, bool want_n) { return sdf_q(sh, p, want_n); }
-__device__ __forceinline__ SdfOut<Dual> sdf_qs(const SdfShape& sh, V3<Dual> p, bool want_n) { return sdf_query<Dual>(sh, p, want_n); }
-template <class S> __device__ __forceinline__ V3<S> lift(V3<double> a, S proto) {
-    return v3<S>(cst(proto, a.x), cst(proto, a.y), cst(proto, a.z));
-}
-__device__ __forceinline__ V3<double> strip(V3<double> a) { return a; }
-__device__ __forceinline__ V3<Dual> strip(V3<Dual> a) { return v3<Dual>(Dual(a.x.v), Dual(a.y.v), Dual(a.z.v)); }
-
-__device__ __forceinline__ double laplacian_fd(const SdfShape& s, V3<double> c, double d0, double h) {
-    double acc = 0.0;
-#pragma unroll
-    for (int ax = 0; ax < 3; ++ax) {
-        V3<double> sh = v3<double>(ax == 0 ? h : 0.0, ax == 1 ? h : 0.0, ax == 2 ? h : 0.0);
-        const double qp = sdf_q(s, c + sh, false).d;
-        const double qm = sdf_q(s, c - sh, false).d;
-        acc = acc + ((qp - 2 * d0) + qm);
-    }
-    return acc;
-}
-
-// contacts.py:161-214 for one contact; c_tri = sum(abc * local verts of the face) is pose-independent.
-template <class S>
-__device__ ContactGeo<S> contact_geometry(const SdfShape& s1, const SdfShape& s2, Q4<S> q1, V3<S> x1, Q4<S> q2, V3<S> x2,
-                                          V3<double> c_tri, double fd_eps, bool detach_b2) {
-    S proto = q1.w;
-    V3<S> c1 = lift<S>(c_tri, proto);
-    SdfOut<S> o1 = sdf_qs(s1, c1, true);
-    c1 = c1 - o1.n * o1.d;
-    o1 = sdf_qs(s1, c1, true);
-    V3<S> cw = qapply(q1, c1) + x1;
-    V3<S> c2 = qapply(qinv(q2), cw - x2);
-    if (detach_b2) c2 = strip(c2);
-    SdfOut<S> o2 = sdf_qs(s2, c2, true);
-    const V3<double> c1v = v3<double>(val(c1.x), val(c1.y), val(c1.z));
-    const V3<double> c2v = v3<double>(val(c2.x), val(c2.y), val(c2.z));
-    const double lap1 = laplacian_fd(s1, c1v, val(o1.d), fd_eps);
-    const double lap2 = laplacian_fd(s2, c2v, val(o2.d), fd_eps);
-    const bool stable = fabs(lap2) < fabs(lap1);
-    ContactGeo<S> g;
-    g.n = stable ? qapply(q2, o2.n) : neg(qapply(q1, o1.n));
-    g.p2 = qapply(q2, c2 - o2.n * o2.d);
-    g.p1 = qapply(q1, c1);
-    g.pen = -o2.d;
-    return g;
-}
-
 // ------------------------------------------------------------------------------------------ block helpers
 // Rank sorts: every element counts how many precede it (O(n^2/threads) compares on broadcast shared loads, two
 // barriers) -- far cheaper here than a bitonic network's ~45 barrier-separated passes for n <= 1024.
 enum { SORT_MAX_ROUNDS = 8 };                                   // n <= SORT_MAX_ROUNDS * blockDim.x
-__device__ inline void rank_sort_int(int* a, int* tmp, int n) {  // ascending; DISTINCT values; a 16-byte aligned
+__device__ __noinline__ void rank_sort_int(int* a, int* tmp, int n) {  // ascending; DISTINCT values; a 16-byte aligned
     for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const int x = a[i];
         int r = 0, j = 0;
@@ -290,10 +200,10 @@ __device__ inline void rank_sort_int(int* a, int* tmp, int n) {  // ascending; D
     __syncthreads();
 }
 // (key, key2, payload) ascending lexicographically, in place
-__device__ inline void rank_sort_kv(double* key, double* key2, int* pay, int n) {
+__device__ __noinline__ void rank_sort_kv(double* key, double* key2, int* pay, int n) {
     double k1[SORT_MAX_ROUNDS], k2[SORT_MAX_ROUNDS];
     int pl[SORT_MAX_ROUNDS], rk[SORT_MAX_ROUNDS];
-#pragma unroll
+#pragma unroll 1
     for (int rd = 0; rd < SORT_MAX_ROUNDS; ++rd) {
         const int i = rd * blockDim.x + threadIdx.x;
         rk[rd] = -1;
@@ -309,14 +219,14 @@ __device__ inline void rank_sort_kv(double* key, double* key2, int* pay, int n) 
         }
     }
     __syncthreads();
-#pragma unroll
+#pragma unroll 1
     for (int rd = 0; rd < SORT_MAX_ROUNDS; ++rd)
         if (rk[rd] >= 0) { key[rk[rd]] = k1[rd]; key2[rk[rd]] = k2[rd]; pay[rk[rd]] = pl[rd]; }
     __syncthreads();
 }
 // order-preserving compaction offsets: returns exclusive prefix of flag over index order 0..n-1; *total = sum.
 // idx loop layout: element e handled by thread e % nt in round e / nt.  scan buffer: n ints.
-__device__ inline void block_exclusive_scan(int* buf, int n, int* total) {
+__device__ __noinline__ void block_exclusive_scan(int* buf, int n, int* total) {
     // simple Hillis-Steele over shared memory (n <= 1024), in place, exclusive
     __syncthreads();
     __shared__ int carry;
@@ -349,6 +259,11 @@ __device__ inline void block_exclusive_scan(int* buf, int n, int* total) {
     *total = carry;
     __syncthreads();
 }
+
+// out-of-line block reductions (the template in dsdf_dense.cuh is inlined at every call site)
+__device__ __noinline__ double bred_sum(double v, double* red) { return block_reduce<RED_SUM>(v, red); }
+__device__ __noinline__ double bred_min(double v, double* red) { return block_reduce<RED_MIN>(v, red); }
+__device__ __noinline__ double bred_max(double v, double* red) { return block_reduce<RED_MAX>(v, red); }
 
 // ------------------------------------------------------------------------------------------ refine kernel
 struct RefineSmem {
@@ -570,8 +485,8 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
             s0 += PX[k]; s1 += PY[k]; s2 += PZ[k];
             mx = fmax(mx, fmax(fabs(PX[k]), fmax(fabs(PY[k]), fabs(PZ[k]))));
         }
-        s0 = block_reduce<RED_SUM>(s0, sm.red); s1 = block_reduce<RED_SUM>(s1, sm.red);
-        s2 = block_reduce<RED_SUM>(s2, sm.red); mx = block_reduce<RED_MAX>(mx, sm.red);
+        s0 = bred_sum(s0, sm.red); s1 = bred_sum(s1, sm.red);
+        s2 = bred_sum(s2, sm.red); mx = bred_max(mx, sm.red);
         const double m0 = s0 / m, m1 = s1 / m, m2 = s2 / m;
         double v0 = 0, v1 = 0, v2 = 0;
         for (int e = tid; e < m; e += nt) {
@@ -579,9 +494,9 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
             v0 += (PX[k] - m0) * (PX[k] - m0); v1 += (PY[k] - m1) * (PY[k] - m1); v2 += (PZ[k] - m2) * (PZ[k] - m2);
         }
         double var[3];
-        var[0] = block_reduce<RED_SUM>(v0, sm.red) / (m - 1);
-        var[1] = block_reduce<RED_SUM>(v1, sm.red) / (m - 1);
-        var[2] = block_reduce<RED_SUM>(v2, sm.red) / (m - 1);
+        var[0] = bred_sum(v0, sm.red) / (m - 1);
+        var[1] = bred_sum(v1, sm.red) / (m - 1);
+        var[2] = bred_sum(v2, sm.red) / (m - 1);
         // axis order: amin = first argmin (dropped first), then of the remaining two the first argmin is dropped next
         int amin = 0;
         if (var[1] < var[amin]) amin = 1;
@@ -593,7 +508,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
         // extremes along the 1-D axis (first min / first max index, like argmin/argmax)
         double lo = INFINITY, hi = -INFINITY;
         for (int e = tid; e < m; e += nt) { const double c = PA[keep1][sm.HI[e]]; lo = fmin(lo, c); hi = fmax(hi, c); }
-        lo = block_reduce<RED_MIN>(lo, sm.red); hi = block_reduce<RED_MAX>(hi, sm.red);
+        lo = bred_min(lo, sm.red); hi = bred_max(hi, sm.red);
         __shared__ int s_lo, s_hi;
         if (tid == 0) { s_lo = 0x7fffffff; s_hi = 0x7fffffff; }
         __syncthreads();
@@ -618,7 +533,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
             const double dl = lab > 0 ? fdiv(norm3(cross(AB, AP)), lab) : norm3(AP);
             far = fmax(far, dl);
         }
-        far = block_reduce<RED_MAX>(far, sm.red);
+        far = bred_max(far, sm.red);
         __shared__ int s_far;
         if (tid == 0) s_far = 0x7fffffff;
         __syncthreads();
@@ -640,7 +555,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
                 const int k = sm.HI[e];
                 th = fmax(th, fdiv(fabs(dot(nrm, v3<double>(PX[k], PY[k], PZ[k]) - A)), ln));
             }
-            th = block_reduce<RED_MAX>(th, sm.red);
+            th = bred_max(th, sm.red);
             flat3 = !(th > 4.0 * distround(3, mx));
         } else {
             flat3 = true;
@@ -668,8 +583,8 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
                 fd2 = fmax(fd2, l2 > 0 ? fdiv(fabs(cr), l2) : fsqrt((px - ax_) * (px - ax_) + (py - ay_) * (py - ay_)));
                 mx2 = fmax(mx2, fmax(fabs(px), fabs(py)));
             }
-            fd2 = block_reduce<RED_MAX>(fd2, sm.red);
-            mx2 = block_reduce<RED_MAX>(mx2, sm.red);
+            fd2 = bred_max(fd2, sm.red);
+            mx2 = bred_max(mx2, sm.red);
             line2 = !(fd2 > 3.0 * distround(2, mx2));
         }
         if (line2) {
@@ -707,9 +622,9 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
                 }
             }
             const int lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-#pragma unroll
+#pragma unroll 1
             for (int q = 0; q < 8; ++q) {
-#pragma unroll
+#pragma unroll 1
                 for (int o = 16; o > 0; o >>= 1) {
                     const double ov = __shfl_xor_sync(DSDF_FULL, bv[q], o);
                     const int oi = __shfl_xor_sync(DSDF_FULL, bi[q], o);
@@ -717,7 +632,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
                 }
                 if (lane == 0) { s_ev[warp][q] = bv[q]; s_ei[warp][q] = bi[q]; }
             }
-            const double mxc_all = block_reduce<RED_MAX>(mxl, sm.red);     // (contains the barriers)
+            const double mxc_all = bred_max(mxl, sm.red);     // (contains the barriers)
             if (tid < 8) {
                 double v = -INFINITY; int ix = 0x7fffffff;
                 for (int ww = 0; ww < nw; ++ww)
@@ -807,7 +722,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
 // One CTA per world: broad phase, _overlap, and both search directions of every body pair, fused.
 enum { CONTACT_THREADS = 128 };
 #ifndef DSDF_CONTACT_MINBLOCKS
-#define DSDF_CONTACT_MINBLOCKS 3
+#define DSDF_CONTACT_MINBLOCKS 4
 #endif
 __global__ void __launch_bounds__(CONTACT_THREADS, DSDF_CONTACT_MINBLOCKS)
 contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs, int npairs,
@@ -901,57 +816,6 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
     if (tid == 0) { count[w] = nout; wstatus[w] = status; }
 }
 
-// One CTA per world.  Work item = (contact k, seed j): j < 7 seeds component j of body i1's pose, j >= 7 component
-// j - 7 of body i2's (forward-mode dual through contact_geometry); the 14 partials of every contact go to shared
-// memory and thread (body, component) then sums them over the contacts in index order (deterministic).
-__global__ void __launch_bounds__(128)
-contact_geometry_bwd_kernel(const BodyGeom* __restrict__ geom, const double* __restrict__ p,
-                            const double* __restrict__ shape, int nb, double fd_eps, int detach_b2, int maxc,
-                            const int* __restrict__ count, const int* __restrict__ cbody, const int* __restrict__ cface,
-                            const double* __restrict__ cabc, const double* __restrict__ ggeo, double* __restrict__ gp) {
-    extern __shared__ double part[];          // [maxc][14]
-    const int w = blockIdx.x;
-    const int nc = min(count[w], maxc);
-    for (int item = threadIdx.x; item < nc * 14; item += blockDim.x) {
-        const int k = item / 14, j = item % 14;
-        const size_t oo = (size_t)w * maxc + k;
-        const int i1 = cbody[2 * oo], i2 = cbody[2 * oo + 1];
-        const BodyGeom g1 = geom[i1];
-        const SdfShape s1 = body_shape(g1, shape, w, nb, i1);
-        const SdfShape s2 = body_shape(geom[i2], shape, w, nb, i2);
-        const double* P1 = p + ((size_t)w * nb + i1) * 7;
-        const double* P2 = p + ((size_t)w * nb + i2) * 7;
-        const int s1seed = j < 7 ? j : -1, s2seed = j >= 7 ? j - 7 : -1;
-        auto D = [](const double* s, int k_, int seed) { return Dual(s[k_], seed == k_ ? 1.0 : 0.0); };
-        Q4<Dual> q1 = q4<Dual>(D(P1, 0, s1seed), D(P1, 1, s1seed), D(P1, 2, s1seed), D(P1, 3, s1seed));
-        V3<Dual> x1 = v3<Dual>(D(P1, 4, s1seed), D(P1, 5, s1seed), D(P1, 6, s1seed));
-        Q4<Dual> q2 = q4<Dual>(D(P2, 0, s2seed), D(P2, 1, s2seed), D(P2, 2, s2seed), D(P2, 3, s2seed));
-        V3<Dual> x2 = v3<Dual>(D(P2, 4, s2seed), D(P2, 5, s2seed), D(P2, 6, s2seed));
-        const int f = cface[oo];
-        const V3<double> va = load_vert(g1, w, g1.faces[3 * f]), vb = load_vert(g1, w, g1.faces[3 * f + 1]),
-                         vc = load_vert(g1, w, g1.faces[3 * f + 2]);
-        const double a = cabc[3 * oo], b = cabc[3 * oo + 1], c = cabc[3 * oo + 2];
-        const V3<double> ct = v3<double>(va.x * a + vb.x * b + vc.x * c, va.y * a + vb.y * b + vc.y * c,
-                                         va.z * a + vb.z * b + vc.z * c);
-        const ContactGeo<Dual> g = contact_geometry<Dual>(s1, s2, q1, x1, q2, x2, ct, fd_eps, detach_b2 != 0);
-        const double* gg = ggeo + 10 * oo;
-        part[item] = gg[0] * g.n.x.d + gg[1] * g.n.y.d + gg[2] * g.n.z.d + gg[3] * g.p1.x.d + gg[4] * g.p1.y.d +
-                     gg[5] * g.p1.z.d + gg[6] * g.p2.x.d + gg[7] * g.p2.y.d + gg[8] * g.p2.z.d + gg[9] * g.pen.d;
-    }
-    __syncthreads();
-    for (int t = threadIdx.x; t < nb * 7; t += blockDim.x) {
-        const int body = t / 7, comp = t % 7;
-        double acc = 0.0;
-        for (int k = 0; k < nc; ++k) {
-            const size_t oo = (size_t)w * maxc + k;
-            const int i1 = cbody[2 * oo], i2 = cbody[2 * oo + 1];
-            if (body == i1) acc += part[k * 14 + comp];
-            if (body == i2) acc += part[k * 14 + 7 + comp];
-        }
-        gp[((size_t)w * nb + body) * 7 + comp] = acc;
-    }
-}
-
 }  // namespace dsdf
 
 using namespace dsdf;
@@ -985,16 +849,6 @@ int dsdf_contacts_phase_cycles(unsigned long long* out8, int reset) {   /* out8:
     (void)out8; (void)reset;
     return -1;
 #endif
-}
-
-int dsdf_contact_geometry_backward(const dsdf_body_geom* geom, const double* p, const double* shape, int W, int nb,
-                                   double fd_eps, int detach_b2, int maxc, const int32_t* count, const int32_t* cbody,
-                                   const int32_t* cface, const double* cabc, const double* ggeo, double* gp, void* stream) {
-    if (W <= 0 || nb <= 0 || maxc <= 0) return -1;
-    contact_geometry_bwd_kernel<<<W, 128, (size_t)maxc * 14 * sizeof(double), (cudaStream_t)stream>>>(reinterpret_cast<const BodyGeom*>(geom), p, shape, nb,
-                                                                    fd_eps, detach_b2, maxc, count, cbody, cface, cabc,
-                                                                    ggeo, gp);
-    return (int)cudaGetLastError();
 }
 
 }  // extern "C"

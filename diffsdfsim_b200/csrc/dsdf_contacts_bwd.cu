@@ -1,0 +1,77 @@
+// Pose gradients of the contact geometry: VJP of the reference's grad-enabled second _compute_contacts
+// (sdf_physics/physics3d/contacts.py:262-264) by forward-mode duals of the same device code.  Separate translation unit
+// from the detection kernel so that the small backward kernel keeps its math inlined (the detection kernel outlines it
+// to fit the instruction cache); same -fmad=false so both evaluate the identical expression tree.
+#include "dsdf_contact_geo.cuh"
+#include "../../include/dsdf_b200.h"
+
+namespace dsdf {
+
+// One CTA per world.  Work item = (contact k, seed j): j < 7 seeds component j of body i1's pose, j >= 7 component
+// j - 7 of body i2's (forward-mode dual through contact_geometry); the 14 partials of every contact go to shared
+// memory and thread (body, component) then sums them over the contacts in index order (deterministic).
+__global__ void __launch_bounds__(128)
+contact_geometry_bwd_kernel(const BodyGeom* __restrict__ geom, const double* __restrict__ p,
+                            const double* __restrict__ shape, int nb, double fd_eps, int detach_b2, int maxc,
+                            const int* __restrict__ count, const int* __restrict__ cbody, const int* __restrict__ cface,
+                            const double* __restrict__ cabc, const double* __restrict__ ggeo, double* __restrict__ gp) {
+    extern __shared__ double part[];          // [maxc][14]
+    const int w = blockIdx.x;
+    const int nc = min(count[w], maxc);
+    for (int item = threadIdx.x; item < nc * 14; item += blockDim.x) {
+        const int k = item / 14, j = item % 14;
+        const size_t oo = (size_t)w * maxc + k;
+        const int i1 = cbody[2 * oo], i2 = cbody[2 * oo + 1];
+        const BodyGeom g1 = geom[i1];
+        const SdfShape s1 = body_shape(g1, shape, w, nb, i1);
+        const SdfShape s2 = body_shape(geom[i2], shape, w, nb, i2);
+        const double* P1 = p + ((size_t)w * nb + i1) * 7;
+        const double* P2 = p + ((size_t)w * nb + i2) * 7;
+        const int s1seed = j < 7 ? j : -1, s2seed = j >= 7 ? j - 7 : -1;
+        auto D = [](const double* s, int k_, int seed) { return Dual(s[k_], seed == k_ ? 1.0 : 0.0); };
+        Q4<Dual> q1 = q4<Dual>(D(P1, 0, s1seed), D(P1, 1, s1seed), D(P1, 2, s1seed), D(P1, 3, s1seed));
+        V3<Dual> x1 = v3<Dual>(D(P1, 4, s1seed), D(P1, 5, s1seed), D(P1, 6, s1seed));
+        Q4<Dual> q2 = q4<Dual>(D(P2, 0, s2seed), D(P2, 1, s2seed), D(P2, 2, s2seed), D(P2, 3, s2seed));
+        V3<Dual> x2 = v3<Dual>(D(P2, 4, s2seed), D(P2, 5, s2seed), D(P2, 6, s2seed));
+        const int f = cface[oo];
+        const V3<double> va = load_vert(g1, w, g1.faces[3 * f]), vb = load_vert(g1, w, g1.faces[3 * f + 1]),
+                         vc = load_vert(g1, w, g1.faces[3 * f + 2]);
+        const double a = cabc[3 * oo], b = cabc[3 * oo + 1], c = cabc[3 * oo + 2];
+        const V3<double> ct = v3<double>(va.x * a + vb.x * b + vc.x * c, va.y * a + vb.y * b + vc.y * c,
+                                         va.z * a + vb.z * b + vc.z * c);
+        const ContactGeo<Dual> g = contact_geometry<Dual>(s1, s2, q1, x1, q2, x2, ct, fd_eps, detach_b2 != 0);
+        const double* gg = ggeo + 10 * oo;
+        part[item] = gg[0] * g.n.x.d + gg[1] * g.n.y.d + gg[2] * g.n.z.d + gg[3] * g.p1.x.d + gg[4] * g.p1.y.d +
+                     gg[5] * g.p1.z.d + gg[6] * g.p2.x.d + gg[7] * g.p2.y.d + gg[8] * g.p2.z.d + gg[9] * g.pen.d;
+    }
+    __syncthreads();
+    for (int t = threadIdx.x; t < nb * 7; t += blockDim.x) {
+        const int body = t / 7, comp = t % 7;
+        double acc = 0.0;
+        for (int k = 0; k < nc; ++k) {
+            const size_t oo = (size_t)w * maxc + k;
+            const int i1 = cbody[2 * oo], i2 = cbody[2 * oo + 1];
+            if (body == i1) acc += part[k * 14 + comp];
+            if (body == i2) acc += part[k * 14 + 7 + comp];
+        }
+        gp[((size_t)w * nb + body) * 7 + comp] = acc;
+    }
+}
+
+}  // namespace dsdf
+
+using namespace dsdf;
+
+extern "C" {
+
+int dsdf_contact_geometry_backward(const dsdf_body_geom* geom, const double* p, const double* shape, int W, int nb,
+                                   double fd_eps, int detach_b2, int maxc, const int32_t* count, const int32_t* cbody,
+                                   const int32_t* cface, const double* cabc, const double* ggeo, double* gp, void* stream) {
+    if (W <= 0 || nb <= 0 || maxc <= 0) return -1;
+    contact_geometry_bwd_kernel<<<W, 128, (size_t)maxc * 14 * sizeof(double), (cudaStream_t)stream>>>(reinterpret_cast<const BodyGeom*>(geom), p, shape, nb,
+                                                                    fd_eps, detach_b2, maxc, count, cbody, cface, cabc,
+                                                                    ggeo, gp);
+    return (int)cudaGetLastError();
+}
+
+}  // extern "C"

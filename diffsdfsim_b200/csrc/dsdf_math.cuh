@@ -24,8 +24,16 @@ struct Dual {
 // Newton steps) fall into a ~100-instruction slow path whenever the numerator (radicand) is zero or denormal, and the
 // whole warp waits for it; exact zeros are everywhere in contact geometry (axis-aligned normals, points on coordinate
 // planes, clamped box distances).  0 / b = +-0 and sqrt(+-0) = +-0 exactly, so the shortcut changes no bit.
-HD double fdiv(double a, double b) { return (a == 0.0 && b != 0.0 && b == b) ? (b > 0.0 ? a : -a) : a / b; }
-HD double fsqrt(double a) { return a == 0.0 ? a : sqrt(a); }
+// DSDF_OUTLINE_MATH (defined by large kernels before including this header): keep ONE out-of-line copy of the
+// division / square-root / quaternion-rotation sequences instead of inlining them at every call site -- the contact
+// kernel otherwise exceeds the instruction cache several times over.
+#ifdef DSDF_OUTLINE_MATH
+#define DSDF_MATH_FN __host__ __device__ __noinline__
+#else
+#define DSDF_MATH_FN HD
+#endif
+DSDF_MATH_FN double fdiv(double a, double b) { return (a == 0.0 && b != 0.0 && b == b) ? (b > 0.0 ? a : -a) : a / b; }
+DSDF_MATH_FN double fsqrt(double a) { return a == 0.0 ? a : sqrt(a); }
 HD Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
 HD Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
 HD Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
@@ -117,11 +125,13 @@ template <class S> HD Q4<S> qmul_raw(Q4<S> a, Q4<S> b) {
 template <class S> HD Q4<S> qstd(Q4<S> q) { return val(q.w) < 0.0 ? q4<S>(-q.w, -q.x, -q.y, -q.z) : q; }
 template <class S> HD Q4<S> qmul(Q4<S> a, Q4<S> b) { return qstd(qmul_raw(a, b)); }
 template <class S> HD Q4<S> qinv(Q4<S> q) { return q4<S>(q.w, -q.x, -q.y, -q.z); }
-template <class S> HD V3<S> qapply(Q4<S> q, V3<S> p) {
+template <class S> HD V3<S> qapply_inl(Q4<S> q, V3<S> p) {
     S zero = cst(p.x, 0.0);
     Q4<S> o = qmul_raw(qmul_raw(q, q4<S>(zero, p.x, p.y, p.z)), qinv(q));
     return v3<S>(o.x, o.y, o.z);
 }
+DSDF_MATH_FN V3<double> qapply(Q4<double> q, V3<double> p) { return qapply_inl<double>(q, p); }
+HD V3<Dual> qapply(Q4<Dual> q, V3<Dual> p) { return qapply_inl<Dual>(q, p); }
 template <class S> HD M3<S> q2mat(Q4<S> q) {
     S r = q.w, i = q.x, j = q.y, k = q.z;
     S two = cst(r, 2.0), one = cst(r, 1.0);

@@ -28,6 +28,135 @@ sdf_query_kernel(int kind, const double* __restrict__ shape, const double* __res
     }
 }
 
+
+// ---- grid bodies: the same arithmetic as grid_eval_raw / sdf_query (identical expression order, so identical bits),
+// but every voxel of the 32-voxel stencil (8 corners + their axis neighbours) is loaded ONCE into registers instead
+// of once per use (56 loads): the kernel is bound by L1/LSU wavefronts and FP64 issue, not by DRAM, until the
+// redundant loads are gone.  One thread per point; consecutive points of a warp walk the grid's fastest axis.
+// v / max(|v|, 1e-12) with ONE division: r = RN(1/n), then per component q = a r corrected by one exact-remainder
+// Newton step (q' = fma(fma(-q, n, a), r, q)), which is the correctly rounded quotient whenever r is the correctly
+// rounded reciprocal (Markstein); zero components stay exact zeros.  Replaces three ~35-instruction divisions.
+__device__ __forceinline__ V3<double> normalize3_rcp(V3<double> a) {
+    double n = norm3(a);
+    if (n < 1e-12) n = 1e-12;
+    const double r = 1.0 / n;
+    auto q = [&](double x) {
+        if (x == 0.0) return x;
+        const double q0 = x * r;
+        return fma(fma(-q0, n, x), r, q0);
+    };
+    return v3<double>(q(a.x), q(a.y), q(a.z));
+}
+
+#ifndef SDFQ_MINB
+#define SDFQ_MINB 2
+#endif
+#ifndef SDFQ_WAVES
+#define SDFQ_WAVES 8
+#endif
+__global__ void __launch_bounds__(256, SDFQ_MINB)
+sdf_query_grid_kernel(const double* __restrict__ shape, const double* __restrict__ grid, int R, long long grid_stride,
+                      const double* __restrict__ pts, int N, int want_dir, double* __restrict__ sdf,
+                      double* __restrict__ dir) {
+    const int w = blockIdx.y;
+    const double sc = shape[4 * (size_t)w + 3];
+    const double* __restrict__ g = grid + (size_t)w * grid_stride;
+    const double ext = (double)(R - 1);
+    const size_t sx = (size_t)R * R, sy = (size_t)R;
+    // persistent-style loop with the NEXT point's coordinates prefetched: the DRAM latency of the point stream overlaps
+    // the ~400 FP64 instructions of the current point
+    const int step = gridDim.x * blockDim.x;
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    double qx = 0.0, qy = 0.0, qz = 0.0;
+    if (i < N) { const size_t o = (size_t)w * N + i; qx = pts[3 * o]; qy = pts[3 * o + 1]; qz = pts[3 * o + 2]; }
+    for (; i < N; i += step) {
+        const size_t o = (size_t)w * N + i;
+        const double px = qx, py = qy, pz = qz;
+        if (i + step < N) { const size_t o2 = o + step; qx = pts[3 * o2]; qy = pts[3 * o2 + 1]; qz = pts[3 * o2 + 2]; }
+        double val_ = 1.0 * sc, n0 = 0.0, n1 = 0.0, n2 = 0.0;
+        const bool inside = fabs(px) <= sc && fabs(py) <= sc && fabs(pz) <= sc;
+        if (inside) {
+            const bool unit = sc == 1.0;                       // x / 1 = x exactly
+            const double ux = unit ? px : fdiv(px, sc), uy = unit ? py : fdiv(py, sc), uz = unit ? pz : fdiv(pz, sc);
+            const double ix = (ux + 1.) * 0.5 * ext, iy = (uy + 1.) * 0.5 * ext, iz = (uz + 1.) * 0.5 * ext;
+            const bool ok = ix <= ext && ix >= 0.0 && iy <= ext && iy >= 0.0 && iz <= ext && iz >= 0.0;
+            double v = 1.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+            if (ok) {
+                const int bx = min(max((int)floor(ix), 0), R - 2), by = min(max((int)floor(iy), 0), R - 2),
+                          bz = min(max((int)floor(iz), 0), R - 2);
+                const double tx = ix - bx, ty = iy - by, tz = iz - bz;
+                const double* c = g + ((size_t)bx * R + by) * R + bz;
+                // corners C[dx][dy][dz]
+                double C[2][2][2];
+#pragma unroll
+                for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+                    for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                        for (int dz = 0; dz < 2; ++dz) C[dx][dy][dz] = c[dx * sx + dy * sy + dz];
+                double acc = 0.0;
+                if (want_dir) {
+                    // axis neighbours one step outside the cell.  On a boundary plane the reference's central difference
+                    // is zero (bodies.py:225-234): there the neighbour is redirected to the voxel it is subtracted from,
+                    // so hi - lo = 0 exactly and no per-corner select is needed.
+                    double XM[2][2], XP[2][2], YM[2][2], YP[2][2], ZM[2][2], ZP[2][2];
+                    const long long oxm = bx > 0 ? -(long long)sx : (long long)sx, oxp = bx + 2 < R ? 2 * (long long)sx : 0;
+                    const long long oym = by > 0 ? -(long long)sy : (long long)sy, oyp = by + 2 < R ? 2 * (long long)sy : 0;
+                    const long long ozm = bz > 0 ? -1 : 1, ozp = bz + 2 < R ? 2 : 0;
+#pragma unroll
+                    for (int a = 0; a < 2; ++a)
+#pragma unroll
+                        for (int b = 0; b < 2; ++b) {
+                            XM[a][b] = c[oxm + a * sy + b];  XP[a][b] = c[oxp + a * sy + b];
+                            YM[a][b] = c[a * sx + oym + b];  YP[a][b] = c[a * sx + oyp + b];
+                            ZM[a][b] = c[a * sx + b * sy + ozm];  ZP[a][b] = c[a * sx + b * sy + ozp];
+                        }
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx) {
+                        const double wx = dx ? tx : 1 - tx;
+#pragma unroll
+                        for (int dy = 0; dy < 2; ++dy) {
+                            const double wy = dy ? ty : 1 - ty;
+#pragma unroll
+                            for (int dz = 0; dz < 2; ++dz) {
+                                const double wz = dz ? tz : 1 - tz;
+                                const double wgt = wx * wy * wz;
+                                acc = acc + C[dx][dy][dz] * wgt;
+                                // twice the central differences; the exact factor 1/2 is applied once after the sums
+                                // (scaling by a power of two commutes with every rounding involved)
+                                const double hi_x = dx ? XP[dy][dz] : C[1][dy][dz], lo_x = dx ? C[0][dy][dz] : XM[dy][dz];
+                                const double hi_y = dy ? YP[dx][dz] : C[dx][1][dz], lo_y = dy ? C[dx][0][dz] : YM[dx][dz];
+                                const double hi_z = dz ? ZP[dx][dy] : C[dx][dy][1], lo_z = dz ? C[dx][dy][0] : ZM[dx][dy];
+                                a0 = a0 + (hi_x - lo_x) * wgt;
+                                a1 = a1 + (hi_y - lo_y) * wgt;
+                                a2 = a2 + (hi_z - lo_z) * wgt;
+                            }
+                        }
+                    }
+                    a0 *= 0.5; a1 *= 0.5; a2 *= 0.5;
+                } else {
+#pragma unroll
+                    for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+                        for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                            for (int dz = 0; dz < 2; ++dz)
+                                acc = acc + C[dx][dy][dz] * ((dx ? tx : 1 - tx) * (dy ? ty : 1 - ty) * (dz ? tz : 1 - tz));
+                }
+                v = acc;
+            }
+            val_ = v * sc;
+            if (want_dir) {
+                const V3<double> d1 = ok ? normalize3_rcp(v3<double>(a0, a1, a2)) : v3<double>(0.0, 0.0, 0.0);
+                const V3<double> d2 = normalize3_rcp(d1);
+                n0 = d2.x; n1 = d2.y; n2 = d2.z;
+            }
+        }
+        sdf[o] = val_;
+        if (want_dir) { dir[3 * o] = n0; dir[3 * o + 1] = n1; dir[3 * o + 2] = n2; }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 sdf_query_bwd_kernel(int kind, const double* __restrict__ shape, const double* __restrict__ grid, int res,
                      long long grid_stride, const double* __restrict__ pts, int N,
@@ -125,8 +254,16 @@ int dsdf_sdf_query(int kind, const double* shape, const double* grid, int res, l
     if (N == 0) return 0;
     int bx = (N + 255) / 256;
     if (bx > 148 * 8) bx = 148 * 8;
-    sdf_query_kernel<<<dim3(bx, W), 256, 0, (cudaStream_t)stream>>>(kind, shape, grid, res, grid_world_stride, pts, N,
-                                                                    want_dir, sdf, dir);
+    if (kind == DSDF_SDF_GRID) {
+        // ~4 resident waves of CTAs over the whole launch (148 SMs x 3 CTAs); each thread streams several points
+        int per_world = (148 * SDFQ_MINB * SDFQ_WAVES + W - 1) / W;
+        if (per_world < 1) per_world = 1;
+        if (bx > per_world) bx = per_world;
+        sdf_query_grid_kernel<<<dim3(bx, W), 256, 0, (cudaStream_t)stream>>>(shape, grid, res, grid_world_stride, pts, N,
+                                                                             want_dir, sdf, dir);
+    } else
+        sdf_query_kernel<<<dim3(bx, W), 256, 0, (cudaStream_t)stream>>>(kind, shape, grid, res, grid_world_stride, pts,
+                                                                        N, want_dir, sdf, dir);
     return (int)cudaGetLastError();
 }
 

@@ -75,7 +75,7 @@ class World3D:
                  contact_callback=Defaults3D.CONTACT, eps=Defaults3D.EPSILON, tol=Defaults3D.TOL,
                  fric_dirs=Defaults3D.FRIC_DIRS, post_stab=Defaults3D.POST_STABILIZATION,
                  strict_no_penetration=True, time_of_contact_diff=True, stop_contact_grad=False,
-                 stop_friction_grad=False, detach_contact_b2=False, device=None, capK=512, maxc=32,
+                 stop_friction_grad=False, detach_contact_b2=False, device=None, capK=384, maxc=32,
                  record_prefilter=False):
         if post_stab:
             raise NotImplementedError('post_stab (off by default in the reference) is not built yet')
