@@ -124,6 +124,23 @@ def bouncing_sphere(rad=0.5, height=1.0, vel=(0, 0, 0, 2.0, 0, 0), floor=(20.0, 
     ], time_of_contact_diff=toc, steps=steps)
 
 
+def mixed_primitives(floor=(6.0, 1.0, 6.0), floor_tri=0.3, steps=8, toc=True, subdivisions=3):
+    """Sphere, box and cylinder falling onto a pinned floor and onto each other (trajectory-fitting shape, config 3:
+    several mixed primitives per world, every body pair searched).  The LAST body (cylinder) takes the per-world
+    parameters ('mass', 'vel')."""
+    q = [math.cos(math.pi / 4), math.sin(math.pi / 4), 0.0, 0.0]       # cylinder axis (local z) -> world -y
+    return scene([
+        body('box', [0, -floor[1] / 2, 0], dims=list(floor), pinned=True, fric_coeff=0.4, restitution=0.3,
+             max_tri_length=floor_tri),
+        body('sphere', [-0.55, 0.45, 0.0], rad=0.4, vel=[0, 0, 0, 0.3, 0, 0], fric_coeff=0.4, restitution=0.3,
+             gravity=True, mesh=dict(subdivisions=subdivisions)),
+        body('box', [0.5, 0.35, 0.05], dims=[0.6, 0.6, 0.6], fric_coeff=0.4, restitution=0.3, gravity=True,
+             max_tri_length=0.15),
+        body('cylinder', q + [0.05, 1.15, 0.0], rad=0.25, height=0.6, vel=[0, 0, 0, 0, -1.0, 0], fric_coeff=0.4,
+             restitution=0.3, gravity=True, max_tri_length=0.15),
+    ], time_of_contact_diff=toc, steps=steps)
+
+
 def baked_grid(res=32, kind='ellipsoid', seed=0):
     """A res^3 float64 SDF grid on [-1,1]^3 standing in for a decoded IGR latent (no checkpoints offline)."""
     t = np.linspace(-1.0, 1.0, res)

@@ -112,3 +112,43 @@ def test_undo_step_restores_state():
     world.step(fixed_dt=True)
     world.undo_step()
     assert torch.equal(world.get_p(), p0) and torch.equal(world.v, v0) and torch.equal(world.t, t0)
+
+
+def test_mixed_primitives_multi_body_matches_oracle_per_world():
+    """Config-3 shape: sphere + box + cylinder + pinned floor per world, every body pair searched, contacts between
+    free bodies and with the floor at once (nz = 24, up to ~14 contacts); per-world mass / initial velocity of the
+    cylinder.  Poses, velocities, contact counts and gradients vs the oracle, world by world."""
+    W, steps = 3, 8
+    gen = torch.Generator().manual_seed(1)
+    mass = 0.8 + 0.6 * torch.rand(W, generator=gen, dtype=F64)
+    vel = torch.tensor([0, 0, 0, 0.2, -1.0, 0.1], dtype=F64) + 0.2 * (torch.rand(W, 6, generator=gen, dtype=F64) - 0.5)
+    spec = scenes.mixed_primitives(steps=steps)
+    params = dict(mass=mass.cuda().requires_grad_(True), vel=vel.cuda().requires_grad_(True))
+    world = scenes.build_world(spec, device='cuda', params=params)
+    assert world.W == W and world.nb == 4
+    loss, traj = 0., []
+    for k in range(steps):
+        world.step(fixed_dt=True)
+        traj.append((world.get_p().detach().cpu(), world.v.detach().cpu(), world.contact_set.count.cpu()))
+        loss = loss + (world.bodies[-1].pos ** 2).sum()
+    loss.backward()
+    assert int(traj[-1][2].max()) >= 6, 'scene should end in multi-body contact'
+    drift = 0.0
+    for w in range(W):
+        leaves = dict(mass=mass[w].clone().requires_grad_(True), vel=vel[w].clone().requires_grad_(True))
+        ow = build_oracle(spec, leaves)
+        lo = 0.
+        for k in range(steps):
+            ow.step()
+            drift = max(drift, float(np.abs(traj[k][0][w].numpy() - ow.get_p().detach().numpy()).max()))
+            np.testing.assert_allclose(traj[k][0][w].numpy(), ow.get_p().detach().numpy(), atol=1e-7, rtol=0)
+            np.testing.assert_allclose(traj[k][1][w].numpy(), ow.v.detach().numpy(), atol=1e-5, rtol=1e-4)
+            assert int(traj[k][2][w]) == len(ow.contacts), f'world {w} step {k}: contact count'
+            lo = lo + (ow.bodies[-1].pos ** 2).sum()
+        lo.backward()
+        for k in leaves:
+            ref = leaves[k].grad.numpy()
+            got = params[k].grad[w].cpu().numpy()
+            np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4 * max(1e-9, np.abs(ref).max()),
+                                       err_msg=f'world {w} grad {k}')
+    print('mixed_primitives max pose drift %.2e over %d steps' % (drift, steps))
