@@ -669,6 +669,24 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
             }
             m = msurv;
             rank_sort_kv(KU, KV, sm.HI, m);
+            // exact duplicates (faces sharing a vertex yield the same contact point): only the first of a run (lowest
+            // contact index, the sort is stable in it) can be a hull vertex -- compact the others away in parallel so the
+            // sequential chain below only walks distinct points
+            for (int e = tid; e < m; e += nt) {
+                const int keep = (e == 0) || !(KU[e] == KU[e - 1] && KV[e] == KV[e - 1]);
+                sm.TMP[e] = keep; sm.SC[e] = keep;
+            }
+            int mu = 0;
+            block_exclusive_scan(sm.SC, m, &mu);
+            for (int rd = 0; rd < (m + nt - 1) / nt; ++rd) {
+                const int e = rd * nt + tid;
+                double x = 0, y = 0; int hi_ = 0, dst = -1;
+                if (e < m && sm.TMP[e]) { dst = sm.SC[e]; x = KU[e]; y = KV[e]; hi_ = sm.HI[e]; }
+                __syncthreads();
+                if (dst >= 0) { KU[dst] = x; KV[dst] = y; sm.HI[dst] = hi_; }
+                __syncthreads();
+            }
+            m = mu;
             if (tid == 0) sm.red[39] = mxc_all;
             __syncthreads();
         }
@@ -677,14 +695,6 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
             const double tol_d = 2.0 * distround(2, mxc);
             int* H = sm.SC;                 // stack of sorted positions
             int top = 0;
-            // exact duplicates (faces sharing a vertex yield the same contact point): only the first (lowest
-            // contact index, the sort is stable in it) can be a hull vertex -- compact them away first
-            int mu = 0;
-            for (int e = 0; e < m; ++e) {
-                if (mu > 0 && KU[e] == KU[mu - 1] && KV[e] == KV[mu - 1]) continue;
-                KU[mu] = KU[e]; KV[mu] = KV[e]; sm.HI[mu] = sm.HI[e]; ++mu;
-            }
-            m = mu;
             // lower chain
             for (int e = 0; e < m; ++e) {
                 while (top >= 2) {

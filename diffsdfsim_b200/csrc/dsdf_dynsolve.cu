@@ -61,21 +61,22 @@ template <class S> __device__ __forceinline__ M3<S> winertia(Q4<S> q, const S* I
 }
 
 struct DynSmem {
-    int C, per, R, nz, neq, nq, nF, ldF, nb;
-    size_t oG, oYG, oA, oDen, oV, oK, oQ, oS, oI, bytes;
+    int C, per, R, nz, neq, nq, nF, ldF, nb, half, gs;   // gs = doubles of G per contact = (1 + fd/2) * 12
+    size_t oG, oYG, oA, oDen, oAP, oV, oK, oQ, oS, oI, bytes;
 };
-enum { DV_S = 0, DV_Z, DV_H, DV_RZ, DV_T, DV_DSA, DV_DZA, DV_DS, DV_DZ, DV_BS, DV_BZ, DV_D, DV_COUNT };
+enum { DV_S = 0, DV_Z, DV_H, DV_RZ, DV_T, DV_DSA, DV_DZA, DV_DS, DV_DZ, DV_BS, DV_BZ, DV_D, DV_GX, DV_COUNT };
 enum { DS_XY = 0, DS_RXY, DS_DXYA, DS_DXY, DS_BXY, DS_P, DS_RHS, DS_TF, DS_XF, DS_COUNT };
 
 __host__ __device__ inline DynSmem dyn_layout(int nb, int neq, int C, int fd) {
     DynSmem L;
     L.C = C; L.per = 2 + fd; L.R = C * L.per; L.nz = 6 * nb; L.neq = neq; L.nq = L.nz + neq; L.nb = nb;
-    L.nF = L.nz - neq; L.ldF = L.nF | 1;
+    L.nF = L.nz - neq; L.ldF = L.nF | 1; L.half = fd / 2; L.gs = (1 + L.half) * 12;
     size_t o = 0;
-    L.oG = o;   o += (size_t)C * (1 + fd) * 12;
+    L.oG = o;   o += (size_t)C * L.gs;        // normal row + the first fd/2 friction rows (the rest are their negatives)
     L.oYG = o;  o += (size_t)C * 12;
     L.oA = o;   o += L.R;                 // a = 1/d
     L.oDen = o; o += C;
+    L.oAP = o;  o += (size_t)2 * C * L.half;  // per friction pair: 1/a_q + 1/a_{q+half}, 1/a_q - 1/a_{q+half}
     L.oV = o;   o += (size_t)DV_COUNT * L.R;
     L.oK = o;   o += (size_t)L.nz * L.ldF;      // rows [0,nF): M~_FF (LU in place); rows [nF,nz): M~_PF
     L.oQ = o;   o += (size_t)nb * 36;
@@ -88,7 +89,7 @@ __host__ __device__ inline DynSmem dyn_layout(int nb, int neq, int C, int fd) {
 struct DynCtx {
     DynSmem L;
     int nc, ni;                     // active contacts / rows of this world
-    double *G, *YG, *a, *den, *V, *K, *Qb, *Sv;
+    double *G, *YG, *a, *den, *AP, *V, *K, *Qb, *Sv;
     int *cb, *eq, *perm, *fidx, *fpos;   // fidx[jf] = free dof; fpos[I] = jf (free) or -(m+1) (pinned by row m)
     __device__ double* vec(int k) const { return V + (size_t)k * L.R; }
     __device__ double* sv(int k) const { return Sv + (size_t)k * L.nq; }
@@ -174,11 +175,11 @@ __device__ void dyn_load(DynCtx& c, int w, const double* p, const double* v, con
         c.cb[2 * cc] = i1; c.cb[2 * cc + 1] = i2;
         const double* g = cgeo + 10 * oo;
         const V3<double> n = v3<double>(g[0], g[1], g[2]), p1 = v3<double>(g[3], g[4], g[5]), p2 = v3<double>(g[6], g[7], g[8]);
-        double* Gc = c.G + (size_t)cc * (1 + fd) * 12;
+        double* Gc = c.G + (size_t)cc * L.gs;
         row12<double>(p1, p2, n, Gc);
         V3<double> dirs[8];
         fdirs<double>(n, fd, dirs);
-        for (int r = 0; r < fd; ++r) row12<double>(p1, p2, dirs[r], Gc + 12 * (1 + r));
+        for (int r = 0; r < L.half; ++r) row12<double>(p1, p2, dirs[r], Gc + 12 * (1 + r));   // rows r + half = -rows r
         mu_out[cc] = 0.5 * (fric[(size_t)w * nb + i1] + fric[(size_t)w * nb + i2]);
         e_out[cc] = (rest[(size_t)w * nb + i1] + rest[(size_t)w * nb + i2]) / 2;
     }
@@ -198,7 +199,7 @@ __device__ void dyn_load(DynCtx& c, int w, const double* p, const double* v, con
         const int cc = r / L.per, j = r % L.per;
         double hv = 0.0;
         if (j == 0) {
-            const double* Gc = c.G + (size_t)cc * (1 + fd) * 12;
+            const double* Gc = c.G + (size_t)cc * L.gs;
             double jv = 0.0;
             for (int k = 0; k < 12; ++k) jv += Gc[k] * v[(size_t)w * nz + c.gidx(cc, k)];
             hv = jv * e_out[cc];
@@ -217,26 +218,32 @@ __device__ __forceinline__ double Fz_row(const DynCtx& c, const double* z, const
     for (int q = 1; q <= fd; ++q) acc -= z[cc * per + q];
     return acc;
 }
-// (G x)[r]
-__device__ __forceinline__ double Gx_row(const DynCtx& c, const double* x, int r, int fd) {
-    const int per = c.L.per, cc = r / per, j = r % per;
-    if (j > fd) return 0.0;
-    const double* Gc = c.G + ((size_t)cc * (1 + fd) + j) * 12;
-    double acc = 0.0;
+// out = G x for all rows (contact-major): friction row q + half is the negative of row q, the cone row is zero
+__device__ __forceinline__ void Gx_all(const DynCtx& c, const double* x, double* out) {
+    const int lane = threadIdx.x & 31, per = c.L.per, half = c.L.half, rows = 1 + half;
+    for (int e = lane; e < c.nc * rows; e += 32) {
+        const int cc = e / rows, j = e % rows;
+        const double* Gc = c.G + (size_t)cc * c.L.gs + 12 * j;
+        double acc = 0.0;
 #pragma unroll
-    for (int k = 0; k < 12; ++k) acc += Gc[k] * x[c.gidx(cc, k)];
-    return acc;
+        for (int k = 0; k < 12; ++k) acc += Gc[k] * x[c.gidx(cc, k)];
+        out[cc * per + j] = acc;
+        if (j >= 1) out[cc * per + j + half] = -acc;
+        else out[cc * per + per - 1] = 0.0;
+    }
+    __syncwarp();
 }
 // (G' w)[I]
 __device__ __forceinline__ double Gtw_row(const DynCtx& c, const double* w, int I, int fd) {
-    const int per = c.L.per, b = I / 6, k6 = I % 6;
+    const int per = c.L.per, half = c.L.half, b = I / 6, k6 = I % 6;
     double acc = 0.0;
     for (int cc = 0; cc < c.nc; ++cc) {
         int k;
         if (c.cb[2 * cc] == b) k = k6; else if (c.cb[2 * cc + 1] == b) k = 6 + k6; else continue;
-        const double* Gc = c.G + (size_t)cc * (1 + fd) * 12 + k;
-        double a2 = 0.0;
-        for (int j = 0; j <= fd; ++j) a2 += Gc[12 * j] * w[cc * per + j];
+        const double* Gc = c.G + (size_t)cc * c.L.gs + k;
+        const double* wc = w + cc * per;
+        double a2 = Gc[0] * wc[0];
+        for (int q = 1; q <= half; ++q) a2 += Gc[12 * q] * (wc[q] - wc[q + half]);
         acc += a2;
     }
     return acc;
@@ -273,41 +280,49 @@ __device__ int dyn_factor(DynCtx& c, const double* d, const double* mu, int fd) 
         c.den[cc] = 1.0 / dn;
     }
     __syncwarp();
+    const int half = L.half;
+    for (int e = lane; e < c.nc * half; e += 32) {
+        const int cc = e / half, q = 1 + e % half;
+        const double* ac = c.a + cc * per;
+        c.AP[(size_t)2 * e] = ac[q] + ac[q + half];
+        c.AP[(size_t)2 * e + 1] = ac[q] - ac[q + half];
+    }
+    __syncwarp();
     for (int e = lane; e < c.nc * 12; e += 32) {
         const int cc = e / 12, k = e % 12;
-        const double* Gc = c.G + (size_t)cc * (1 + fd) * 12 + k;
-        const double* ac = c.a + cc * per;
-        double acc = -mu[cc] * Gc[0] * ac[0];
-        for (int q = 1; q <= fd; ++q) acc += Gc[12 * q] * ac[q];
+        const double* Gc = c.G + (size_t)cc * L.gs + k;
+        const double* ap = c.AP + (size_t)2 * cc * half;
+        double acc = -mu[cc] * Gc[0] * c.a[cc * per];
+        for (int q = 1; q <= half; ++q) acc += Gc[12 * q] * ap[2 * (q - 1) + 1];
         c.YG[e] = acc * c.den[cc];
     }
     __syncwarp();
-    // M~ entries (I, J free): thread per entry; free rows land in the LU block, pinned rows below it
-    for (int e = lane; e < nz * nF; e += 32) {
-        const int I = e / nF, jf = e % nF, J = c.fidx[jf], bI = I / 6, bJ = J / 6;
+    // M~_FF = Q_FF + sum_c G_c' B_c^-1 G_c restricted to the free components; thread per entry
+    for (int e = lane; e < nF * nF; e += 32) {
+        const int If = e / nF, jf = e % nF, I = c.fidx[If], J = c.fidx[jf], bI = I / 6, bJ = J / 6;
         double acc = bI == bJ ? c.Qb[36 * bI + 6 * (I % 6) + (J % 6)] : 0.0;
         for (int cc = 0; cc < c.nc; ++cc) {
             const int i1 = c.cb[2 * cc], i2 = c.cb[2 * cc + 1];
             int ki, kj;
             if (i1 == bI) ki = I % 6; else if (i2 == bI) ki = 6 + I % 6; else continue;
             if (i1 == bJ) kj = J % 6; else if (i2 == bJ) kj = 6 + J % 6; else continue;
-            const double* Gc = c.G + (size_t)cc * (1 + fd) * 12;
-            const double* ac = c.a + cc * per;
-            double a2 = Gc[ki] * (Gc[kj] * ac[0]);
+            const double* Gc = c.G + (size_t)cc * L.gs;
+            const double* ap = c.AP + (size_t)2 * cc * half;
+            double a2 = Gc[ki] * (Gc[kj] * c.a[cc * per]);
             const double yg = c.YG[cc * 12 + kj];
-            for (int q = 1; q <= fd; ++q) a2 += Gc[12 * q + ki] * ((Gc[12 * q + kj] - yg) * ac[q]);
+            for (int q = 1; q <= half; ++q)
+                a2 += Gc[12 * q + ki] * (Gc[12 * q + kj] * ap[2 * (q - 1)] - yg * ap[2 * (q - 1) + 1]);
             acc += a2;
         }
-        const int fp = c.fpos[I];
-        const int row = fp >= 0 ? fp : nF + (-fp - 1);
-        c.K[row * ld + jf] = acc;
+        c.K[If * ld + jf] = acc;
     }
     __syncwarp();
     return warp_lu(c.K, ld, nF, c.perm);
 }
 
-// [[M~, A'], [A, 0]] [dx; dy] = rhs with A a 0/1 selection of the pinned components and rhs_y = 0 (b = 0, x_P = 0):
-// dx_P = rhs_y (= 0), dx_F = (M~_FF)^-1 rhs_F, dy = rhs_P - M~_PF dx_F.
+// dx of [[M~, A'], [A, 0]] [dx; dy] = rhs with A a 0/1 selection of the pinned components and rhs_y = 0 (b = 0, x_P = 0):
+// dx_P = rhs_y (= 0), dx_F = (M~_FF)^-1 rhs_F.  The multipliers dy follow from the pinned rows of the un-reduced
+// system once dz is known: dy = -rx_P - (G' dz)_P - (Q dx)_P   (see dyn_solve).
 __device__ inline void kkt_solve(DynCtx& c, const double* rhs, double* dxy) {
     const int lane = threadIdx.x & 31;
     const DynSmem& L = c.L;
@@ -317,12 +332,6 @@ __device__ inline void kkt_solve(DynCtx& c, const double* rhs, double* dxy) {
     __syncwarp();
     warp_lu_solve(c.K, ld, nF, c.perm, tF, xF);
     for (int I = lane; I < nz; I += 32) { const int fp = c.fpos[I]; dxy[I] = fp >= 0 ? xF[fp] : rhs[nz + (-fp - 1)]; }
-    for (int m = lane; m < L.neq; m += 32) {
-        const double* row = c.K + (size_t)(nF + m) * ld;
-        double acc = rhs[6 * c.eq[2 * m] + c.eq[2 * m + 1]];
-        for (int jf = 0; jf < nF; ++jf) acc -= row[jf] * xF[jf];
-        dxy[nz + m] = acc;
-    }
     __syncwarp();
 }
 
@@ -347,9 +356,18 @@ __device__ void dyn_solve(DynCtx& c, const double* d, const double* mu, int fd, 
     }
     __syncwarp();
     kkt_solve(c, rhs, dxy);
-    for (int r = lane; r < c.ni; r += 32) dz[r] = Gx_row(c, dxy, r, fd) + dz[r];   // G dx + t
+    double* gx = c.vec(DV_GX);
+    Gx_all(c, dxy, gx);
+    for (int r = lane; r < c.ni; r += 32) dz[r] = gx[r] + dz[r];                    // G dx + t
     __syncwarp();
     block_solve(c, mu, dz, fd);
+    for (int m = lane; m < L.neq; m += 32) {                                       // multipliers of the pinned rows
+        const int b = c.eq[2 * m], k = c.eq[2 * m + 1], I = 6 * b + k;
+        double acc = (rxy ? -rxy[I] : 0.0) - Gtw_row(c, dz, I, fd);
+        for (int j = 0; j < 6; ++j) acc -= c.Qb[36 * b + 6 * k + j] * dxy[6 * b + j];
+        dxy[nz + m] = acc;
+    }
+    __syncwarp();
     for (int r = lane; r < c.ni; r += 32) ds[r] = ((rs ? -rs[r] : 0.0) - dz[r]) / d[r];
     __syncwarp();
 }
@@ -368,7 +386,7 @@ __device__ double dyn_ratio_step(const DynCtx& c, const double* v, const double*
 __device__ inline DynCtx dyn_ctx(double* sm, const DynSmem& L) {
     DynCtx c;
     c.L = L;
-    c.G = sm + L.oG; c.YG = sm + L.oYG; c.a = sm + L.oA; c.den = sm + L.oDen; c.V = sm + L.oV; c.K = sm + L.oK;
+    c.G = sm + L.oG; c.YG = sm + L.oYG; c.a = sm + L.oA; c.den = sm + L.oDen; c.AP = sm + L.oAP; c.V = sm + L.oV; c.K = sm + L.oK;
     c.Qb = sm + L.oQ; c.Sv = sm + L.oS;
     int* ib = reinterpret_cast<int*>(sm + L.oI);
     c.cb = ib; c.eq = ib + 2 * L.C; c.perm = c.eq + 2 * L.neq; c.fidx = c.perm + L.nq; c.fpos = c.fidx + L.nz;
@@ -452,8 +470,9 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
                 }
                 rxy[I] = acc;
             }
+            Gx_all(c, xy, c.vec(DV_GX));
             for (int r = lane; r < ni; r += 32) {
-                const double val_ = Gx_row(c, xy, r, fd) + s[r] - h[r] - Fz_row(c, z, mu, r, fd);
+                const double val_ = c.vec(DV_GX)[r] + s[r] - h[r] - Fz_row(c, z, mu, r, fd);
                 rz[r] = val_;
                 nrz += val_ * val_;
                 sz += s[r] * z[r];
@@ -574,7 +593,7 @@ dyn_backward_kernel(const double* __restrict__ p, const double* __restrict__ v, 
         for (int cc = 0; cc < nc; ++cc) {
             int kk;
             if (c.cb[2 * cc] == b) kk = k; else if (c.cb[2 * cc + 1] == b) kk = 6 + k; else continue;
-            acc += c.G[(size_t)cc * (1 + fd) * 12 + kk] * s_e[cc] * (-dl[cc * per]);
+            acc += c.G[(size_t)cc * L.gs + kk] * s_e[cc] * (-dl[cc * per]);
         }
         gv[(size_t)w * nz + I] = acc;
         gf[(size_t)w * nz + I] = dtw * dxy[I];
@@ -613,7 +632,7 @@ dyn_backward_kernel(const double* __restrict__ p, const double* __restrict__ v, 
             // dF[cone row, normal col] = dlam_cone * lam_normal
             gfr += 0.5 * dl[cc * per + per - 1] * lam[cc * per];
             double jv = 0.0;
-            for (int k = 0; k < 12; ++k) jv += c.G[(size_t)cc * (1 + fd) * 12 + k] * vw[c.gidx(cc, k)];
+            for (int k = 0; k < 12; ++k) jv += c.G[(size_t)cc * L.gs + k] * vw[c.gidx(cc, k)];
             gre += 0.5 * (-dl[cc * per]) * jv;
         }
         gfric[(size_t)w * nb + b] = gfr;

@@ -70,7 +70,33 @@ class TimeOfContact(torch.autograd.Function):
         return tuple(outs)
 
 
+class TimeOfContactNative(torch.autograd.Function):
+    """World.H + its gather (world.py:141-237, 275-327) for ALL worlds through dsdf_toc_backward: identity forward,
+    one kernel backward; worlds without a new contact pass dL/ddt through unchanged."""
+
+    @staticmethod
+    def forward(ctx, dt_, p_try, new_v, geo, f, mass, toc_mask, cbody):
+        ctx.save_for_backward(dt_, p_try, new_v, geo, f, mass, toc_mask, cbody)
+        return dt_.clone()
+
+    @staticmethod
+    def backward(ctx, gh):
+        dt_, p_try, new_v, geo, f, mass, toc_mask, cbody = ctx.saved_tensors
+        W, nb, maxc = p_try.shape[0], p_try.shape[1], geo.shape[1]
+        c = lambda t: t.contiguous()
+        g_dt, gp, gv = torch.empty_like(dt_), torch.empty_like(p_try), torch.empty_like(new_v)
+        ggeo, gf, gm = torch.empty_like(geo), torch.empty_like(f), torch.empty_like(mass)
+        rc = _lib.call('dsdf_toc_backward', W, nb, maxc, _lib.ptr(c(dt_)), _lib.ptr(c(toc_mask)), _lib.ptr(c(cbody)),
+                       _lib.ptr(c(p_try)), _lib.ptr(c(new_v)), _lib.ptr(c(geo)), _lib.ptr(c(f)), _lib.ptr(c(mass)),
+                       _lib.ptr(c(gh)), BASE_TOL, _lib.ptr(g_dt), _lib.ptr(gp), _lib.ptr(gv), _lib.ptr(ggeo),
+                       _lib.ptr(gf), _lib.ptr(gm), _lib.stream())
+        _lib.check(rc, 'dsdf_toc_backward')
+        return g_dt, gp, gv, ggeo, gf, gm, None, None
+
+
 class World3D:
+    toc_native = True      # False: the torch-autograd restatement of World.H (TimeOfContact) on the affected worlds
+
     def __init__(self, bodies, constraints=[], dt=Defaults3D.DT, engine=Defaults3D.ENGINE,
                  contact_callback=Defaults3D.CONTACT, eps=Defaults3D.EPSILON, tol=Defaults3D.TOL,
                  fric_dirs=Defaults3D.FRIC_DIRS, post_stab=Defaults3D.POST_STABILIZATION,
@@ -351,7 +377,11 @@ class World3D:
         self.max_nc = int(fl[3])                   # sizes the dynamics kernel's shared memory for the next solve
         if toc:
             if fl[2]:
-                dt_h = self._time_of_contact(dt_, p_try, new_v, geo, cs, toc_mask.bool())
+                if self.toc_native:
+                    dt_h = TimeOfContactNative.apply(dt_, p_try, new_v, geo, self.step_forces(), st.mass, toc_mask,
+                                                     cs.body)
+                else:
+                    dt_h = self._time_of_contact(dt_, p_try, new_v, geo, cs, toc_mask.bool())
                 p_redo = ops.integrate(st.p, new_v, dt_h, toc_now)
                 tn = toc_now.bool()
                 p_try = torch.where(tn[:, None, None], p_redo, p_try)

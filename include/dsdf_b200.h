@@ -246,6 +246,21 @@ int dsdf_attempt_commit(int W, int nb, int maxc, const unsigned char* active, co
                         double* dt_next, unsigned char* active_next, unsigned char* toc_now,
                         unsigned char* toc_mask, int32_t* flags, void* stream);
 
+/* ---------------------------------------------------- time-of-contact ----
+ * Replaces World.H.backward (lcp_physics/physics/world.py:141-237) together with the gather that feeds it
+ * (world.py:275-327), for all worlds.  H.forward is the identity on dt, so there is no forward entry point.
+ * In:  dt (W) the sub-step length that entered the attempt; toc_mask (W,maxc) uint8 = contacts whose body pair had
+ *      no contact before; cbody (W,maxc,2); p (W,nb,7) / v (W,nb,6) the end-of-attempt poses and velocities;
+ *      geo (W,maxc,10) contact tuples; f (W,nb,6) generalized forces; mass (W,nb); g_dt_h (W) = dL/d(dt after H).
+ * Out: g_dt (W) = g_dt_h + the dependence of the reconstructed start-of-step frame on dt; gp (W,nb,7), gv (W,nb,6),
+ *      ggeo (W,maxc,10), gf (W,nb,6), gmass (W,nb) = -(dD/dh)^+ dD/dtheta g_dt_h  (zero for worlds without new
+ *      contacts).  base_tol = 1e-6 (lcp_physics/physics/utils.py:43).
+ */
+int dsdf_toc_backward(int W, int nb, int maxc, const double* dt, const unsigned char* toc_mask,
+                      const int32_t* cbody, const double* p, const double* v, const double* geo,
+                      const double* f, const double* mass, const double* g_dt_h, double base_tol,
+                      double* g_dt, double* gp, double* gv, double* ggeo, double* gf, double* gmass, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
