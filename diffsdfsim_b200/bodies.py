@@ -69,8 +69,9 @@ class Body3D:
 
     def set_p(self, new_p):
         self.p = as_batched(new_p, 1, self.p.device)
-        if self._world is not None:
-            self._world._body_pose_changed(self._index)
+        world = self._world() if self._world is not None else None     # weak reference: no body <-> world cycle
+        if world is not None:
+            world._body_pose_changed(self._index)
 
     def add_force(self, f):
         self.forces.append(f)

@@ -5,6 +5,8 @@ A force returns a generalized force [torque(3); force(3)] of shape (B,6), B in {
 engines.py:36 / bodies.py:120-124); functions that must see each world's own sub-step time can set
 ``vectorized=True`` and will then be called with a (W,) tensor.
 """
+import weakref
+
 import torch
 
 F64 = torch.float64
@@ -42,7 +44,7 @@ class ExternalForce3D:
         self.body = None
 
     def set_body(self, body):
-        self.body = body
+        self.body = weakref.proxy(body)      # weak: no body <-> force cycle keeping an autograd graph alive
 
     def force(self, t):
         f = self.force_func(t)

@@ -8,6 +8,8 @@ touch), expressed with per-world masks: one "round" = one attempt of every still
 All arithmetic of the round runs in the CUDA kernels (engines.py, contacts.py, ops.py); this file only
 routes tensors and merges accepted/rejected worlds with ``torch.where``.
 """
+import weakref
+
 import torch
 
 from . import contacts as contacts_module
@@ -127,7 +129,7 @@ class World3D:
         self.maxc = maxc
         W, nb, dev = self.W, self.nb, self.device
         for i, b in enumerate(self.bodies):
-            b._world, b._index = self, i
+            b._world, b._index = weakref.ref(self), i      # weak: a finished world is freed by refcount, not by the GC
 
         def ex(t, *shape):
             return t.to(dev).expand(W, *shape)
