@@ -38,7 +38,7 @@ def parse():
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--worlds', type=int, default=4096, help='worlds per GPU')
     ap.add_argument('--sim-steps', type=int, default=30)
-    ap.add_argument('--cpu-worlds', type=int, default=0, help='worlds of the bounded CPU sample (0 = one per core)')
+    ap.add_argument('--cpu-worlds', type=int, default=0, help='worlds of the bounded CPU sample (0 = two per core)')
     ap.add_argument('--cpu-sim-steps', type=int, default=0, help='0 = --sim-steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-sdf-query', action='store_true', help='skip the SDF-query HBM-roofline microbenchmark')
@@ -331,7 +331,7 @@ def cpu_sample(n_worlds, sim_steps, seed=0):
 
 def cpu_sizes(args):
     cores = os.cpu_count() or 1
-    return (args.cpu_worlds or cores), (args.cpu_sim_steps or args.sim_steps), cores
+    return (args.cpu_worlds or 2 * cores), (args.cpu_sim_steps or args.sim_steps), cores
 
 
 def run_reference(args):

@@ -34,12 +34,30 @@ struct Dual {
 #endif
 DSDF_MATH_FN double fdiv(double a, double b) { return (a == 0.0 && b != 0.0 && b == b) ? (b > 0.0 ? a : -a) : a / b; }
 DSDF_MATH_FN double fsqrt(double a) { return a == 0.0 ? a : sqrt(a); }
+// Three quotients by one divisor with ONE division: r = RN(1/b), then q = RN(a r) corrected by one exact-remainder step
+// q' = fma(fma(-q, b, a), r, q).  With r the correctly rounded reciprocal and q within one ulp of a/b this is the
+// correctly rounded quotient RN(a/b) (Markstein's theorem), i.e. the same bits as a / b; zero numerators stay exact
+// zeros and the non-finite / tiny-divisor cases take the plain divisions.
+DSDF_MATH_FN void fdiv3(double& x, double& y, double& z, double b) {
+    if (!(b > 1e-290 && b < 1e290)) { x = fdiv(x, b); y = fdiv(y, b); z = fdiv(z, b); return; }
+    const double r = 1.0 / b;
+    if (x != 0.0) { const double q = x * r; x = fma(fma(-q, b, x), r, q); }
+    if (y != 0.0) { const double q = y * r; y = fma(fma(-q, b, y), r, q); }
+    if (z != 0.0) { const double q = z * r; z = fma(fma(-q, b, z), r, q); }
+}
 HD Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
 HD Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
 HD Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
 HD Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, a.d * b.v + a.v * b.d); }
 HD Dual operator/(Dual a, Dual b) { double q = fdiv(a.v, b.v); return Dual(q, fdiv(a.d - q * b.d, b.v)); }
 HD Dual fdiv(Dual a, Dual b) { return a / b; }
+HD void fdiv3(Dual& x, Dual& y, Dual& z, Dual b) {      // values and tangents: two batches of three quotients by b.v
+    double qx = x.v, qy = y.v, qz = z.v;
+    fdiv3(qx, qy, qz, b.v);
+    double tx = x.d - qx * b.d, ty = y.d - qy * b.d, tz = z.d - qz * b.d;
+    fdiv3(tx, ty, tz, b.v);
+    x = Dual(qx, tx); y = Dual(qy, ty); z = Dual(qz, tz);
+}
 HD Dual& operator+=(Dual& a, Dual b) { a = a + b; return a; }
 HD Dual& operator-=(Dual& a, Dual b) { a = a - b; return a; }
 HD Dual& operator*=(Dual& a, Dual b) { a = a * b; return a; }
@@ -106,7 +124,8 @@ HD Dual norm2(Dual a, Dual b) {
 template <class S> HD V3<S> normalize3(V3<S> a) {
     S n = norm3(a);
     if (val(n) < 1e-12) n = cst(n, 1e-12);
-    return v3<S>(fdiv(a.x, n), fdiv(a.y, n), fdiv(a.z, n));
+    fdiv3(a.x, a.y, a.z, n);
+    return a;
 }
 template <class S> HD void normalize2(S& a, S& b) {
     S n = norm2(a, b);

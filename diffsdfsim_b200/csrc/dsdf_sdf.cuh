@@ -127,7 +127,8 @@ __device__ __forceinline__ SdfOut<S> sdf_query(const SdfShape& sh, V3<S> p, bool
     const bool inside = fabs(val(p.x)) <= sc && fabs(val(p.y)) <= sc && fabs(val(p.z)) <= sc;
     if (!inside) { o.d = cst(p.x, 1.0 * sc); return o; }
     S scs = cst(p.x, sc);
-    V3<S> u = v3<S>(fdiv(p.x, scs), fdiv(p.y, scs), fdiv(p.z, scs));
+    V3<S> u = p;
+    fdiv3(u.x, u.y, u.z, scs);
     S value;
     V3<S> dir = o.n;
     if (sh.kind == DSDF_SDF_BOX) box_eval<S>(u, sh.a, sh.b, sh.c, want_n, value, dir);
