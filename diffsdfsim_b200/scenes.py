@@ -60,8 +60,13 @@ def make_bodies(spec, device=None, params=None, W=1):
             grid = baked_grid(g['res'], g['kind'], g.get('seed', 0)) if isinstance(g, dict) else g
             m = b['mesh']
             r = m['radius']
-            ob = B.SDFGrid3D(pos, b['scale'], grid, meshes.icosphere(r, m.get('subdivisions', 3)),
-                             inertia=(2 / 5 * r ** 2 * np.eye(3)), **kw)
+            mesh = meshes.icosphere(r, m.get('subdivisions', 3))
+            if last and 'grid' in params:          # per-world grids (W,R,R,R) and, optionally, per-world vertices
+                grid = params['grid']
+                if 'verts' in params:
+                    mesh = (params['verts'], mesh[1])
+            inertia = params['inertia'] if (last and 'inertia' in params) else 2 / 5 * r ** 2 * np.eye(3)
+            ob = B.SDFGrid3D(pos, b['scale'], grid, mesh, inertia=inertia, **kw)
         else:
             raise ValueError(k)
         if b['gravity']:
