@@ -146,6 +146,15 @@ def mixed_primitives(floor=(6.0, 1.0, 6.0), floor_tri=0.3, steps=8, toc=True, su
     ], time_of_contact_diff=toc, steps=steps)
 
 
+def inertia_fitting(dims=(1.0, 0.5, 0.25), torque=(1.0, 0.5, 0.25), until=0.3, mass=1.0, steps=20):
+    """One box whose translation is locked by X/Y/Z constraints, spun up by a torque for t < until (inertia-fitting
+    shape of the scaling sweep, config 5: experiments/inertia_fitting/optim_primitives.py:97-117).  No contacts:
+    nz = 6, neq = 3."""
+    return scene([body('box', [0.0, 0.0, 0.0], dims=list(dims), mass=mass, ext_force=list(torque) + [0.0, 0.0, 0.0],
+                       ext_until=until)],
+                 axis_locks=[(0, 3), (0, 4), (0, 5)], steps=steps, time_of_contact_diff=False)
+
+
 def baked_grid(res=32, kind='ellipsoid', seed=0):
     """A res^3 float64 SDF grid on [-1,1]^3 standing in for a decoded IGR latent (no checkpoints offline)."""
     t = np.linspace(-1.0, 1.0, res)
