@@ -64,7 +64,7 @@ struct DynSmem {
     int C, per, R, nz, neq, nq, nF, ldF, nb, half, gs;   // gs = doubles of G per contact = (1 + fd/2) * 12
     size_t oG, oYG, oA, oDen, oAP, oV, oK, oQ, oS, oI, bytes;
 };
-enum { DV_S = 0, DV_Z, DV_H, DV_RZ, DV_T, DV_DSA, DV_DZA, DV_DS, DV_DZ, DV_BS, DV_BZ, DV_D, DV_GX, DV_COUNT };
+enum { DV_S = 0, DV_Z, DV_RZ, DV_T, DV_DSA, DV_DZA, DV_DS, DV_DZ, DV_D, DV_COUNT };   // 9 row vectors per world
 enum { DS_XY = 0, DS_RXY, DS_DXYA, DS_DXY, DS_BXY, DS_P, DS_RHS, DS_TF, DS_XF, DS_COUNT };
 
 __host__ __device__ inline DynSmem dyn_layout(int nb, int neq, int C, int fd) {
@@ -142,7 +142,7 @@ __device__ inline void warp_lu_solve(const double* LU, int ld, int n, const int*
 __device__ void dyn_load(DynCtx& c, int w, const double* p, const double* v, const double* mass, const double* Ibody,
                          const double* fric, const double* rest, const double* f, double dtw, const int* count,
                          const int* cbody, const double* cgeo, const int* eq_rows, int maxc, int fd, double* mu_out,
-                         double* e_out) {
+                         double* e_out, double* h_out) {
     const int lane = threadIdx.x & 31;
     const DynSmem& L = c.L;
     const int nb = L.nb, nz = L.nz;
@@ -193,18 +193,12 @@ __device__ void dyn_load(DynCtx& c, int w, const double* p, const double* v, con
         for (int j = 0; j < 6; ++j) acc += Q[6 * k + j] * v[(size_t)w * nz + 6 * b + j];
         pv[i] = acc + dtw * f[(size_t)w * nz + i];
     }
-    // h = [e (Jc v); 0; 0] in contact-major rows
-    double* h = c.vec(DV_H);
-    for (int r = lane; r < c.ni; r += 32) {
-        const int cc = r / L.per, j = r % L.per;
-        double hv = 0.0;
-        if (j == 0) {
-            const double* Gc = c.G + (size_t)cc * L.gs;
-            double jv = 0.0;
-            for (int k = 0; k < 12; ++k) jv += Gc[k] * v[(size_t)w * nz + c.gidx(cc, k)];
-            hv = jv * e_out[cc];
-        }
-        h[r] = hv;
+    // h = [e (Jc v); 0; 0]: one value per contact (normal row), zero on the friction and cone rows
+    for (int cc = lane; cc < c.nc; cc += 32) {
+        const double* Gc = c.G + (size_t)cc * L.gs;
+        double jv = 0.0;
+        for (int k = 0; k < 12; ++k) jv += Gc[k] * v[(size_t)w * nz + c.gidx(cc, k)];
+        h_out[cc] = jv * e_out[cc];
     }
     __syncwarp();
 }
@@ -356,7 +350,7 @@ __device__ void dyn_solve(DynCtx& c, const double* d, const double* mu, int fd, 
     }
     __syncwarp();
     kkt_solve(c, rhs, dxy);
-    double* gx = c.vec(DV_GX);
+    double* gx = t;                                                                 // t is dead from here on
     Gx_all(c, dxy, gx);
     for (int r = lane; r < c.ni; r += 32) dz[r] = gx[r] + dz[r];                    // G dx + t
     __syncwarp();
@@ -422,18 +416,21 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
         if (lane == 0) { status_o[w] = DSDF_LCP_TOO_LARGE; if (iters_o) iters_o[w] = 0; }
         return;
     }
-    __shared__ double s_mu[64], s_e[64];      // per-contact friction coefficient and restitution (C <= 64)
+    __shared__ double s_mu[64], s_e[64], s_h[64];   // per contact: friction coefficient, restitution, h (C <= 64)
     const double* mu = s_mu;
-    dyn_load(c, w, p, v, mass, Ibody, fric, rest, f, dt[w], count, cbody, cgeo, eq_rows, maxc, fd, s_mu, s_e);
+    dyn_load(c, w, p, v, mass, Ibody, fric, rest, f, dt[w], count, cbody, cgeo, eq_rows, maxc, fd, s_mu, s_e, s_h);
+    auto hrow = [&](int r) { return (r % per == 0) ? s_h[r / per] : 0.0; };
+    const int niCap = maxc * per;
+    for (int r = lane; r < niCap; r += 32) { lamo[(size_t)w * niCap + r] = 0.0; so[(size_t)w * niCap + r] = 0.0; }
     const int ni = c.ni;
-    double *s = c.vec(DV_S), *z = c.vec(DV_Z), *h = c.vec(DV_H), *rz = c.vec(DV_RZ), *dsa = c.vec(DV_DSA),
-           *dza = c.vec(DV_DZA), *ds = c.vec(DV_DS), *dz = c.vec(DV_DZ), *bs = c.vec(DV_BS), *bz = c.vec(DV_BZ),
+    double *s = c.vec(DV_S), *z = c.vec(DV_Z), *rz = c.vec(DV_RZ), *dsa = c.vec(DV_DSA),
+           *dza = c.vec(DV_DZA), *ds = c.vec(DV_DS), *dz = c.vec(DV_DZ),
            *d = c.vec(DV_D);
     double *xy = c.sv(DS_XY), *rxy = c.sv(DS_RXY), *dxya = c.sv(DS_DXYA), *dxy = c.sv(DS_DXY), *bxy = c.sv(DS_BXY),
            *pv = c.sv(DS_P);
     int status = 0, iters = 0;
     // ---- initial point (batch.py:84-110): d = 1, solve_kkt(p, 0, -h, -b)
-    for (int r = lane; r < ni; r += 32) { d[r] = 1.0; rz[r] = -h[r]; }
+    for (int r = lane; r < ni; r += 32) { d[r] = 1.0; rz[r] = -hrow(r); }
     for (int i = lane; i < nq; i += 32) rxy[i] = i < nz ? pv[i] : 0.0;      // ry = -b = 0
     __syncwarp();
     if (dyn_factor(c, d, mu, fd)) status |= DSDF_LCP_FACTOR_FAIL;
@@ -470,9 +467,9 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
                 }
                 rxy[I] = acc;
             }
-            Gx_all(c, xy, c.vec(DV_GX));
+            Gx_all(c, xy, c.vec(DV_T));
             for (int r = lane; r < ni; r += 32) {
-                const double val_ = c.vec(DV_GX)[r] + s[r] - h[r] - Fz_row(c, z, mu, r, fd);
+                const double val_ = c.vec(DV_T)[r] + s[r] - hrow(r) - Fz_row(c, z, mu, r, fd);
                 rz[r] = val_;
                 nrz += val_ * val_;
                 sz += s[r] * z[r];
@@ -487,7 +484,11 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
             if (!have_best || res < best_res) {
                 have_best = true; best_res = res; stalled = 0;
                 for (int i = lane; i < nq; i += 32) bxy[i] = xy[i];
-                for (int r = lane; r < ni; r += 32) { bz[r] = z[r]; bs[r] = s[r]; }
+                for (int r = lane; r < ni; r += 32) {        // best (lam, s) go straight to the outputs (reference row order)
+                    const int rr = ref_row(r / per, r % per, c.nc, fd);
+                    lamo[(size_t)w * niCap + rr] = z[r];
+                    so[(size_t)w * niCap + rr] = s[r];
+                }
             } else {
                 ++stalled;
             }
@@ -517,20 +518,11 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
         have_best = true;
     }
     __syncwarp();
-    const int niCap = maxc * per;
     for (int i = lane; i < nz; i += 32) {
         xo[(size_t)w * nz + i] = have_best ? bxy[i] : NAN;
         if (nvo) nvo[(size_t)w * nz + i] = have_best ? -bxy[i] : NAN;       // engines.py:81-82
     }
     for (int m = lane; m < L.neq; m += 32) nuo[(size_t)w * L.neq + m] = have_best ? bxy[nz + m] : NAN;
-    for (int r = lane; r < niCap; r += 32) { lamo[(size_t)w * niCap + r] = 0.0; so[(size_t)w * niCap + r] = 0.0; }
-    __syncwarp();
-    if (have_best)
-        for (int r = lane; r < ni; r += 32) {
-            const int rr = ref_row(r / per, r % per, c.nc, fd);
-            lamo[(size_t)w * niCap + rr] = bz[r];
-            so[(size_t)w * niCap + rr] = bs[r];
-        }
     if (lane == 0) { status_o[w] = status; if (iters_o) iters_o[w] = iters; }
 }
 
@@ -568,9 +560,9 @@ dyn_backward_kernel(const double* __restrict__ p, const double* __restrict__ v, 
         if (lane == 0) gdt[w] = 0.0;
         return;
     }
-    __shared__ double s_mu[64], s_e[64];
+    __shared__ double s_mu[64], s_e[64], s_h[64];
     const double dtw = dt[w];
-    dyn_load(c, w, p, v, mass, Ibody, fric, rest, f, dtw, count, cbody, cgeo, eq_rows, maxc, fd, s_mu, s_e);
+    dyn_load(c, w, p, v, mass, Ibody, fric, rest, f, dtw, count, cbody, cgeo, eq_rows, maxc, fd, s_mu, s_e, s_h);
     const int ni = c.ni, nc = c.nc;
     const double* vw = v + (size_t)w * nz;
     double *lam = c.vec(DV_Z), *d = c.vec(DV_D), *dl = c.vec(DV_DZ), *ds = c.vec(DV_DS);
