@@ -429,27 +429,21 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
     double *xy = c.sv(DS_XY), *rxy = c.sv(DS_RXY), *dxya = c.sv(DS_DXYA), *dxy = c.sv(DS_DXY), *bxy = c.sv(DS_BXY),
            *pv = c.sv(DS_P);
     int status = 0, iters = 0;
-    // ---- initial point (batch.py:84-110): d = 1, solve_kkt(p, 0, -h, -b)
-    for (int r = lane; r < ni; r += 32) { d[r] = 1.0; rz[r] = -hrow(r); }
-    for (int i = lane; i < nq; i += 32) rxy[i] = i < nz ? pv[i] : 0.0;      // ry = -b = 0
-    __syncwarp();
-    if (dyn_factor(c, d, mu, fd)) status |= DSDF_LCP_FACTOR_FAIL;
-    dyn_solve(c, d, mu, fd, rxy, nullptr, rz, xy, s, z);
+    // One loop for the initial point (it = -1; batch.py:84-110: d = 1, solve_kkt(p, 0, -h, -b), shift s, z >= 1) and the
+    // interior-point iterations (batch.py:115-231), so that the factorisation and the KKT solve are instantiated ONCE:
+    // the kernel is instruction-cache bound otherwise (29 k SASS instructions with the phases written out).
     bool have_best = false;
-    double best_res = INFINITY;
-    if (ni > 0) {
-        double ms = INFINITY, mz = INFINITY;
-        for (int r = lane; r < ni; r += 32) { ms = fmin(ms, s[r]); mz = fmin(mz, z[r]); }
-        ms = warp_min(ms); mz = warp_min(mz);
-        for (int r = lane; r < ni; r += 32) {
-            if (ms < 0.0) s[r] -= ms - 1.0;
-            if (mz < 0.0) z[r] -= mz - 1.0;
-        }
-        __syncwarp();
-        int stalled = 0;
-        for (int it = 0; it < max_iter; ++it) {
+    double best_res = INFINITY, mu_gap = 0.0, sz = 0.0;
+    int stalled = 0;
+    for (int it = -1; it < max_iter; ++it) {
+        double res = 0.0;
+        if (it < 0) {
+            for (int r = lane; r < ni; r += 32) { d[r] = 1.0; rz[r] = -hrow(r); }
+            for (int i = lane; i < nq; i += 32) rxy[i] = i < nz ? pv[i] : 0.0;      // ry = -b = 0
+        } else {
             // residuals (batch.py:117-131)
-            double nrx = 0.0, nry = 0.0, nrz = 0.0, sz = 0.0;
+            double nrx = 0.0, nry = 0.0, nrz = 0.0;
+            sz = 0.0;
             for (int I = lane; I < nq; I += 32) {
                 double acc;
                 if (I < nz) {
@@ -475,11 +469,13 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
                 sz += s[r] * z[r];
             }
             nrx = wsum(nrx); nry = wsum(nry); nrz = wsum(nrz); sz = wsum(sz);
-            const double mu_gap = fabs(sz / ni);
-            const double res = (L.neq > 0 ? sqrt(nry) : 0.0) + sqrt(nrz) + sqrt(nrx) + ni * mu_gap;
+            mu_gap = fabs(sz / ni);
+            res = (L.neq > 0 ? sqrt(nry) : 0.0) + sqrt(nrz) + sqrt(nrx) + ni * mu_gap;
             for (int r = lane; r < ni; r += 32) d[r] = z[r] / s[r];
-            __syncwarp();
-            if (dyn_factor(c, d, mu, fd)) { status |= DSDF_LCP_FACTOR_FAIL; break; }
+        }
+        __syncwarp();
+        if (dyn_factor(c, d, mu, fd)) { status |= DSDF_LCP_FACTOR_FAIL; if (it >= 0) break; }
+        if (it >= 0) {
             iters = it + 1;
             if (!have_best || res < best_res) {
                 have_best = true; best_res = res; stalled = 0;
@@ -493,30 +489,59 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
                 ++stalled;
             }
             if (stalled == not_improved_lim || best_res < eps || mu_gap > 1e32) break;
-            // affine direction: rs = z
-            dyn_solve(c, d, mu, fd, rxy, z, rz, dxya, dsa, dza);
-            double alpha = fmin(fmin(dyn_ratio_step(c, z, dza), dyn_ratio_step(c, s, dsa)), 1.0);
-            double t3 = 0.0;
-            for (int r = lane; r < ni; r += 32) t3 += (s[r] + alpha * dsa[r]) * (z[r] + alpha * dza[r]);
-            t3 = wsum(t3);
-            const double r3 = t3 / sz, sig = r3 * r3 * r3;
-            // corrector: rs = (-mu sig + dsa dza) / s  (stored in rz, which is free now)
-            for (int r = lane; r < ni; r += 32) rz[r] = (-mu_gap * sig + dsa[r] * dza[r]) / s[r];
-            __syncwarp();
-            dyn_solve(c, d, mu, fd, nullptr, rz, nullptr, dxy, ds, dz);
-            for (int i = lane; i < nq; i += 32) dxy[i] += dxya[i];
-            for (int r = lane; r < ni; r += 32) { ds[r] += dsa[r]; dz[r] += dza[r]; }
-            __syncwarp();
-            alpha = fmin(0.999 * fmin(dyn_ratio_step(c, z, dz), dyn_ratio_step(c, s, ds)), 1.0);
-            for (int i = lane; i < nq; i += 32) xy[i] += alpha * dxy[i];
-            for (int r = lane; r < ni; r += 32) { s[r] += alpha * ds[r]; z[r] += alpha * dz[r]; }
-            __syncwarp();
         }
-        if (have_best && best_res > 1.0) status |= DSDF_LCP_INACCURATE;
-    } else {
-        for (int i = lane; i < nq; i += 32) bxy[i] = xy[i];
-        have_best = true;
+        bool init_done = false;
+        for (int pass = 0; pass < 2; ++pass) {
+            // pass 0: initial solve (it < 0) or affine direction (rs = z); pass 1: corrector (rs in rz)
+            const double* a_rxy = pass == 0 ? rxy : nullptr;
+            const double* a_rs = pass == 0 ? (it < 0 ? nullptr : z) : rz;
+            const double* a_rz = pass == 0 ? rz : nullptr;
+            double* o_xy = pass == 0 ? (it < 0 ? xy : dxya) : dxy;
+            double* o_s = pass == 0 ? (it < 0 ? s : dsa) : ds;
+            double* o_z = pass == 0 ? (it < 0 ? z : dza) : dz;
+            dyn_solve(c, d, mu, fd, a_rxy, a_rs, a_rz, o_xy, o_s, o_z);
+            if (it < 0) {
+                if (ni > 0) {                                   // batch.py:100-110
+                    double ms = INFINITY, mz = INFINITY;
+                    for (int r = lane; r < ni; r += 32) { ms = fmin(ms, s[r]); mz = fmin(mz, z[r]); }
+                    ms = warp_min(ms); mz = warp_min(mz);
+                    for (int r = lane; r < ni; r += 32) {
+                        if (ms < 0.0) s[r] -= ms - 1.0;
+                        if (mz < 0.0) z[r] -= mz - 1.0;
+                    }
+                    __syncwarp();
+                }
+                init_done = true;
+                break;
+            }
+            if (pass == 0) {
+                double alpha = fmin(fmin(dyn_ratio_step(c, z, dza), dyn_ratio_step(c, s, dsa)), 1.0);
+                double t3 = 0.0;
+                for (int r = lane; r < ni; r += 32) t3 += (s[r] + alpha * dsa[r]) * (z[r] + alpha * dza[r]);
+                t3 = wsum(t3);
+                const double r3 = t3 / sz, sig = r3 * r3 * r3;
+                // corrector: rs = (-mu sig + dsa dza) / s  (stored in rz, which is free now)
+                for (int r = lane; r < ni; r += 32) rz[r] = (-mu_gap * sig + dsa[r] * dza[r]) / s[r];
+                __syncwarp();
+            }
+        }
+        if (init_done) {
+            if (ni == 0) {                                      // no contacts: the equality-constrained solve is the answer
+                for (int i = lane; i < nq; i += 32) bxy[i] = xy[i];
+                have_best = true;
+                break;
+            }
+            continue;
+        }
+        for (int i = lane; i < nq; i += 32) dxy[i] += dxya[i];
+        for (int r = lane; r < ni; r += 32) { ds[r] += dsa[r]; dz[r] += dza[r]; }
+        __syncwarp();
+        const double alpha = fmin(0.999 * fmin(dyn_ratio_step(c, z, dz), dyn_ratio_step(c, s, ds)), 1.0);
+        for (int i = lane; i < nq; i += 32) xy[i] += alpha * dxy[i];
+        for (int r = lane; r < ni; r += 32) { s[r] += alpha * ds[r]; z[r] += alpha * dz[r]; }
+        __syncwarp();
     }
+    if (ni > 0 && have_best && best_res > 1.0) status |= DSDF_LCP_INACCURATE;
     __syncwarp();
     for (int i = lane; i < nz; i += 32) {
         xo[(size_t)w * nz + i] = have_best ? bxy[i] : NAN;
