@@ -393,7 +393,7 @@ __device__ __forceinline__ int ref_row(int cc, int j, int nc, int fd) {
     return j == 0 ? cc : (j <= fd ? nc + fd * cc + (j - 1) : nc + fd * nc + cc);
 }
 
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 12)
 dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, const double* __restrict__ mass,
                    const double* __restrict__ Ibody, const double* __restrict__ fric, const double* __restrict__ rest,
                    const double* __restrict__ f, const double* __restrict__ dt, const unsigned char* __restrict__ active,
@@ -552,7 +552,7 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
 }
 
 // ---- backward: implicit differentiation at the solution, contracted straight onto the physical inputs ---------
-__global__ void __launch_bounds__(32)
+__global__ void __launch_bounds__(32, 10)
 dyn_backward_kernel(const double* __restrict__ p, const double* __restrict__ v, const double* __restrict__ mass,
                     const double* __restrict__ Ibody, const double* __restrict__ fric, const double* __restrict__ rest,
                     const double* __restrict__ f, const double* __restrict__ dt, const unsigned char* __restrict__ active,
