@@ -10,7 +10,7 @@ namespace dsdf {
 // One CTA per world.  Work item = (contact k, seed j): j < 7 seeds component j of body i1's pose, j >= 7 component
 // j - 7 of body i2's (forward-mode dual through contact_geometry); the 14 partials of every contact go to shared
 // memory and thread (body, component) then sums them over the contacts in index order (deterministic).
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, 5)
 contact_geometry_bwd_kernel(const BodyGeom* __restrict__ geom, const double* __restrict__ p,
                             const double* __restrict__ shape, int nb, double fd_eps, int detach_b2, int maxc,
                             const int* __restrict__ count, const int* __restrict__ cbody, const int* __restrict__ cface,
