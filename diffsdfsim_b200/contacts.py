@@ -14,9 +14,10 @@ F64 = torch.float64
 _GEOM_DTYPE = np.dtype([('kind', 'i4'), ('nverts', 'i4'), ('nfaces', 'i4'), ('res', 'i4'), ('verts', 'u8'),
                         ('faces', 'u8'), ('grid', 'u8'), ('vstride', 'i8'), ('gstride', 'i8'),
                         ('cell_lo', 'f8', (3,)), ('cell_inv', 'f8'), ('cell_dims', 'i4', (3,)), ('has_cells', 'i4'),
-                        ('fcell_start', 'u8'), ('fcell_items', 'u8'), ('vcell_start', 'u8'), ('vcell_items', 'u8')],
+                        ('fcell_start', 'u8'), ('fcell_items', 'u8'), ('vcell_start', 'u8'), ('vcell_items', 'u8'),
+                        ('max_face_rad', 'f8')],
                        align=True)
-assert _GEOM_DTYPE.itemsize == 136
+assert _GEOM_DTYPE.itemsize == 144
 
 
 _CELL_CACHE = {}
@@ -29,7 +30,10 @@ def cached_cell_index(verts_np, faces_np, device):
     hit = _CELL_CACHE.get(key)
     if hit is None:
         lo, inv, dims, fs, fi, vs, vi = build_cell_index(verts_np, faces_np)
-        hit = (lo, inv, dims, [torch.from_numpy(a).to(device) for a in (fs, fi, vs, vi)])
+        tri = np.asarray(verts_np, dtype=np.float64)[np.asarray(faces_np, dtype=np.int64)]
+        cen = tri.mean(1, keepdims=True)
+        max_rad = float(np.linalg.norm(tri - cen, axis=2).max()) * (1.0 + 1e-9)
+        hit = (lo, inv, dims, [torch.from_numpy(a).to(device) for a in (fs, fi, vs, vi)], max_rad)
         if len(_CELL_CACHE) > 64:
             _CELL_CACHE.clear()
         _CELL_CACHE[key] = hit
@@ -96,12 +100,13 @@ class GeometryTable:
                 self.keep.append(grid)
             self.keep += [verts, faces]
             cell = (np.zeros(3), 0.0, np.zeros(3, dtype=np.int32), 0, 0, 0, 0, 0)
+            max_rad = 0.0
             if not per_world:
-                lo, inv, dims, dev_arrays = cached_cell_index(verts.cpu().numpy(), faces.cpu().numpy(), device)
+                lo, inv, dims, dev_arrays, max_rad = cached_cell_index(verts.cpu().numpy(), faces.cpu().numpy(), device)
                 self.keep += dev_arrays
                 cell = (lo, inv, dims, 1) + tuple(a.data_ptr() for a in dev_arrays)
             rows[i] = (b.kind, nverts, faces.shape[0], res, verts.data_ptr(), faces.data_ptr(), gptr,
-                       nverts * 3 if per_world else 0, gstride) + cell
+                       nverts * 3 if per_world else 0, gstride) + cell + (max_rad,)
             self.nfaces.append(int(faces.shape[0]))
         self.rows = rows
         self.dev = torch.from_numpy(rows.view(np.uint8).copy()).to(device)

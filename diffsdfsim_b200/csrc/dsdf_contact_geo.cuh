@@ -18,6 +18,7 @@ struct BodyGeom {                 // mirrors dsdf_body_geom in include/dsdf_b200
     double cell_lo[3], cell_inv;
     int cell_dims[3], has_cells;
     const int *fcell_start, *fcell_items, *vcell_start, *vcell_items;
+    double max_face_rad;          // max_f max_i |centroid_f - v_i|; 0 = unknown (no fp32 pre-filter)
 };
 
 // One out-of-line copy of the SDF evaluation for the whole contact kernel: inlining it at ~30 call sites made the

@@ -134,6 +134,55 @@ __device__ __forceinline__ bool face_is_candidate(const BodyGeom& g1, int w, int
     return (o.d < rad + eps) && (norm3(o.n) > 1e-12);
 }
 
+// ---- conservative fp32 pre-filter of the candidate test ---------------------------------------------------------
+// The exact test (face_is_candidate) costs ~1000 fp64-path instructions per face and rejects most faces it sees.
+// A face can only pass if sdf2(centroid) < rad_f + eps <= max_face_rad + eps, and the analytic SDFs are exact distance
+// fields (1-Lipschitz), so a single-precision evaluation with a margin far above its rounding error discards the
+// clearly-far faces first.  Survivors -- every true candidate among them -- still take the exact fp64 test.
+struct Pre32 { float R[9], t[3]; float a, b, c, scale, thresh; int kind; bool on; };
+
+__device__ __forceinline__ Pre32 make_pre32(const BodyGeom& g1, const SdfShape& s2, Q4<double> q1, V3<double> x1,
+                                            Q4<double> q2, V3<double> x2, double eps) {
+    Pre32 P;
+    P.on = g1.max_face_rad > 0.0 && s2.kind != DSDF_SDF_GRID;
+    const M3<double> R1 = q2mat(q1), R2 = q2mat(q2);
+    const V3<double> t = mat_applyT(R2, x1 - x2);
+    double amax = fabs(t.x) + fabs(t.y) + fabs(t.z);
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+        for (int k = 0; k < 3; ++k)
+            P.R[3 * i + k] = (float)(R2.m[i] * R1.m[k] + R2.m[3 + i] * R1.m[3 + k] + R2.m[6 + i] * R1.m[6 + k]);   // R2' R1
+    P.t[0] = (float)t.x; P.t[1] = (float)t.y; P.t[2] = (float)t.z;
+    P.a = (float)s2.a; P.b = (float)s2.b; P.c = (float)s2.c; P.scale = (float)s2.scale; P.kind = s2.kind;
+    // margin: fp32 rounding of coordinates up to (mesh extent + offset) plus the un-normalised quaternion slack
+    const double ext = 1.0 / g1.cell_inv * (g1.cell_dims[0] + g1.cell_dims[1] + g1.cell_dims[2]);
+    const double margin = 1e-4 * (1.0 + amax + ext + s2.scale);
+    P.thresh = (float)(g1.max_face_rad * 1.001 + eps + margin);
+    return P;
+}
+// true = provably not a candidate
+__device__ __forceinline__ bool pre32_reject(const Pre32& P, float cx, float cy, float cz) {
+    const float px = P.R[0] * cx + P.R[1] * cy + P.R[2] * cz + P.t[0];
+    const float py = P.R[3] * cx + P.R[4] * cy + P.R[5] * cz + P.t[1];
+    const float pz = P.R[6] * cx + P.R[7] * cy + P.R[8] * cz + P.t[2];
+    const float is = 1.0f / P.scale;
+    const float ux = px * is, uy = py * is, uz = pz * is;
+    float d;
+    if (P.kind == DSDF_SDF_BOX) {
+        const float qx = fabsf(ux) - 0.5f * P.a, qy = fabsf(uy) - 0.5f * P.b, qz = fabsf(uz) - 0.5f * P.c;
+        const float ox = fmaxf(qx, 0.f), oy = fmaxf(qy, 0.f), oz = fmaxf(qz, 0.f);
+        d = sqrtf(ox * ox + oy * oy + oz * oz) + fminf(fmaxf(qx, fmaxf(qy, qz)), 0.f);
+    } else if (P.kind == DSDF_SDF_SPHERE) {
+        d = sqrtf(ux * ux + uy * uy + uz * uz) - P.a;
+    } else {                                                    // cylinder along local z
+        const float q0 = sqrtf(ux * ux + uy * uy) - P.a, q1 = fabsf(uz) - 0.5f * P.b;
+        const float o0 = fmaxf(q0, 0.f), o1 = fmaxf(q1, 0.f);
+        d = sqrtf(o0 * o0 + o1 * o1) + fminf(fmaxf(q0, q1), 0.f);
+    }
+    return d * P.scale > P.thresh;
+}
+
 // Centroid candidate pass of one search direction into the shared list ids[0..capK) (unsorted); returns the count
 // (which may exceed capK: overflow).  s_cnt: one shared int.
 __device__ int gather_candidates(const BodyGeom& g1, int w, const SdfShape& s2, Q4<double> q1, V3<double> x1,
@@ -161,6 +210,7 @@ __device__ int gather_candidates(const BodyGeom& g1, int w, const SdfShape& s2, 
         }
     } else {
         const CellRange cr = cube_cells(g1, q1, x1, q2, x2, s2.scale);
+        const Pre32 P32 = make_pre32(g1, s2, q1, x1, q2, x2, eps);
         if (!cr.empty) {
             const int nx = cr.hi[0] - cr.lo[0] + 1, ny = cr.hi[1] - cr.lo[1] + 1, nzc = cr.hi[2] - cr.lo[2] + 1;
             const int ncell = nx * ny * nzc;
@@ -171,7 +221,14 @@ __device__ int gather_candidates(const BodyGeom& g1, int w, const SdfShape& s2, 
                 for (int k0 = s; k0 < e; k0 += 32) {
                     const int k = k0 + lane;
                     const int f = k < e ? g1.fcell_items[k] : 0;
-                    push(k < e && face_is_candidate(g1, w, f, s2, q1, x1, q2i, x2, eps), f);
+                    bool test = k < e;
+                    if (test && P32.on) {
+                        const V3<double> a = load_vert(g1, w, g1.faces[3 * f]), b = load_vert(g1, w, g1.faces[3 * f + 1]),
+                                         c = load_vert(g1, w, g1.faces[3 * f + 2]);
+                        test = !pre32_reject(P32, (float)((a.x + b.x + c.x) * (1.0 / 3.0)), (float)((a.y + b.y + c.y) * (1.0 / 3.0)),
+                                             (float)((a.z + b.z + c.z) * (1.0 / 3.0)));
+                    }
+                    push(test && face_is_candidate(g1, w, f, s2, q1, x1, q2i, x2, eps), f);
                 }
             }
         }

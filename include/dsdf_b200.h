@@ -124,6 +124,10 @@ typedef struct dsdf_body_geom {
     double cell_lo[3], cell_inv;
     int32_t cell_dims[3], has_cells;
     const int32_t *fcell_start, *fcell_items, *vcell_start, *vcell_items;
+    /* max over faces of max_i |centroid - v_i| (body frame), or 0 if unknown.  Lets the candidate pass discard, with a
+     * cheap conservative fp32 bound, faces whose centroid is provably farther than this radius + eps from the other
+     * body; everything that survives goes through the exact fp64 test, so results are unchanged. */
+    double max_face_rad;
 } dsdf_body_geom;
 
 /* per-world contact status bits (int32) */
