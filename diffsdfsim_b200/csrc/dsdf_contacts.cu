@@ -378,13 +378,23 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
     // Frank-Wolfe, <= 32 iterations, PAIR-GLOBAL exit (contacts.py:63-82).  A candidate whose step is zero
     // (|gain| <= tol) keeps its x, so re-evaluating it would reproduce the same decision: it is skipped from then on
     // (TMP[k] = 1) -- the reference recomputes it every iteration with identical results.
-    for (int k = tid; k < K; k += nt) sm.TMP[k] = 0;
+    // The still-moving candidates are kept as a compact list (two ping-pong buffers in HI / CL, free until the filter),
+    // so that from the second iteration on every thread evaluates at most one of the few dozen survivors instead of
+    // walking all K slots: the iteration latency is one SDF evaluation, not ceil(K / threads) of them.
+    __shared__ int s_nact[2];
+    int* lists[2] = {sm.HI, sm.CL};
+    for (int k = tid; k < K; k += nt) lists[0][k] = k;
+    if (tid == 0) { s_nact[0] = K; s_nact[1] = 0; }
+    __syncthreads();
     PH_MARK(PH_SORT_INIT);
     for (int it = 0; it < 32; ++it) {
+        const int cur = it & 1, nxt = cur ^ 1;
+        const int nact = s_nact[cur];
+        const int* act_list = lists[cur];
         int any_active = 0, any_pen = 0;
         // phase 1: evaluate (no state change until the exit test is known)
-        for (int k = tid; k < K; k += nt) {
-            if (sm.TMP[k]) { sm.SC[k] = -1; continue; }              // frozen, not penetrating
+        for (int a = tid; a < nact; a += nt) {
+            const int k = act_list[a];
             const V3<double> x = v3<double>(sm.X[k], sm.X[capK + k], sm.X[2 * capK + k]);
             const SdfOut<double> o = sdf_q(s2, x, true);
             double dmin = 0.0; int pick = 0;
@@ -401,7 +411,9 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
             any_active |= act;
             any_pen |= (o.d < -tol);
             sm.SC[k] = act ? pick : -1;
-            if (!act && !(o.d < -tol)) sm.TMP[k] = 1;
+            // a candidate whose step is zero keeps its x, so re-evaluating it would reproduce the same decision: it leaves
+            // the list for good (the reference recomputes it every iteration with identical results)
+            if (act) lists[nxt][atomicAdd(&s_nact[nxt], 1)] = k;
         }
         // __syncthreads_or returns a predicate, not a bitwise OR: one barrier per flag
         const int blk_active = __syncthreads_or(any_active);
@@ -409,7 +421,8 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
         PH_ADD(PH_FW_ITERS, 1);
         if (!blk_active || blk_pen) break;
         const double gamma = 2.0 / (it + 2.0);
-        for (int k = tid; k < K; k += nt) {
+        for (int a = tid; a < nact; a += nt) {
+            const int k = act_list[a];
             const int pick = sm.SC[k];
             if (pick >= 0) {
 #pragma unroll
@@ -419,8 +432,9 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
                 }
                 sm.ABC[pick * capK + k] += gamma;
             }
-            // frozen candidates: gamma = 0 -> x, abc unchanged (x = 1*x + 0*s, abc *= 1, += 0)
+            // dropped candidates: gamma = 0 -> x, abc unchanged (x = 1*x + 0*s, abc *= 1, += 0)
         }
+        if (tid == 0) s_nact[cur] = 0;                 // becomes the "next" counter of the following iteration
         __syncthreads();
     }
     __syncthreads();
