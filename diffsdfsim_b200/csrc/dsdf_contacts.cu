@@ -18,7 +18,7 @@ namespace dsdf {
 
 // Optional per-phase cycle counters (build with -DDSDF_PHASE_PROFILE; read back with dsdf_contacts_phase_cycles).
 enum { PH_OVERLAP = 0, PH_GATHER, PH_SORT_INIT, PH_FW, PH_PUSH_COMPACT, PH_GEOMETRY, PH_FILTER, PH_APPEND, PH_FW_ITERS, PH_CAND,
-       PH_PREFILTER, PH_COUNT };
+       PH_PREFILTER, PH_F_CLUSTER, PH_F_STATS, PH_F_AKL, PH_F_SORT, PH_F_CHAIN, PH_COUNT };
 #ifdef DSDF_PHASE_PROFILE
 __device__ unsigned long long g_phase[PH_COUNT];
 __device__ __noinline__ void ph_mark(int k) {          // k < 0: (re)start the clock
@@ -549,6 +549,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
         for (int k = tid; k < n; k += nt) if (sm.CL[k] == cl) sm.HI[sm.SC[k]] = k;
         __syncthreads();
         if (m == 1) { if (tid == 0) sm.KEEP[sm.HI[0]] = 1; __syncthreads(); continue; }
+        PH_MARK(PH_F_CLUSTER);
         // statistics: mean/variance per axis, max |coord|
         double s0 = 0, s1 = 0, s2 = 0, mx = 0;
         for (int e = tid; e < m; e += nt) {
@@ -667,6 +668,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
             __syncthreads();
             continue;
         }
+        PH_MARK(PH_F_STATS);
         // --- planar convex hull (strict vertices only)
         double* KU = sm.HK; double* KV = sm.HK + capK;
         for (int e = tid; e < m; e += nt) { const int k = sm.HI[e]; KU[e] = PA[u_ax][k]; KV[e] = PA[v_ax][k]; }
@@ -739,6 +741,7 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
                 __syncthreads();
             }
             m = msurv;
+            PH_MARK(PH_F_AKL);
             rank_sort_kv(KU, KV, sm.HI, m);
             // exact duplicates (faces sharing a vertex yield the same contact point): only the first of a run (lowest
             // contact index, the sort is stable in it) can be a hull vertex -- compact the others away in parallel so the
@@ -758,43 +761,35 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
                 __syncthreads();
             }
             m = mu;
+            PH_MARK(PH_F_SORT);
             if (tid == 0) sm.red[39] = mxc_all;
             __syncthreads();
         }
-        if (tid == 0) {
+        if (tid == 0 || tid == 32) {
+            // Monotone chain over the sorted distinct points: the lower hull (thread 0, ascending) and the upper hull
+            // (thread 32, descending) are independent and run concurrently on two warps, each with its own stack.
+            // b stays a vertex iff the turn a -> b -> e is left by more than the round-off bound: cr > tol |e - a|,
+            // tested without the square root as cr > 0 and cr^2 > tol^2 |e - a|^2.
             const double mxc = sm.red[39];
-            const double tol_d = 2.0 * distround(2, mxc);
-            int* H = sm.SC;                 // stack of sorted positions
+            const double tol_d = 2.0 * distround(2, mxc), tol2 = tol_d * tol_d;
+            const bool up = tid != 0;
+            int* H = up ? sm.TMP : sm.SC;   // stack of sorted positions
             int top = 0;
-            // lower chain
-            for (int e = 0; e < m; ++e) {
+            for (int i = 0; i < m; ++i) {
+                const int e = up ? m - 1 - i : i;
                 while (top >= 2) {
                     const int a = H[top - 2], b = H[top - 1];
                     const double ex = KU[e] - KU[a], ey = KV[e] - KV[a];
                     const double cr = (KU[b] - KU[a]) * ey - (KV[b] - KV[a]) * ex;   // > 0: left turn keeps b
-                    const double len = fsqrt(ex * ex + ey * ey);
-                    if (cr > tol_d * len) break;
+                    if (cr > 0.0 && cr * cr > tol2 * (ex * ex + ey * ey)) break;
                     --top;
                 }
                 H[top++] = e;
             }
-            const int lower = top + 1;
-            for (int e = m - 2; e >= 0; --e) {
-                while (top >= lower) {
-                    const int a = H[top - 2], b = H[top - 1];
-                    const double ex = KU[e] - KU[a], ey = KV[e] - KV[a];
-                    const double cr = (KU[b] - KU[a]) * ey - (KV[b] - KV[a]) * ex;
-                    const double len = fsqrt(ex * ex + ey * ey);
-                    if (cr > tol_d * len) break;
-                    --top;
-                }
-                H[top++] = e;
-            }
-            --top;                           // last point equals the first
-            if (m == 1) { top = 1; H[0] = 0; }
             for (int t = 0; t < top; ++t) sm.KEEP[sm.HI[H[t]]] = 1;
         }
         __syncthreads();
+        PH_MARK(PH_F_CHAIN);
     }
     __syncthreads();
     return status;
@@ -921,7 +916,7 @@ int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, int n
     return (int)cudaGetLastError();
 }
 
-int dsdf_contacts_phase_cycles(unsigned long long* out8, int reset) {   /* out8: PH_COUNT = 11 counters */
+int dsdf_contacts_phase_cycles(unsigned long long* out8, int reset) {   /* out: PH_COUNT = 16 counters */
 #ifdef DSDF_PHASE_PROFILE
     if (out8 && cudaMemcpyFromSymbol(out8, g_phase, sizeof(unsigned long long) * PH_COUNT) != cudaSuccess) return 1;
     if (reset) { unsigned long long z[PH_COUNT] = {0}; if (cudaMemcpyToSymbol(g_phase, z, sizeof(z)) != cudaSuccess) return 1; }
