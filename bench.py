@@ -248,6 +248,17 @@ def sdf_query_roofline(device, W=256, R=64, N=1 << 17, reps=5):
                            'algorithmic_bytes_per_launch': alg_v}}
 
 
+def ncu_counters(kernel):
+    """Selected ncu counters of `kernel` from the committed capture (profiles/ncu_counters.json), for context."""
+    try:
+        with open(os.path.join(ROOT, 'profiles', 'ncu_counters.json')) as fh:
+            c = json.load(fh).get(kernel, {})
+        keep = ('achieved occupancy %', 'issue slots busy %', 'FP64 pipe active %', 'DRAM throughput %', 'regs/thread')
+        return {k: c[k] for k in keep if k in c}
+    except Exception:
+        return None
+
+
 def ncu_traffic(kernel):
     """dram bytes (read + write) per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json)."""
     try:
@@ -274,7 +285,9 @@ def roofline(name, stat, W, spec, peaks, which, attempts):
         alg = per_world * W + shared
         return {'kernel': name, 'bound': 'hbm', 'achieved': alg / 1e9 / (avg_ms / 1e3), 'peak': peaks['hbm_gbs'],
                 'unit': 'GB/s', 'frac': alg / 1e9 / (avg_ms / 1e3) / peaks['hbm_gbs'], 'traffic': ncu_traffic('contacts_kernel'),
-                'peak_source': which, 'avg_launch_ms': avg_ms, 'algorithmic_bytes_per_launch': alg}
+                'peak_source': which, 'avg_launch_ms': avg_ms, 'algorithmic_bytes_per_launch': alg,
+                'note': 'shared L2-resident meshes: not an HBM-bound kernel on this workload; its limits are latency, '
+                        'barriers and FP64 issue (DESIGN.md s4)', 'ncu': ncu_counters('contacts_kernel')}
     else:
         per_world = 8 * (nz * nz + ni * nz)
     alg = per_world * W

@@ -68,6 +68,7 @@ def source_top(rep, kernel, top=12):
 
 
 def main(rnd):
+    counters = {}
     traffic, md = {}, ['# ncu summary, round %s' % rnd, '',
                        'Captured with `ncu --set full --clock-control none --import-source on` under gpurun on one B200, '
                        'after the same command had exited 0 without ncu.  Durations under ncu are serialised and cold-cache: '
@@ -89,6 +90,7 @@ def main(rnd):
                     if k.startswith('dram__bytes'):
                         byt += float(r[i]) * UNIT.get(units[i], 1.0)
             traffic[name] = byt
+            counters[name] = {label: r[hdr.index(k)] + ' ' + units[hdr.index(k)] for k, label in KEYS if k in hdr}
             stalls = []
             for i, h in enumerate(hdr):
                 if h.startswith('smsp__pcsamp_warps_issue_stalled_') and not h.endswith('_not_issued'):
@@ -106,6 +108,8 @@ def main(rnd):
         fh.write('\n'.join(md) + '\n')
     with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json'), 'w') as fh:
         json.dump(traffic, fh, indent=1, sort_keys=True)
+    with open(os.path.join(ROOT, 'profiles', 'ncu_counters.json'), 'w') as fh:
+        json.dump(counters, fh, indent=1, sort_keys=True)
     # launch shares
     lst = os.path.join(ROOT, 'gpurun_out', 'launches_%s.csv' % rnd)
     if os.path.exists(lst):
