@@ -216,10 +216,40 @@ def differentiable_geometry(p, shape, cs, table, fd_eps=1e-3, detach_b2=False):
 
 
 class FWContactHandler:
-    """Name-compatible with sdf_physics.physics3d.contacts.FWContactHandler; batched worlds call ``detector``."""
+    """Name-compatible with sdf_physics.physics3d.contacts.FWContactHandler (contacts.py:217-272).
+
+    ``World3D`` detects the contacts of all worlds and all body pairs with one launch (``ContactDetector``); this
+    callable keeps the reference's per-pair plug-in signature ``handler(args=[world], geom1, geom2)`` (the py3ode
+    callback of world.py:399) for code that drives a handler directly: it searches that one pair -- both directions,
+    same kernels -- and appends the reference tuples ``((normal, p1, p2, pen), i1, i2)`` to ``world.contacts_debug``
+    (and returns them).  ``geom1`` / ``geom2`` are the bodies (or their indices); ``no_contact`` is honoured
+    (contacts.py:224).
+    """
 
     def __call__(self, args, geom1, geom2):
-        raise RuntimeError('the batched World3D detects all contacts in one pass; per-pair callbacks are not used')
+        world = args[0]
+        idx = lambda g: g if isinstance(g, int) else world.bodies.index(g)
+        i1, i2 = idx(geom1), idx(geom2)
+        b1, b2 = world.bodies[i1], world.bodies[i2]
+        if b2 in b1.no_contact or b1 in b2.no_contact:
+            return []
+        with world._on_device():
+            det = ContactDetector(world.table, [(min(i1, i2), max(i1, i2))], world.W, world.nb, world.device,
+                                  capK=world.detector.capK, maxc=world.maxc)
+            cs = det.new_set()
+            det.detect(world.state.p.detach().contiguous(), world.shape, cs, None, eps=world.eps, tol=world.tol,
+                       fd_eps=1e-3, body_eps=world.body_eps, detach_b2=world.detach_contact_b2)
+            geo = differentiable_geometry(world.state.p, world.shape, cs, world.table, 1e-3, world.detach_contact_b2)
+        out = []
+        for w in range(world.W):
+            lst = [((geo[w, k, 0:3], geo[w, k, 3:6], geo[w, k, 6:9], geo[w, k, 9]), int(cs.body[w, k, 0]),
+                    int(cs.body[w, k, 1])) for k in range(int(cs.count[w]))]
+            out.append(lst)
+        res = out if world.batched else out[0]
+        if not hasattr(world, 'contacts_debug'):
+            world.contacts_debug = []
+        world.contacts_debug += res if not world.batched else [res]
+        return res
 
 
 B200ContactHandler = FWContactHandler

@@ -167,6 +167,17 @@ class PdipmEngine(Engine):
         self.last_status = None
 
     def solve_dynamics(self, world, dt, active=None):
+        """The reference's plug-in entry point (engines.py:31): ``dt`` is a float, a 0-d tensor (may carry grad,
+        world.py:256-259) or a (W,) tensor; returns the new generalized velocity -- ``(nz,)`` for a single world like the
+        reference, ``(W, nz)`` for a batch.  ``World3D`` itself calls ``solve`` (same thing, (W,nb,6) layout, with the
+        active mask)."""
+        if active is None and not (isinstance(dt, torch.Tensor) and dt.dim() == 1 and dt.shape[0] == world.W):
+            dt = world._dt_tensor(dt)
+        with world._on_device():
+            new_v = self.solve(world, dt, active).reshape(world.W, -1)
+        return new_v if world.batched else new_v[0]
+
+    def solve(self, world, dt, active=None):
         """dt: (W,) tensor (may carry grad).  Returns new_v (W,nb,6)."""
         st = world.state
         f = world.step_forces()

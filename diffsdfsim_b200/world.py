@@ -352,7 +352,7 @@ class World3D:
         if toc and self._any_toc_flag:
             # world.py:253-257: value == dt_try, carries -d last_dt
             dt_ = torch.where(self.toc_flag.bool(), -self.last_dt + (self.last_dt.detach() + dt_try), dt_try)
-        new_v = self.engine.solve_dynamics(self, dt_, active)
+        new_v = self.engine.solve(self, dt_, active)
         p_try = ops.integrate(st.p, new_v, dt_, active)
         old = self.contact_set
         cs = old.clone()

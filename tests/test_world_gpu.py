@@ -289,3 +289,26 @@ def test_inertia_fitting_scene_matches_oracle_per_world():
         lo = (ow.bodies[0].v[:3] ** 2).sum()
         lo.backward()
         np.testing.assert_allclose(float(params['mass'].grad[w]), float(leaf.grad), rtol=1e-6)
+
+
+def test_plugin_entry_points_keep_the_reference_signatures():
+    """engine.solve_dynamics(world, dt) -> (nz,) and handler(args=[world], geom1, geom2) -> reference contact tuples,
+    for a single world, agree with what World3D computes internally (engines.py:31, contacts.py:221-270)."""
+    spec = scenes.box_on_plane(floor=(4.0, 1.0, 4.0), steps=4)
+    world = scenes.build_world(spec, device='cuda')
+    for _ in range(3):
+        world.step(fixed_dt=True)
+    assert not world.batched and len(world.contacts) > 0
+    v_float = world.engine.solve_dynamics(world, world.dt)
+    v_tensor = world.engine.solve_dynamics(world, torch.tensor(world.dt, dtype=F64, device='cuda'))
+    assert v_float.shape == (6 * world.nb,) and torch.equal(v_float, v_tensor)
+    ref = world.engine.solve(world, world._dt_tensor(world.dt)).reshape(-1)
+    assert torch.equal(v_float, ref)
+    got = world.contact_callback([world], world.bodies[0], world.bodies[1])
+    assert len(got) == len(world.contacts)
+    for (g, i1, i2), (h, j1, j2) in zip(got, world.contacts):
+        assert (i1, i2) == (j1, j2)
+        for a, b in zip(g, h):
+            assert torch.equal(a, b)
+    world.bodies[0].add_no_contact(world.bodies[1])
+    assert world.contact_callback([world], world.bodies[0], world.bodies[1]) == []
