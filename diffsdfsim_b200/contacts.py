@@ -141,6 +141,16 @@ class ContactSet:
         self.geo = seg(5, F64).view(W, maxc, 10)
         self.pre_ids = self.pre_cnt = None
 
+    def resized(self, maxc):
+        """The same contacts in a set of larger per-world capacity."""
+        c = ContactSet(self.W, maxc, self.flat.device)
+        m = self.maxc
+        c.count.copy_(self.count)
+        c.status.copy_(self.status)
+        c.body[:, :m], c.face[:, :m], c.abc[:, :m], c.geo[:, :m] = self.body, self.face, self.abc, self.geo
+        c.pre_ids, c.pre_cnt = self.pre_ids, self.pre_cnt
+        return c
+
     def clone(self):
         c = ContactSet(self.W, self.maxc, self.flat.device, self.flat.clone())
         if self.pre_ids is not None:

@@ -33,9 +33,9 @@ attempt_commit_kernel(int W, int nb, int maxc, const unsigned char* __restrict__
     bool accept = clean;
     const double dtw = dt_try[w];
     if (!strict) accept = clean || (act && dtw < world_dt / 1024.0);                 // world.py:345-347
-    int bad = 0;
-    if (act && (st & DSDF_CON_CAND_OVERFLOW)) bad = 1;
-    if (accept && (st & DSDF_CON_OVERFLOW)) bad = 1;
+    int bad = 0;                                   // bit 0: candidate list overflow (capK), bit 1: contact overflow (maxc)
+    if (act && (st & DSDF_CON_CAND_OVERFLOW)) bad |= 1;
+    if (accept && (st & DSDF_CON_OVERFLOW)) bad |= 2;
     const double tn = accept ? t[w] + dtw : t[w];
     double dn = (act && !accept) ? dtw / 2 : dtw;                                     // world.py:348
     bool nact = act && !accept;
@@ -83,7 +83,7 @@ attempt_commit_kernel(int W, int nb, int maxc, const unsigned char* __restrict__
     dt_next[w] = dn;
     active_next[w] = nact;
     const int cnt_after = accept ? cn : co;
-    if (bad) atomicOr(&flags[0], 1);
+    if (bad) atomicOr(&flags[0], bad);
     if (nact) atomicOr(&flags[1], 1);
     if (any_toc) atomicOr(&flags[2], 1);
     atomicMax(&flags[3], cnt_after);

@@ -97,6 +97,7 @@ class TimeOfContactNative(torch.autograd.Function):
 
 
 class World3D:
+    max_rounds_per_step = 256
     toc_native = True      # False: the torch-autograd restatement of World.H (TimeOfContact) on the affected worlds
 
     def __init__(self, bodies, constraints=[], dt=Defaults3D.DT, engine=Defaults3D.ENGINE,
@@ -317,6 +318,13 @@ class World3D:
         rounds = 0
         while True:
             rounds += 1
+            if rounds > self.max_rounds_per_step:
+                # strict_no_penetration=True halves dt for ever in the reference too (world.py:344-348); stop instead of
+                # accumulating an unbounded autograd graph
+                stuck = active.nonzero().flatten().tolist()[:8]
+                raise RuntimeError('step did not complete in %d attempts: worlds %s keep penetrating (dt < %.3g); '
+                                   'use strict_no_penetration=False or a smaller dt'
+                                   % (self.max_rounds_per_step, stuck, float(dt_try.min())))
             self.stats['attempts'] += active
             accept, dt_try, active, any_active = self._attempt(active, dt_try, end_t)
             had |= accept.bool() & (self.contact_set.count > 0)
@@ -374,8 +382,9 @@ class World3D:
         _lib.check(rc, 'dsdf_attempt_commit')
         fl = flags.tolist()                                              # the sync
         if fl[0]:
-            raise RuntimeError('contact capacity exceeded (capK=%d, maxc=%d): raise World3D(capK=..., maxc=...)'
-                               % (self.detector.capK, self.maxc))
+            # nothing of this attempt has been committed yet: enlarge the buffers and run the attempt again
+            self._grow_capacity(fl[0])
+            return self._attempt(active, dt_try, end_t)
         self.max_nc = int(fl[3])                   # sizes the dynamics kernel's shared memory for the next solve
         if toc:
             if fl[2]:
@@ -399,6 +408,27 @@ class World3D:
         self.contact_set = cs
         self.t = t_new
         return accept, dt_next, active_next, bool(fl[1])
+
+    MAX_CAPK, MAX_MAXC = 1024, 64      # shared-memory limits of the contact / dynamics kernels
+
+    def _grow_capacity(self, bits):
+        """Double the candidate (capK) and / or contact (maxc) capacity after an overflow; raises when at the limit."""
+        capK, maxc = self.detector.capK, self.maxc
+        if bits & 1:
+            if capK >= self.MAX_CAPK:
+                raise RuntimeError('contact candidate capacity exceeded at the kernel limit capK=%d (mesh too fine '
+                                   'for the one-CTA-per-world contact kernel)' % capK)
+            capK = min(self.MAX_CAPK, 2 * capK)
+        if bits & 2:
+            if maxc >= self.MAX_MAXC:
+                raise RuntimeError('more than %d contacts in one world: beyond the dynamics kernel limit' % maxc)
+            maxc = min(self.MAX_MAXC, 2 * maxc)
+            self.contact_set = self.contact_set.resized(maxc)
+            pad = self.contact_geo.new_zeros(self.W, maxc - self.maxc, 10)
+            self.contact_geo = torch.cat([self.contact_geo, pad], 1)
+            self.maxc = maxc
+        self.detector = ContactDetector(self.table, self.pairs, self.W, self.nb, self.device, capK=capK, maxc=maxc,
+                                        record_prefilter=self.detector.record_prefilter)
 
     def _time_of_contact(self, dt_, p_try, new_v, geo, cs, toc_mask):
         """Gather of world.py:275-327 (padded to maxc) + the H function, evaluated only for the worlds that have a new
