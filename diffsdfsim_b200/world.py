@@ -180,11 +180,15 @@ class World3D:
         self.contact_set = self.detector.new_set()
         self.contact_geo = None
         with self._on_device():
-            self.find_contacts()
+            while True:
+                self.find_contacts()
+                bits = self._capacity_bits(self.contact_set)
+                if not bits:
+                    break
+                self._grow_capacity(bits)
         if self.strict_no_pen:
             assert not bool(((self.contact_set.status & 8) != 0).any()), \
                 'Interpenetration at start:\n{}'.format(self.contacts_of(0))
-        self._check_capacity(self.contact_set)
 
     # ------------------------------------------------------------------ reference-style accessors
     @property
@@ -268,13 +272,10 @@ class World3D:
             return dt.to(self.device).expand(self.W).contiguous() if dt.dim() <= 1 else dt
         return torch.full((self.W,), float(dt), dtype=F64, device=self.device)
 
-    def _check_capacity(self, cs):
+    def _capacity_bits(self, cs):
+        """bit 0: candidate-list overflow (capK) in some world; bit 1: contact overflow (maxc) on a non-penetrating state."""
         st = cs.status
-        bad = int((st & 1).max().item()) | (int(((st & 2) != 0).logical_and((st & 8) == 0).any().item()) << 1)
-        if bad & 1:
-            raise RuntimeError('contact candidate capacity exceeded: raise capK')
-        if bad & 2:
-            raise RuntimeError('contact capacity exceeded on an accepted state: raise maxc')
+        return int((st & 1).max().item()) | (int(((st & 2) != 0).logical_and((st & 8) == 0).any().item()) << 1)
 
     # ------------------------------------------------------------------ contact detection
     def find_contacts(self, active=None):

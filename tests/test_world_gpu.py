@@ -312,3 +312,23 @@ def test_plugin_entry_points_keep_the_reference_signatures():
             assert torch.equal(a, b)
     world.bodies[0].add_no_contact(world.bodies[1])
     assert world.contact_callback([world], world.bodies[0], world.bodies[1]) == []
+
+
+def test_capacity_overflow_grows_buffers_and_reruns_the_attempt():
+    """A world built with far too small candidate / contact capacities grows them on the first overflow and ends up
+    bit-identical to a world that had room from the start."""
+    spec = scenes.box_on_plane(floor=(4.0, 1.0, 4.0), steps=5)
+    outs = []
+    for kw in (dict(), dict(capK=32, maxc=2)):
+        mass = torch.tensor([1.0, 1.2], dtype=F64, device='cuda', requires_grad=True)
+        world = scenes.build_world(spec, device='cuda', params=dict(mass=mass), **kw)
+        loss = 0.
+        for _ in range(5):
+            world.step(fixed_dt=True)
+            loss = loss + (world.bodies[-1].pos ** 2).sum()
+        loss.backward()
+        outs.append((world.get_p().detach().clone(), world.v.detach().clone(), mass.grad.clone(), world.maxc,
+                     world.detector.capK, world.contact_set.count.clone()))
+    assert outs[1][3] > 2 and outs[1][4] > 32, 'the small world must have grown'
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
+    assert torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][5], outs[1][5])
