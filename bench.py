@@ -169,6 +169,8 @@ def run_ours(args):
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     sampler.stop_flag = True
+    final_pos = world.bodies[-1].pos.detach().cpu()
+    final_grads = {k: v.detach().cpu() for k, v in grads.items()}
     ms, ms_e2e = D.max_over_ranks([ms, ms_e2e], device)
     sdfq = None
     if rank == 0 and not args.no_sdf_query:
@@ -197,6 +199,7 @@ def run_ours(args):
     }
     if sdfq is not None:
         line['sdf_query'] = sdfq
+    line['_final'] = (final_pos, final_grads)
     return line
 
 
@@ -299,14 +302,14 @@ def roofline(name, stat, W, spec, peaks, which, attempts):
 
 def _cpu_world(job):
     """One world of the bounded CPU sample: the oracle port (oracle/, CPU float64) -- `sim_steps` World.step + backward."""
-    w, sim_steps, seed = job
+    w, sim_steps, seed, n_total = job
     import warnings
     warnings.filterwarnings('ignore')
     torch.set_num_threads(1)
     from oracle.scenes import build as build_oracle
     from diffsdfsim_b200 import scenes
     spec = scenes.box_on_plane(steps=sim_steps)
-    host = make_params(w + 1, torch.device('cpu'), seed)
+    host = make_params(n_total, torch.device('cpu'), seed)     # world w of the SAME parameter draw the GPU arm uses
     t0 = time.time()
     leaves = dict(mass=host['mass'][w].clone().requires_grad_(True),
                   fric_coeff=host['fric_coeff'][w].clone().requires_grad_(True),
@@ -317,7 +320,8 @@ def _cpu_world(job):
         ow.step()
         loss = loss + (ow.bodies[-1].pos ** 2).sum()
     loss.backward()
-    return time.time() - t0
+    return (time.time() - t0, ow.bodies[-1].pos.detach().tolist(), float(leaves['mass'].grad),
+            float(leaves['fric_coeff'].grad), leaves['push'].grad.tolist())
 
 
 _POOL = None
@@ -329,16 +333,20 @@ def cpu_pool():
     if _POOL is None:
         import multiprocessing as mp
         _POOL = mp.get_context('spawn').Pool(os.cpu_count() or 1)
-        _POOL.map(_cpu_world, [(0, 1, 0)] * (os.cpu_count() or 1))      # import + warm every worker
+        _POOL.map(_cpu_world, [(0, 1, 0, 1)] * (os.cpu_count() or 1))      # import + warm every worker
     return _POOL
 
 
-def cpu_sample(n_worlds, sim_steps, seed=0):
-    """world-steps/s of the CPU path on `n_worlds` worlds spread over all host cores, and the wall seconds it took."""
+def cpu_sample(n_worlds, sim_steps, seed=0, n_total=None, results=None):
+    """world-steps/s of the CPU path on `n_worlds` worlds spread over all host cores, and the wall seconds it took.
+    The worlds are the first `n_worlds` of the `n_total`-world parameter draw; `results` (a list) receives each
+    world's (seconds, final position, d loss / d mass, d loss / d friction, d loss / d push)."""
     pool = cpu_pool()
     t0 = time.time()
-    pool.map(_cpu_world, [(w, sim_steps, seed) for w in range(n_worlds)], chunksize=1)
+    out = pool.map(_cpu_world, [(w, sim_steps, seed, n_total or n_worlds) for w in range(n_worlds)], chunksize=1)
     dt = time.time() - t0
+    if results is not None:
+        results.extend(out)
     return n_worlds * sim_steps / dt, dt
 
 
@@ -397,10 +405,30 @@ def main():
         return
     if args.gpus == 1 and not args.no_cpu_baseline:
         nw, ns, cores = cpu_sizes(args)
-        v, secs = cpu_sample(nw, ns)
+        res = []
+        v, secs = cpu_sample(nw, ns, seed=0, n_total=args.worlds, results=res)
         line['cpu_baseline'] = {'value': v, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                                 'sample': '%d worlds x %d World.step + backward, one world per process on %d cores, '
                                           '%.1f s wall' % (nw, ns, cores, secs)}
+        if ns == args.sim_steps and '_final' in line:
+            # the CPU sample re-simulated worlds 0..nw-1 of the GPU batch: report the end-of-rollout drift
+            import numpy as np
+            pos, gr = line['_final']
+            ref_pos = np.array([r[1] for r in res])
+            dpos = float(np.abs(pos[:nw].numpy() - ref_pos).max())
+
+            def rel(a, b):
+                a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+                return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+            line['parity'] = {'worlds': nw, 'rollout_steps': ns,
+                              'max_abs_pos_drift_vs_oracle': dpos,
+                              'max_rel_grad_err': {'mass': rel(gr['mass'][:nw], [r[2] for r in res]),
+                                                   'fric_coeff': rel(gr['fric_coeff'][:nw], [r[3] for r in res]),
+                                                   'push': rel(gr['push'][:nw], [r[4] for r in res])},
+                              'note': 'GPU worlds 0..%d of the timed batch vs the CPU oracle on the same parameters, '
+                                      'after the full %d-step rollout (normalised by the largest reference gradient)'
+                                      % (nw - 1, ns)}
+    line.pop('_final', None)
     print(json.dumps(line))
 
 
