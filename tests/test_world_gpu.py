@@ -332,3 +332,21 @@ def test_capacity_overflow_grows_buffers_and_reruns_the_attempt():
     assert outs[1][3] > 2 and outs[1][4] > 32, 'the small world must have grown'
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][1], outs[1][1])
     assert torch.equal(outs[0][2], outs[1][2]) and torch.equal(outs[0][5], outs[1][5])
+
+
+def test_variable_dt_stepping_matches_oracle():
+    """World.step(fixed_dt=False), the reference's default (world.py:119-139): a step ends after ONE accepted sub-step,
+    however short, so simulated time advances by less than dt around impacts."""
+    spec = scenes.bouncing_sphere(floor=(4.0, 1.0, 4.0), steps=14, floor_tri=0.2, height=0.75, subdivisions=3)
+    world = scenes.build_world(spec, device='cuda')
+    ow = build_oracle(spec, {})
+    short = 0
+    for k in range(14):
+        had = world.step(fixed_dt=False)
+        had_o = ow.step(fixed_dt=False)
+        assert had == had_o
+        assert abs(float(world.t[0]) - float(ow.t)) < 1e-15, f'step {k}: simulated time'
+        np.testing.assert_allclose(world.get_p().detach().cpu().numpy(), ow.get_p().detach().numpy(), atol=1e-9, rtol=0)
+        np.testing.assert_allclose(world.v.detach().cpu().numpy(), ow.v.detach().numpy(), atol=1e-7, rtol=0)
+        short += float(world.t[0]) < (k + 1) * spec['dt'] - 1e-12
+    assert short > 0, 'the scene must contain a shortened step'
