@@ -55,7 +55,7 @@ def shape_for(b, mass):
     raise ValueError(k)
 
 
-def build(spec, params=None, max_iter=10):
+def build(spec, params=None, max_iter=10, **world_kw):
     params = params or {}
     bodies, pinned = [], []
     n = len(spec['bodies'])
@@ -85,4 +85,4 @@ def build(spec, params=None, max_iter=10):
     locks = [(bodies[i], a) for i, a in spec['axis_locks']]
     return World(bodies, pinned=pinned, axis_locks=locks, dt=spec['dt'], eps=spec['eps'], tol=spec['tol'],
                  fric_dirs=spec['fric_dirs'], strict_no_penetration=spec['strict_no_penetration'],
-                 time_of_contact_diff=spec['time_of_contact_diff'], max_iter=max_iter)
+                 time_of_contact_diff=spec['time_of_contact_diff'], max_iter=max_iter, **world_kw)

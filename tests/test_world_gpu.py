@@ -350,3 +350,37 @@ def test_variable_dt_stepping_matches_oracle():
         np.testing.assert_allclose(world.v.detach().cpu().numpy(), ow.v.detach().numpy(), atol=1e-7, rtol=0)
         short += float(world.t[0]) < (k + 1) * spec['dt'] - 1e-12
     assert short > 0, 'the scene must contain a shortened step'
+
+
+@pytest.mark.parametrize('flag', ['stop_contact_grad', 'stop_friction_grad', 'detach_contact_b2'])
+def test_gradient_stopping_flags_match_oracle(flag):
+    """World3D(stop_contact_grad / stop_friction_grad / detach_contact_b2 = True) (physics3d/world.py:37-39, 59-62,
+    77-80; contacts.py:176-181): same states, and the gradients with that part of the graph detached."""
+    W, steps = 2, 6
+    mass = torch.tensor([0.9, 1.1], dtype=F64)
+    fric = torch.tensor([0.08, 0.2], dtype=F64)
+    push = torch.tensor([[3.0, 2.0], [4.0, 2.5]], dtype=F64)
+    spec = scenes.box_on_plane(floor=(4.0, 1.0, 4.0), steps=steps)
+    params = dict(mass=mass.cuda().requires_grad_(True), fric_coeff=fric.cuda().requires_grad_(True),
+                  push=push.cuda().requires_grad_(True))
+    world = scenes.build_world(spec, device='cuda', params=params, **{flag: True})
+    loss = 0.
+    for _ in range(steps):
+        world.step(fixed_dt=True)
+        loss = loss + (world.bodies[-1].pos ** 2).sum()
+    loss.backward()
+    for w in range(W):
+        leaves = dict(mass=mass[w].clone().requires_grad_(True), fric_coeff=fric[w].clone().requires_grad_(True),
+                      push=push[w].clone().requires_grad_(True))
+        ow = build_oracle(spec, leaves, **{flag: True})
+        lo = 0.
+        for _ in range(steps):
+            ow.step()
+            lo = lo + (ow.bodies[-1].pos ** 2).sum()
+        lo.backward()
+        np.testing.assert_allclose(world.get_p()[w].detach().cpu().numpy(), ow.get_p().detach().numpy(), atol=1e-8, rtol=0)
+        for k in leaves:
+            ref = leaves[k].grad.numpy()
+            got = params[k].grad[w].cpu().numpy()
+            np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4 * max(1e-9, np.abs(ref).max()),
+                                       err_msg=f'{flag}: world {w} grad {k}')
