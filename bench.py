@@ -42,6 +42,7 @@ def parse():
     ap.add_argument('--cpu-sim-steps', type=int, default=0, help='0 = --sim-steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-sdf-query', action='store_true', help='skip the SDF-query HBM-roofline microbenchmark')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the config-4 / config-5 secondary workloads')
     return ap.parse_args()
 
 
@@ -175,6 +176,9 @@ def run_ours(args):
     sdfq = None
     if rank == 0 and not args.no_sdf_query:
         sdfq = sdf_query_roofline(device)
+    secondary = None
+    if rank == 0 and not args.no_secondary:
+        secondary = secondary_workloads(device)
     units = W * args.sim_steps * args.steps * world_size
     if rank != 0:
         return None
@@ -199,8 +203,70 @@ def run_ours(args):
     }
     if sdfq is not None:
         line['sdf_query'] = sdfq
+    if secondary is not None:
+        line['secondary'] = secondary
     line['_final'] = (final_pos, final_grads)
     return line
+
+
+def secondary_workloads(device, reps=3):
+    """world-steps/s (forward + backward, device-resident parameters) of the other BASELINE shapes at their full sizes,
+    for context next to the headline: config 4 (256 worlds, per-world 64^3 SDF grids and per-world meshes, grid body
+    falling on a pinned pole over a floor, 12 steps) and config 5's per-GPU share (8192 worlds of the inertia-fitting
+    scene: box under X/Y/Z constraints spun up by a torque, no contacts, 60 steps)."""
+    import numpy as np
+    from diffsdfsim_b200 import meshes, scenes
+    F64 = torch.float64
+    out = {}
+
+    def timed(build, steps, leaf_key):
+        best = None
+        for _ in range(reps):
+            torch.cuda.synchronize()
+            t0 = time.time()
+            params, world = build()
+            loss = 0.
+            for _ in range(steps):
+                world.step(fixed_dt=True)
+                loss = loss + (world.bodies[-1].pos ** 2).sum() + (world.bodies[-1].v ** 2).sum()
+            loss.backward()
+            torch.cuda.synchronize()
+            dt = time.time() - t0
+            assert torch.isfinite(params[leaf_key].grad).all()
+            best = dt if best is None else min(best, dt)
+        return world.W * steps / best, best
+
+    g = torch.Generator().manual_seed(0)
+    W, R = 256, 64
+    radii = (0.5 + 0.2 * torch.rand(W, generator=g, dtype=F64)).numpy()
+    t = np.linspace(-1.0, 1.0, R)
+    X, Y, Z = np.meshgrid(t, t, t, indexing='ij')
+    base = np.sqrt(X * X + Y * Y + Z * Z)
+    grids = torch.as_tensor(np.stack([base - r for r in radii])).to(device)
+    verts = torch.as_tensor(np.stack([meshes.icosphere(float(r), 3)[0] for r in radii])).to(device)
+    inertia = torch.stack([2 / 5 * float(r) ** 2 * torch.eye(3, dtype=F64) for r in radii]).to(device)
+    pos = torch.tensor([[0.0, float(r) + 2.03, 0.0] for r in radii], dtype=F64, device=device)
+    spec4 = scenes.grid_on_pole(res=R, steps=12, with_floor=True)
+
+    def build4():
+        params = dict(pos=pos.detach().requires_grad_(True), grid=grids, verts=verts, inertia=inertia)
+        return params, scenes.build_world(spec4, device=device, params=params)
+    v, secs = timed(build4, 12, 'pos')
+    out['grid_on_pole'] = {'value': v, 'unit': UNIT, 'worlds': W, 'steps': 12, 'seconds': secs,
+                           'workload': 'config 4 shape: per-world 64^3 f64 grids + per-world meshes (642 v / 1280 f), '
+                                       'pinned pole + floor'}
+    W5 = 8192
+    mass = (0.5 + torch.rand(W5, generator=g, dtype=F64)).to(device)
+    spec5 = scenes.inertia_fitting(steps=60)
+
+    def build5():
+        params = dict(mass=mass.detach().requires_grad_(True))
+        return params, scenes.build_world(spec5, device=device, params=params)
+    v, secs = timed(build5, 60, 'mass')
+    out['inertia_fitting'] = {'value': v, 'unit': UNIT, 'worlds': W5, 'steps': 60, 'seconds': secs,
+                              'workload': "config 5's per-GPU share: 8192 worlds, box under X/Y/Z constraints, torque "
+                                          'until t = 0.3, no contacts'}
+    return out
 
 
 def sdf_query_roofline(device, W=256, R=64, N=1 << 17, reps=5):
