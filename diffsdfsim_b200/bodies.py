@@ -92,6 +92,32 @@ class Body3D:
                                         self.ang_inertia, self.scale, self.shape))
 
 
+_MESH_TENSORS = {}
+
+
+def _mesh_tensors(verts, faces, device):
+    """(verts f64, faces i32) tensors on ``device``.  Read-only numpy meshes (the memoised analytic meshes of meshes.py)
+    are uploaded once per device and shared by every body built from them (worlds are rebuilt each optimisation
+    iteration; a 20x1x20 floor is 4 MB)."""
+    key = None
+    if isinstance(verts, np.ndarray) and isinstance(faces, np.ndarray) and not verts.flags.writeable \
+            and not faces.flags.writeable:
+        key = (id(verts), id(faces), str(device))
+        hit = _MESH_TENSORS.get(key)
+        if hit is not None and hit[0] is verts:
+            return hit[1], hit[2]
+    v = verts if isinstance(verts, torch.Tensor) else torch.from_numpy(np.array(verts, dtype=np.float64))
+    f = faces if isinstance(faces, torch.Tensor) else torch.from_numpy(np.array(faces))
+    v, f = v.to(F64), f.to(torch.int32)
+    if device is not None:
+        v, f = v.to(device), f.to(device)
+    if key is not None:
+        if len(_MESH_TENSORS) > 64:
+            _MESH_TENSORS.clear()
+        _MESH_TENSORS[key] = (verts, v, f)          # keeps the numpy array alive, so its id stays unique
+    return v, f
+
+
 class SDF3D(Body3D):
     """bodies.py:627-760; ``kind`` selects the SDF evaluated on the device."""
     kind = None
@@ -101,10 +127,7 @@ class SDF3D(Body3D):
         self.scale = as_batched(scale, 0, device)
         self.shape = as_batched(shape, 1, device)
         verts, faces = mesh
-        self.verts = torch.as_tensor(np.asarray(verts) if not isinstance(verts, torch.Tensor) else verts).to(F64)
-        self.faces = torch.as_tensor(np.asarray(faces) if not isinstance(faces, torch.Tensor) else faces).to(torch.int32)
-        if device is not None:
-            self.verts, self.faces = self.verts.to(device), self.faces.to(device)
+        self.verts, self.faces = _mesh_tensors(verts, faces, device)
         self.sdf_grid = sdf_grid
         super().__init__(pos, **kw)
 
