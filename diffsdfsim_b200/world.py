@@ -332,7 +332,9 @@ class World3D:
             if not any_active:
                 break
         self.stats['rounds'].append(rounds)
-        self.t_host += self.dt
+        # host copy of the simulated time handed to non-vectorised force functions: exact for fixed_dt stepping; a
+        # variable-dt step may end early (world.py:134-137), then it is read back from the device (one sync, rare mode)
+        self.t_host = self.t_host + self.dt if fixed_dt else float(self.t.max())
         self._sync_bodies()
         self.trajectory.append((self.t if self.batched else float(self.t[0]), self.get_p(), self.v,
                                 self.contact_set, None))
