@@ -10,4 +10,7 @@ SCENES = {
     'bouncing_sphere': (lambda: scenes.bouncing_sphere(floor=(4.0, 1.0, 4.0), steps=14, floor_tri=0.2),
                         dict(fric_coeff=0.25, vel=[0.0, 0.0, 0.0, 2.0, 0.0, 0.0], pos=[0.0, 1.0, 0.0])),
     'grid_on_pole': (lambda: scenes.grid_on_pole(steps=8, with_floor=False), dict(mass=1.0, fric_coeff=0.15)),
+    # config-3 shape: several free bodies + pinned floor, every pair searched (pins pair order and multi-pair contact rows)
+    'mixed_primitives': (lambda: scenes.mixed_primitives(steps=8),
+                         dict(mass=1.2, vel=[0.0, 0.0, 0.0, 0.2, -1.0, 0.1])),
 }
