@@ -483,17 +483,45 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
         }
     }
     PH_MARK(PH_PUSH_COMPACT);
-    // contact geometry for every pre-filter contact (the reference's no_grad _compute_contacts)
-    int bad = 0;
+    // contact geometry for every pre-filter contact (the reference's no_grad _compute_contacts).  Faces that share a
+    // vertex often end at the very same body-frame point (bit-identical coordinates: the barycentrics are a unit
+    // vector); the geometry is a pure function of that point, so it is evaluated once per DISTINCT point and copied.
+    int* REP = sm.TMP;                 // representative (smallest index with identical coordinates)
+    int* UL = sm.HI;                   // compact list of representatives
     for (int k = tid; k < total; k += nt) {
+        const double a0 = sm.X[k], a1 = sm.X[capK + k], a2 = sm.X[2 * capK + k];
+        int rep = k;
+        for (int j = 0; j < k; ++j)
+            if (sm.X[j] == a0 && sm.X[capK + j] == a1 && sm.X[2 * capK + j] == a2) { rep = j; break; }
+        REP[k] = rep;
+        sm.SC[k] = rep == k;
+    }
+    int nuniq = 0;
+    block_exclusive_scan(sm.SC, total, &nuniq);
+    for (int k = tid; k < total; k += nt) if (REP[k] == k) UL[sm.SC[k]] = k;
+    __syncthreads();
+    int bad = 0;
+    for (int u = tid; u < nuniq; u += nt) {
+        const int k = UL[u];
         const V3<double> ct = v3<double>(sm.X[k], sm.X[capK + k], sm.X[2 * capK + k]);
         const ContactGeo<double> g = contact_geometry<double>(s1, s2, q1, x1, q2, x2, ct, fd_eps, detach_b2);
         sm.P[0 * capK + k] = g.n.x; sm.P[1 * capK + k] = g.n.y; sm.P[2 * capK + k] = g.n.z;
         sm.P[3 * capK + k] = g.p1.x; sm.P[4 * capK + k] = g.p1.y; sm.P[5 * capK + k] = g.p1.z;
         sm.P[6 * capK + k] = g.p2.x; sm.P[7 * capK + k] = g.p2.y; sm.P[8 * capK + k] = g.p2.z;
-        sm.X[k] = g.pen;                                   // X row 0 <- pen (this thread already consumed X[.][k])
+        sm.X[capK + k] = g.pen;                            // park pen in X row 1 until every duplicate has read row 0
         bad |= !(g.pen <= tol);
     }
+    __syncthreads();
+    for (int k = tid; k < total; k += nt) {
+        const int rp = REP[k];
+        if (rp != k) {
+#pragma unroll
+            for (int c = 0; c < 9; ++c) sm.P[(size_t)c * capK + k] = sm.P[(size_t)c * capK + rp];
+        }
+    }
+    __syncthreads();
+    for (int k = tid; k < total; k += nt) sm.X[k] = sm.X[capK + REP[k]];      // X row 0 <- pen
+    __syncthreads();
     r.valid = !__syncthreads_or(bad);
     r.count = total;
     PH_ADD(PH_PREFILTER, total);
