@@ -151,6 +151,13 @@ class ContactSet:
         c.pre_ids, c.pre_cnt = self.pre_ids, self.pre_cnt
         return c
 
+    def gathered(self, src):
+        """New set of len(src) worlds whose world w holds the contacts of world src[w] (src: int64 device tensor)."""
+        c = ContactSet(int(src.numel()), self.maxc, self.flat.device)
+        for k in ('count', 'status', 'body', 'face', 'abc', 'geo'):
+            getattr(c, k).copy_(getattr(self, k).index_select(0, src))
+        return c
+
     def clone(self):
         c = ContactSet(self.W, self.maxc, self.flat.device, self.flat.clone())
         if self.pre_ids is not None:
@@ -181,7 +188,7 @@ class ContactDetector:
         L = _lib.lib()
         _lib.require_cuda(p, shape)
         rc = _lib.call('dsdf_contacts_detect', self.table.ptr(), _lib.ptr(self.pairs), self.npairs, _lib.ptr(p),
-                       _lib.ptr(shape), _lib.ptr(active), self.W, self.nb, eps, tol, fd_eps, body_eps, int(detach_b2),
+                       _lib.ptr(shape), _lib.ptr(active), out.W, self.nb, eps, tol, fd_eps, body_eps, int(detach_b2),
                        self.capK, self.maxc, _lib.ptr(out.count), _lib.ptr(out.body), _lib.ptr(out.face),
                        _lib.ptr(out.abc), _lib.ptr(out.geo), _lib.ptr(out.status), _lib.ptr(out.pre_ids),
                        _lib.ptr(out.pre_cnt), _lib.stream())

@@ -84,7 +84,7 @@ attempt_commit_kernel(int W, int nb, int maxc, const unsigned char* __restrict__
     active_next[w] = nact;
     const int cnt_after = accept ? cn : co;
     if (bad) atomicOr(&flags[0], bad);
-    if (nact) atomicOr(&flags[1], 1);
+    if (nact) atomicAdd(&flags[1], 1);             // number of worlds still active
     if (any_toc) atomicOr(&flags[2], 1);
     atomicMax(&flags[3], cnt_after);
 }

@@ -238,7 +238,7 @@ int dsdf_dynamics_solve_backward(const double* p, const double* v, const double*
  * Out: accept (W) uint8; t_out = t (+ dt_try if accepted); dt_next (halved on reject, remaining time after a short
  *      accepted sub-step); active_next (W); toc_now (W) / toc_mask (W,maxc): contacts whose body pair had no contact
  *      before (world.py:273-274); toc_flag (W) updated in place; *_n: worlds that did not accept get the previous set
- *      back; flags[4] (device int32) = [capacity overflow (bit 0: capK, bit 1: maxc), any world still active, any time-of-contact, max contact
+ *      back; flags[4] (device int32) = [capacity overflow (bit 0: capK, bit 1: maxc), number of worlds still active, any time-of-contact, max contact
  *      count after the merge].
  */
 int dsdf_attempt_commit(int W, int nb, int maxc, const unsigned char* active, const double* dt_try,

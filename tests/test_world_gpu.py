@@ -386,3 +386,39 @@ def test_gradient_stopping_flags_match_oracle(flag):
             got = params[k].grad[w].cpu().numpy()
             np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4 * max(1e-9, np.abs(ref).max()),
                                        err_msg=f'{flag}: world {w} grad {k}')
+
+
+def test_speculative_halving_is_bitwise_identical_to_sequential_retries():
+    """Trying dt, dt/2, dt/4 of the few still-active worlds in one round (borrowed slots, first accepted attempt in
+    the reference's order wins) gives the same states, contacts, gradients AND attempt counts as retrying one after
+    the other -- with fewer rounds."""
+    from diffsdfsim_b200.world import World3D
+    W, steps = 4096, 24
+    gen = torch.Generator().manual_seed(0)
+    mass = 0.9 + 0.2 * torch.rand(W, generator=gen, dtype=F64)
+    fric = 0.01 + 0.24 * torch.rand(W, generator=gen, dtype=F64)
+    push = 2.0 + 3.0 * torch.rand(W, 2, generator=gen, dtype=F64)
+    spec = scenes.box_on_plane(steps=steps)
+    out = {}
+    for flag in (False, True):
+        World3D.speculate = flag
+        try:
+            params = dict(mass=mass.cuda().requires_grad_(True), fric_coeff=fric.cuda().requires_grad_(True),
+                          push=push.cuda().requires_grad_(True))
+            world = scenes.build_world(spec, device='cuda', params=params)
+            loss = 0.
+            for _ in range(steps):
+                world.step(fixed_dt=True)
+                loss = loss + (world.bodies[-1].pos ** 2).sum()
+            loss.backward()
+            out[flag] = (world.get_p().detach().clone(), world.v.detach().clone(), world.contact_set.count.clone(),
+                         world.stats['attempts'].clone(), {k: v.grad.clone() for k, v in params.items()},
+                         sum(world.stats['rounds']), world.t.clone())
+        finally:
+            World3D.speculate = True
+    a, b = out[False], out[True]
+    assert b[5] < a[5], 'speculation must save rounds (%d vs %d)' % (b[5], a[5])
+    assert torch.equal(a[3], b[3]), 'attempt counts'
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1]) and torch.equal(a[2], b[2]) and torch.equal(a[6], b[6])
+    for k in a[4]:
+        assert torch.equal(a[4][k], b[4][k]), k
