@@ -172,6 +172,13 @@ def run_ours(args):
     sampler.stop_flag = True
     final_pos = world.bodies[-1].pos.detach().cpu()
     final_grads = {k: v.detach().cpu() for k, v in grads.items()}
+    rounds_last = float(sum(world.stats['rounds']))
+    per_rank = None
+    if world_size > 1:
+        mine = torch.tensor([ms / args.steps, ms_e2e / args.steps, rounds_last], dtype=torch.float64, device=device)
+        allr = [torch.empty_like(mine) for _ in range(world_size)]
+        dist.all_gather(allr, mine)
+        per_rank = [[round(float(x), 2) for x in r] for r in allr]
     ms, ms_e2e = D.max_over_ranks([ms, ms_e2e], device)
     sdfq = None
     if rank == 0 and not args.no_sdf_query:
@@ -202,6 +209,9 @@ def run_ours(args):
         'roofline': roof,
         'kernel_ms_per_step': {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
     }
+    if per_rank is not None:
+        line['per_rank'] = {'columns': ['ms_per_step', 'ms_per_step_e2e', 'rounds_per_iteration'], 'rows': per_rank,
+                            'note': 'ranks step DIFFERENT worlds (seed = rank); the job time is the slowest rank'}
     if sdfq is not None:
         line['sdf_query'] = sdfq
     if secondary is not None:
@@ -462,10 +472,20 @@ def main():
     import atexit
     atexit.register(close_pool)
     args = parse()
+    # stdout carries exactly ONE JSON line: anything libraries print to file descriptor 1 while the benchmark runs
+    # (e.g. NCCL's version banner) is sent to stderr instead
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
     if args.impl == 'reference':
         line = run_reference(args)
         if line is not None:
-            print(json.dumps(line))
+            emit(line)
         return
     line = run_ours(args)
     if line is None:
@@ -496,7 +516,7 @@ def main():
                                       'after the full %d-step rollout (normalised by the largest reference gradient)'
                                       % (nw - 1, ns)}
     line.pop('_final', None)
-    print(json.dumps(line))
+    emit(line)
 
 
 if __name__ == '__main__':
