@@ -35,6 +35,7 @@ SIGNATURES = {
     'dsdf_dynamics_solve': (c_i, [c_p] * 13 + [c_i] * 6 + [c_d, c_i, c_i] + [c_p] * 8),
     'dsdf_dynamics_solve_backward': (c_i, [c_p] * 13 + [c_i] * 8 + [c_p] * 14),
     'dsdf_toc_backward': (c_i, [c_i] * 3 + [c_p] * 9 + [c_d] + [c_p] * 7),
+    'dsdf_contactset_move': (c_i, [c_i, c_i] + [c_p] * 16),
     'dsdf_attempt_commit': (c_i, [c_i] * 3 + [c_p] * 4 + [c_d, c_i, c_i] + [c_p] * 21),
 }
 
@@ -64,7 +65,7 @@ KERNELS_PER_CALL = {
     'dsdf_lcp_forward': 1, 'dsdf_lcp_backward': 1, 'dsdf_sdf_query': 1, 'dsdf_sdf_query_backward': 1,
     'dsdf_integrate': 1, 'dsdf_integrate_backward': 1, 'dsdf_contacts_detect': 1,
     'dsdf_contact_geometry_backward': 1, 'dsdf_dynamics_assemble': 1, 'dsdf_dynamics_assemble_backward': 1,
-    'dsdf_dynamics_solve': 1, 'dsdf_dynamics_solve_backward': 1, 'dsdf_attempt_commit': 1, 'dsdf_toc_backward': 1,
+    'dsdf_dynamics_solve': 1, 'dsdf_dynamics_solve_backward': 1, 'dsdf_attempt_commit': 1, 'dsdf_toc_backward': 1, 'dsdf_contactset_move': 1,
 }
 PROFILE = None      # set to {} to record (start, end) CUDA events around every entry-point call
 LAUNCHES = {}       # name -> number of calls since reset_counters()

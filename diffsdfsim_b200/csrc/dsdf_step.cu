@@ -89,7 +89,44 @@ attempt_commit_kernel(int W, int nb, int maxc, const unsigned char* __restrict__
     atomicMax(&flags[3], cnt_after);
 }
 
+// Row gather / masked row scatter of a contact set (count, status, body, face, abc, geo) between two batches:
+//   mask == NULL:  dst[i]          = src[idx[i]]                 for i < n   (gather into a compact batch)
+//   mask != NULL:  dst[idx[i]]     = src[sel[i]]  where mask[i]  for i < n   (commit the winning virtual worlds)
+__global__ void __launch_bounds__(128)
+contactset_move_kernel(int n, int maxc, const long long* __restrict__ idx, const long long* __restrict__ sel,
+                       const unsigned char* __restrict__ mask,
+                       const int* __restrict__ count_s, const int* __restrict__ status_s, const int* __restrict__ body_s,
+                       const int* __restrict__ face_s, const double* __restrict__ abc_s, const double* __restrict__ geo_s,
+                       int* __restrict__ count_d, int* __restrict__ status_d, int* __restrict__ body_d,
+                       int* __restrict__ face_d, double* __restrict__ abc_d, double* __restrict__ geo_d) {
+    const int i = blockIdx.x;
+    if (i >= n) return;
+    size_t s, d;
+    if (mask) { if (!mask[i]) return; s = (size_t)sel[i]; d = (size_t)idx[i]; }
+    else { s = (size_t)idx[i]; d = (size_t)i; }
+    if (threadIdx.x == 0) { count_d[d] = count_s[s]; status_d[d] = status_s[s]; }
+    const int nc = min(count_s[s], maxc);
+    for (int t = threadIdx.x; t < nc * 2; t += blockDim.x) body_d[d * maxc * 2 + t] = body_s[s * maxc * 2 + t];
+    for (int t = threadIdx.x; t < nc; t += blockDim.x) face_d[d * maxc + t] = face_s[s * maxc + t];
+    for (int t = threadIdx.x; t < nc * 3; t += blockDim.x) abc_d[d * maxc * 3 + t] = abc_s[s * maxc * 3 + t];
+    for (int t = threadIdx.x; t < nc * 10; t += blockDim.x) geo_d[d * maxc * 10 + t] = geo_s[s * maxc * 10 + t];
+}
+
 }  // namespace dsdf
+
+extern "C" int dsdf_contactset_move(int n, int maxc, const long long* idx, const long long* sel,
+                                    const unsigned char* mask,
+                                    const int32_t* count_s, const int32_t* status_s, const int32_t* body_s,
+                                    const int32_t* face_s, const double* abc_s, const double* geo_s,
+                                    int32_t* count_d, int32_t* status_d, int32_t* body_d, int32_t* face_d,
+                                    double* abc_d, double* geo_d, void* stream) {
+    if (n < 0 || maxc <= 0 || !idx || (mask && !sel)) return -1;
+    if (n == 0) return 0;
+    dsdf::contactset_move_kernel<<<n, 128, 0, (cudaStream_t)stream>>>(n, maxc, idx, sel, mask, count_s, status_s, body_s,
+                                                                     face_s, abc_s, geo_s, count_d, status_d, body_d,
+                                                                     face_d, abc_d, geo_d);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int dsdf_attempt_commit(int W, int nb, int maxc, const unsigned char* active, const double* dt_try,
                                    const double* t, const double* end_t, double world_dt, int strict, int toc_enabled,

@@ -499,10 +499,7 @@ class World3D:
         st.p = st.p.index_copy(0, win_w, p_try.index_select(0, win_s))
         st.v = st.v.index_copy(0, win_w, new_v.index_select(0, win_s))
         self.contact_geo = self.contact_geo.index_copy(0, win_w, geo.index_select(0, win_s))
-        new_set = self.contact_set.clone()
-        for k in ('count', 'status', 'body', 'face', 'abc', 'geo'):
-            getattr(new_set, k).index_copy_(0, win_w, getattr(cs, k).index_select(0, win_s))
-        self.contact_set = new_set
+        self.contact_set = self.contact_set.clone().scatter_from(cs, act_idx, sel, any_acc.to(torch.uint8))
         self.t = self.t.index_copy(0, win_w, t_new.index_select(0, win_s))
         if toc:
             self.last_dt = self.last_dt.index_copy(0, win_w, last_dt_in.index_select(0, win_s))
