@@ -472,13 +472,6 @@ class World3D:
                        _lib.ptr(accept), _lib.ptr(t_new), _lib.ptr(dt_next), _lib.ptr(active_next), _lib.ptr(toc_now),
                        _lib.ptr(toc_mask), _lib.ptr(flags), _lib.stream())
         _lib.check(rc, 'dsdf_attempt_commit')
-        if toc:
-            # the batch is tiny: apply the time-of-contact function unconditionally (identity where nothing is new)
-            dt_h = TimeOfContactNative.apply(dt_, p_try, new_v, geo, f_in, mass_in, toc_mask, cs.body)
-            p_redo = ops.integrate(p_in, new_v, dt_h, toc_now)
-            tn = toc_now.bool()
-            p_try = torch.where(tn[:, None, None], p_redo, p_try)
-            last_dt_in = torch.where(tn, dt_h, last_dt_in)
         # first accepted attempt of every active world, in the reference's order dt, dt/2, dt/4
         acc = accept.reshape(D, n).bool()
         any_acc = acc.any(0)
@@ -486,30 +479,34 @@ class World3D:
         sel = first * n + torch.arange(n, device=dev)                  # winning virtual world of active world i
         nxt_act = torch.where(any_acc, active_next.index_select(0, sel).bool(), torch.ones_like(any_acc))
         cnt = torch.where(any_acc, cs.count.index_select(0, sel), self.contact_set.count.index_select(0, act_idx))
-        info = torch.cat([flags, torch.stack([nxt_act.sum(), cnt.max(), toc_now.max()]).to(torch.int32)]).tolist()   # [sync 2]
+        info = torch.cat([flags, torch.stack([nxt_act.sum(), cnt.max()]).to(torch.int32)]).tolist()             # [sync 2]
         if info[0]:
             # an overflow in ANY virtual world (even a discarded one) grows the buffers; nothing has been committed yet
             self._grow_capacity(info[0])
             return self._attempt_speculative(active, dt_try, end_t)
-        if info[6]:
+        if toc and info[2]:
+            dt_h = TimeOfContactNative.apply(dt_, p_try, new_v, geo, f_in, mass_in, toc_mask, cs.body)
+            p_redo = ops.integrate(p_in, new_v, dt_h, toc_now)
+            tn = toc_now.bool()
+            p_try = torch.where(tn[:, None, None], p_redo, p_try)
+            last_dt_in = torch.where(tn, dt_h, last_dt_in)
             self._any_toc_flag = True
         self.stats['attempts'][act_idx] += torch.where(any_acc, first + 1, torch.full_like(first, D))
         # commit: world i takes the outputs of its winning attempt, or stays as it was and goes on halving
-        win_w, win_s, lose_w = act_idx[any_acc], sel[any_acc], act_idx[~any_acc]
-        st.p = st.p.index_copy(0, win_w, p_try.index_select(0, win_s))
-        st.v = st.v.index_copy(0, win_w, new_v.index_select(0, win_s))
-        self.contact_geo = self.contact_geo.index_copy(0, win_w, geo.index_select(0, win_s))
+        # (fixed-shape masked updates of the n active rows: no data-dependent shapes, hence no hidden synchronisation)
+        def put(cur, new_rows):
+            keep = any_acc.reshape((n,) + (1,) * (cur.dim() - 1))
+            return cur.index_copy(0, act_idx, torch.where(keep, new_rows.index_select(0, sel),
+                                                          cur.index_select(0, act_idx)))
+        st.p, st.v, self.contact_geo = put(st.p, p_try), put(st.v, new_v), put(self.contact_geo, geo)
         self.contact_set = self.contact_set.clone().scatter_from(cs, act_idx, sel, any_acc.to(torch.uint8))
-        self.t = self.t.index_copy(0, win_w, t_new.index_select(0, win_s))
+        self.t = put(self.t, t_new)
         if toc:
-            self.last_dt = self.last_dt.index_copy(0, win_w, last_dt_in.index_select(0, win_s))
-            self.toc_flag = self.toc_flag.index_copy(0, win_w, toc_flag.index_select(0, win_s))
-        dt_out = dt_try.index_copy(0, win_w, dt_next.index_select(0, win_s))
-        dt_out = dt_out.index_copy(0, lose_w, dt_try.index_select(0, lose_w) / (2 ** D))
-        act_out = torch.zeros_like(active)
-        act_out[act_idx] = nxt_act.to(torch.uint8)
-        acc_w = torch.zeros_like(active)
-        acc_w[win_w] = 1
+            self.last_dt, self.toc_flag = put(self.last_dt, last_dt_in), put(self.toc_flag, toc_flag)
+        dt_act = dt_try.index_select(0, act_idx)
+        dt_out = dt_try.index_copy(0, act_idx, torch.where(any_acc, dt_next.index_select(0, sel), dt_act / (2 ** D)))
+        act_out = torch.zeros_like(active).index_copy(0, act_idx, nxt_act.to(torch.uint8))
+        acc_w = torch.zeros_like(active).index_copy(0, act_idx, any_acc.to(torch.uint8))
         # the dynamics kernel sizes its shared memory by the largest contact count over ALL worlds
         self.max_nc = max(int(info[5]), int(self.max_nc))      # (an upper bound: the other worlds did not change)
         return acc_w, dt_out, act_out, int(info[4])
