@@ -1,0 +1,67 @@
+"""Host-side logic that needs no GPU: trajectory time matching, the flat contact-set layout, analytic meshes."""
+import numpy as np
+import torch
+
+F64 = torch.float64
+
+
+def test_nearest_time_index_matches_the_reference_scan():
+    """losses.nearest_time_index == the ascending scan of optim_sphere.py:121-139 (ties go to the LATER state)."""
+    from diffsdfsim_b200.losses import nearest_time_index
+    g = torch.Generator().manual_seed(0)
+    for _ in range(20):
+        S, Sp, W = 7, 9, 3
+        t = torch.cumsum(torch.rand(S, W, generator=g, dtype=F64) * 0.05, 0)
+        tt = torch.cumsum(torch.rand(Sp, W, generator=g, dtype=F64) * 0.05, 0)
+        tt[2] = tt[1] + 0.0                      # duplicate target times: exact ties
+        tt = torch.sort(tt, 0)[0]
+        idx = nearest_time_index(t, tt)
+        for w in range(W):
+            last_j = 0
+            for i in range(S):
+                min_diff, last_diff, new_j = 1e100, 1e100, 0
+                for j in range(last_j, Sp):
+                    diff = abs(float(t[i, w]) - float(tt[j, w]))
+                    if diff <= min_diff:
+                        min_diff, new_j = diff, j
+                    if diff > last_diff:
+                        break
+                    last_diff = diff
+                assert int(idx[i, w]) == new_j
+                last_j = new_j
+
+
+def test_contact_set_flat_layout_clone_and_resize():
+    from diffsdfsim_b200.contacts import ContactSet
+    W, m = 5, 4
+    cs = ContactSet(W, m, 'cpu')
+    assert cs.count.shape == (W,) and cs.body.shape == (W, m, 2) and cs.abc.shape == (W, m, 3) and cs.geo.shape == (W, m, 10)
+    for k in ('count', 'status', 'body', 'face', 'abc', 'geo'):
+        t = getattr(cs, k)
+        assert t.is_contiguous() and t.data_ptr() % 8 == 0
+        assert t.untyped_storage().data_ptr() == cs.flat.untyped_storage().data_ptr()      # all views of one buffer
+    cs.count[:] = torch.arange(W, dtype=torch.int32)
+    cs.geo[:] = torch.arange(W * m * 10, dtype=F64).reshape(W, m, 10)
+    c2 = cs.clone()
+    c2.geo.zero_()
+    assert float(cs.geo.sum()) > 0 and float(c2.geo.sum()) == 0 and torch.equal(c2.count, cs.count)
+    big = cs.resized(2 * m)
+    assert big.maxc == 2 * m and torch.equal(big.count, cs.count) and torch.equal(big.geo[:, :m], cs.geo)
+    assert float(big.geo[:, m:].abs().sum()) == 0
+
+
+def test_analytic_meshes_have_the_surveyed_sizes():
+    """custom_mesh=True box meshes (bodies.py:799-854): the sizes SURVEY.md probed on the reference."""
+    from diffsdfsim_b200 import meshes
+    v, f = meshes.box_mesh([20.0, 1.0, 20.0], 0.1)
+    assert v.shape == (89646, 3) and f.shape == (176000, 3)
+    v, f = meshes.box_mesh([1.0, 1.0, 1.0], 0.1)
+    assert v.shape == (726, 3) and f.shape == (1200, 3)
+    assert np.abs(v).max() == 0.5 and f.min() == 0 and f.max() == 725
+    # outward orientation: positive volume by the divergence theorem
+    tri = v[f]
+    vol = np.einsum('ij,ij->i', tri[:, 0], np.cross(tri[:, 1], tri[:, 2])).sum() / 6.0
+    assert abs(vol - 1.0) < 1e-9
+    v, f = meshes.icosphere(0.5, 4)
+    assert v.shape == (2562, 3) and f.shape == (5120, 3)
+    np.testing.assert_allclose(np.linalg.norm(v, axis=1), 0.5, rtol=1e-12)
