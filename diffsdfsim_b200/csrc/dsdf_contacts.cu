@@ -824,7 +824,10 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
 }
 
 // One CTA per world: broad phase, _overlap, and both search directions of every body pair, fused.
-enum { CONTACT_THREADS = 128 };
+#ifndef DSDF_CONTACT_THREADS
+#define DSDF_CONTACT_THREADS 128
+#endif
+enum { CONTACT_THREADS = DSDF_CONTACT_THREADS };
 #ifndef DSDF_CONTACT_MINBLOCKS
 #define DSDF_CONTACT_MINBLOCKS 4
 #endif
