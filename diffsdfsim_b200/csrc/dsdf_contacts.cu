@@ -13,6 +13,7 @@
 // contact_geometry_bwd_kernel (forward-mode duals w.r.t. the two poses).
 #define DSDF_OUTLINE_MATH
 #include "dsdf_contact_geo.cuh"
+#include "dsdf_steploop.cuh"
 
 namespace dsdf {
 
@@ -837,10 +838,15 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
                 int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
                 int capK, int maxc,
                 int* __restrict__ count, int* __restrict__ cbody, int* __restrict__ cface, double* __restrict__ cabc,
-                double* __restrict__ cgeo, int* __restrict__ wstatus, int* __restrict__ pre_ids, int* __restrict__ pre_cnt) {
+                double* __restrict__ cgeo, int* __restrict__ wstatus, int* __restrict__ pre_ids, int* __restrict__ pre_cnt,
+                const int* __restrict__ vmap, const int* __restrict__ ctrl) {
     extern __shared__ double smraw[];
     __shared__ int s_cnt;
+    // loop mode (ctrl != NULL, dsdf_steploop.cu): CTA w detects the contacts of virtual world w (poses p[w], outputs [w])
+    // with the shapes / per-world meshes / per-world grids of the real world wg = vmap[w]
     const int w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    if (ctrl && (loop_idle(ctrl) || w >= ctrl[CT_NVIRT])) return;
+    const int wg = vmap ? vmap[w] : w;
     if (active && !active[w]) return;
     const int ndirs = 2 * npairs;
     RefineSmem sm;
@@ -854,7 +860,7 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
         Q4<double> qi, qj; V3<double> xi, xj;
         load_pose(p, w, nb, bi, qi, xi);
         load_pose(p, w, nb, bj, qj, xj);
-        const double si = shape[((size_t)w * nb + bi) * 4 + 3], sj = shape[((size_t)w * nb + bj) * 4 + 3];
+        const double si = shape[((size_t)wg * nb + bi) * 4 + 3], sj = shape[((size_t)wg * nb + bj) * 4 + 3];
         // broad phase: AABB of the rotated cube of half side scale + eps (declared py3ode semantics)
         const M3<double> Ri = q2mat(qi), Rj = q2mat(qj);
         bool hit = true;
@@ -867,7 +873,7 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
         }
         int ov = 0;
         PH_MARK(-1);
-        if (hit) ov = any_vertex_in_cube(geom[bi], w, qi, xi, qj, xj, sj) && any_vertex_in_cube(geom[bj], w, qj, xj, qi, xi, si);
+        if (hit) ov = any_vertex_in_cube(geom[bi], wg, qi, xi, qj, xj, sj) && any_vertex_in_cube(geom[bj], wg, qj, xj, qi, xi, si);
         PH_MARK(PH_OVERLAP);
         if (!ov) {
             if (pre_cnt && tid == 0) { pre_cnt[(size_t)w * ndirs + 2 * pair] = -1; pre_cnt[(size_t)w * ndirs + 2 * pair + 1] = -1; }
@@ -877,15 +883,15 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
             const int d = 2 * pair + rev;
             const int i1 = rev ? bj : bi, i2 = rev ? bi : bj;
             const BodyGeom g1 = geom[i1];
-            const SdfShape s1 = body_shape(g1, shape, w, nb, i1);
-            const SdfShape s2 = body_shape(geom[i2], shape, w, nb, i2);
+            const SdfShape s1 = body_shape(g1, shape, wg, nb, i1);
+            const SdfShape s2 = body_shape(geom[i2], shape, wg, nb, i2);
             const Q4<double> q1 = rev ? qj : qi, q2 = rev ? qi : qj;
             const V3<double> x1 = rev ? xj : xi, x2 = rev ? xi : xj;
             PH_MARK(-1);
-            const int ncand = gather_candidates(g1, w, s2, q1, x1, q2, x2, eps, capK, sm.ID, &s_cnt);
+            const int ncand = gather_candidates(g1, wg, s2, q1, x1, q2, x2, eps, capK, sm.ID, &s_cnt);
             PH_MARK(PH_GATHER);
             if (ncand > capK) status |= 1;
-            DirResult r = search_direction(sm, capK, g1, s1, s2, q1, x1, q2, x2, w, ncand, eps, tol, fd_eps, detach_b2 != 0);
+            DirResult r = search_direction(sm, capK, g1, s1, s2, q1, x1, q2, x2, wg, ncand, eps, tol, fd_eps, detach_b2 != 0);
             if (pre_cnt) {
                 if (tid == 0) pre_cnt[(size_t)w * ndirs + d] = r.count;
                 for (int k = tid; k < r.count; k += nt) pre_ids[((size_t)w * ndirs + d) * capK + k] = sm.ID[k];
@@ -929,22 +935,35 @@ using namespace dsdf;
 
 extern "C" {
 
-int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, int npairs, const double* p,
-                         const double* shape, const unsigned char* active,
-                         int W, int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
-                         int capK, int maxc, int32_t* count, int32_t* cbody, int32_t* cface, double* cabc, double* cgeo,
-                         int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, void* stream) {
+static size_t g_contacts_smem = 0;
+
+int dsdf_contacts_detect_loop(const dsdf_body_geom* geom, const int32_t* pairs, int npairs, const double* p,
+                              const double* shape, const unsigned char* active,
+                              int W, int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
+                              int capK, int maxc, int32_t* count, int32_t* cbody, int32_t* cface, double* cabc, double* cgeo,
+                              int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, const int32_t* vmap, const int32_t* ctrl,
+                              void* stream) {
     if (W <= 0 || nb <= 0 || npairs < 0 || capK < 32 || capK > 1024 || (capK & 3) || maxc <= 0) return -1;
     static_assert(sizeof(BodyGeom) == sizeof(dsdf_body_geom), "BodyGeom must mirror dsdf_body_geom");
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = refine_smem_bytes(capK);
     if (smem > 227 * 1024) return -2;
-    cudaError_t e = cudaFuncSetAttribute(contacts_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_smem(contacts_kernel, smem, &g_contacts_smem);
     if (e != cudaSuccess) return (int)e;
     contacts_kernel<<<W, CONTACT_THREADS, smem, st>>>(reinterpret_cast<const BodyGeom*>(geom), pairs, npairs, p, shape, active, nb,
                                           eps, tol, fd_eps, body_eps, detach_b2, capK, maxc, count, cbody, cface, cabc,
-                                          cgeo, wstatus, pre_ids, pre_cnt);
+                                          cgeo, wstatus, pre_ids, pre_cnt, vmap, ctrl);
     return (int)cudaGetLastError();
+}
+
+int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, int npairs, const double* p,
+                         const double* shape, const unsigned char* active,
+                         int W, int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
+                         int capK, int maxc, int32_t* count, int32_t* cbody, int32_t* cface, double* cabc, double* cgeo,
+                         int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, void* stream) {
+    return dsdf_contacts_detect_loop(geom, pairs, npairs, p, shape, active, W, nb, eps, tol, fd_eps, body_eps, detach_b2,
+                                     capK, maxc, count, cbody, cface, cabc, cgeo, wstatus, pre_ids, pre_cnt, nullptr,
+                                     nullptr, stream);
 }
 
 int dsdf_contacts_phase_cycles(unsigned long long* out8, int reset) {   /* out: PH_COUNT = 16 counters */

@@ -10,6 +10,15 @@ namespace dsdf {
 
 #define DSDF_FULL 0xffffffffu
 
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize) once per size increase of a kernel, not once per launch
+// (*granted: a per-kernel static of the calling translation unit; one process drives one GPU).
+template <class K> static inline cudaError_t ensure_smem(K kernel, size_t smem, size_t* granted) {
+    if (smem <= *granted) return cudaSuccess;
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) *granted = smem;
+    return e;
+}
+
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(DSDF_FULL, v, o);

@@ -18,6 +18,7 @@
 // round-off; verified against the dense kernels and the oracle in tests/test_dynsolve_gpu.py.
 #include "dsdf_math.cuh"
 #include "dsdf_dense.cuh"
+#include "dsdf_steploop.cuh"
 #include "../../include/dsdf_b200.h"
 
 namespace dsdf {
@@ -401,24 +402,32 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
                    const int* __restrict__ eq_rows, int nb, int neq, int maxc, int C, int fd,
                    double eps, int not_improved_lim, int max_iter,
                    double* __restrict__ xo, double* __restrict__ nvo, double* __restrict__ nuo, double* __restrict__ lamo,
-                   double* __restrict__ so, int* __restrict__ status_o, int* __restrict__ iters_o) {
+                   double* __restrict__ so, int* __restrict__ status_o, int* __restrict__ iters_o,
+                   const int* __restrict__ vmap, int* __restrict__ ctrl) {
     extern __shared__ double smd[];
+    // loop mode (ctrl != NULL, dsdf_steploop.cu): CTA w solves virtual world w = one attempt (its own dt[w]) of the real
+    // world ws = vmap[w], whose state / parameters / contacts are read in place; outputs are indexed by w
     const int w = blockIdx.x, lane = threadIdx.x & 31;
+    if (ctrl && (loop_idle(ctrl) || w >= ctrl[CT_NVIRT])) return;
+    const int ws = vmap ? vmap[w] : w;
     const DynSmem L = dyn_layout(nb, neq, C, fd);
     const int nz = L.nz, nq = L.nq, per = L.per;
     if (active && !active[w]) {               // inactive world: velocity passes through
-        if (nvo) for (int i = lane; i < nz; i += 32) nvo[(size_t)w * nz + i] = v[(size_t)w * nz + i];
+        if (nvo) for (int i = lane; i < nz; i += 32) nvo[(size_t)w * nz + i] = v[(size_t)ws * nz + i];
         return;
     }
     DynCtx c = dyn_ctx(smd, L);
-    if (count[w] > C) {                       // more contacts than this launch's shared memory holds
+    if (count[ws] > C) {                      // more contacts than this launch's shared memory holds
         for (int i = lane; i < nz; i += 32) { xo[(size_t)w * nz + i] = NAN; if (nvo) nvo[(size_t)w * nz + i] = NAN; }
-        if (lane == 0) { status_o[w] = DSDF_LCP_TOO_LARGE; if (iters_o) iters_o[w] = 0; }
+        if (lane == 0) {
+            status_o[w] = DSDF_LCP_TOO_LARGE; if (iters_o) iters_o[w] = 0;
+            if (ctrl) atomicOr(&ctrl[CT_ABORT], DSDF_STEP_DYN_SMEM);      // the host re-launches with a larger C
+        }
         return;
     }
     __shared__ double s_mu[64], s_e[64], s_h[64];   // per contact: friction coefficient, restitution, h (C <= 64)
     const double* mu = s_mu;
-    dyn_load(c, w, p, v, mass, Ibody, fric, rest, f, dt[w], count, cbody, cgeo, eq_rows, maxc, fd, s_mu, s_e, s_h);
+    dyn_load(c, ws, p, v, mass, Ibody, fric, rest, f, dt[w], count, cbody, cgeo, eq_rows, maxc, fd, s_mu, s_e, s_h);
     auto hrow = [&](int r) { return (r % per == 0) ? s_h[r / per] : 0.0; };
     const int niCap = maxc * per;
     for (int r = lane; r < niCap; r += 32) { lamo[(size_t)w * niCap + r] = 0.0; so[(size_t)w * niCap + r] = 0.0; }
@@ -708,6 +717,28 @@ static int dyn_check(int W, int nb, int neq, int maxc, int* C, int fd, size_t* s
     return 0;
 }
 
+static size_t g_fwd_smem = 0, g_bwd_smem = 0;
+
+int dsdf_dynamics_solve_loop(const double* p, const double* v, const double* mass, const double* Ibody,
+                             const double* fric, const double* rest, const double* f, const double* dt,
+                             const unsigned char* active, const int32_t* count, const int32_t* cbody, const double* cgeo,
+                             const int32_t* eq_rows, int W, int nb, int neq, int maxc, int ncontacts_smem, int fric_dirs,
+                             double eps, int not_improved_lim, int max_iter,
+                             double* x, double* new_v, double* nu, double* lam, double* s, int32_t* status, int32_t* iters,
+                             const int32_t* vmap, int32_t* ctrl, void* stream) {
+    size_t smem;
+    int C = ncontacts_smem;
+    int rc = dyn_check(W, nb, neq, maxc, &C, fric_dirs, &smem);
+    if (rc) return rc;
+    cudaError_t e = ensure_smem(dyn_forward_kernel, smem, &g_fwd_smem);
+    if (e != cudaSuccess) return (int)e;
+    dyn_forward_kernel<<<W, 32, smem, (cudaStream_t)stream>>>(p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody,
+                                                              cgeo, eq_rows, nb, neq, maxc, C, fric_dirs, eps,
+                                                              not_improved_lim, max_iter, x, new_v, nu, lam, s, status, iters,
+                                                              vmap, ctrl);
+    return (int)cudaGetLastError();
+}
+
 int dsdf_dynamics_solve(const double* p, const double* v, const double* mass, const double* Ibody,
                         const double* fric, const double* rest, const double* f, const double* dt,
                         const unsigned char* active, const int32_t* count, const int32_t* cbody, const double* cgeo,
@@ -715,16 +746,9 @@ int dsdf_dynamics_solve(const double* p, const double* v, const double* mass, co
                         double eps, int not_improved_lim, int max_iter,
                         double* x, double* new_v, double* nu, double* lam, double* s, int32_t* status, int32_t* iters,
                         void* stream) {
-    size_t smem;
-    int C = ncontacts_smem;
-    int rc = dyn_check(W, nb, neq, maxc, &C, fric_dirs, &smem);
-    if (rc) return rc;
-    cudaError_t e = cudaFuncSetAttribute(dyn_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return (int)e;
-    dyn_forward_kernel<<<W, 32, smem, (cudaStream_t)stream>>>(p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody,
-                                                              cgeo, eq_rows, nb, neq, maxc, C, fric_dirs, eps,
-                                                              not_improved_lim, max_iter, x, new_v, nu, lam, s, status, iters);
-    return (int)cudaGetLastError();
+    return dsdf_dynamics_solve_loop(p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody, cgeo, eq_rows, W, nb, neq,
+                                    maxc, ncontacts_smem, fric_dirs, eps, not_improved_lim, max_iter, x, new_v, nu, lam, s,
+                                    status, iters, nullptr, nullptr, stream);
 }
 
 int dsdf_dynamics_solve_backward(const double* p, const double* v, const double* mass, const double* Ibody,
@@ -739,7 +763,7 @@ int dsdf_dynamics_solve_backward(const double* p, const double* v, const double*
     int C = ncontacts_smem;
     int rc = dyn_check(W, nb, neq, maxc, &C, fric_dirs, &smem);
     if (rc) return rc;
-    cudaError_t e = cudaFuncSetAttribute(dyn_backward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    cudaError_t e = ensure_smem(dyn_backward_kernel, smem, &g_bwd_smem);
     if (e != cudaSuccess) return (int)e;
     dyn_backward_kernel<<<W, 32, smem, (cudaStream_t)stream>>>(p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody,
                                                                cgeo, eq_rows, nb, neq, maxc, C, fric_dirs,

@@ -3,6 +3,7 @@
 //   dsdf_integrate[_backward]   Body3D.move / set_p (pose)   sdf_physics/physics3d/bodies.py:488-511
 // Backward kernels use forward-mode duals of the same device code (dsdf_math.cuh), one seed per input scalar.
 #include "dsdf_sdf.cuh"
+#include "dsdf_integrate.cuh"
 
 namespace dsdf {
 
@@ -174,16 +175,6 @@ sdf_query_bwd_kernel(int kind, const double* __restrict__ shape, const double* _
             gpts[3 * o + k] = gs * r.d.d + g0 * r.n.x.d + g1 * r.n.y.d + g2 * r.n.z.d;
         }
     }
-}
-
-// ---- integrator: q <- standardize(quat(expmap(w dt)) (x) q), x <- x + v dt  (bodies.py:488-491) ----------------------
-template <class S>
-__device__ __forceinline__ void integrate_one(const S* p, const S* v, S dt, S* out) {
-    M3<S> R = expmap<S>(v3<S>(v[0] * dt, v[1] * dt, v[2] * dt));
-    Q4<S> dq = mat2q<S>(R);
-    Q4<S> q = qmul<S>(dq, q4<S>(p[0], p[1], p[2], p[3]));
-    out[0] = q.w; out[1] = q.x; out[2] = q.y; out[3] = q.z;
-    out[4] = p[4] + v[3] * dt; out[5] = p[5] + v[4] * dt; out[6] = p[6] + v[5] * dt;
 }
 
 __global__ void __launch_bounds__(128)

@@ -16,6 +16,7 @@ from . import contacts as contacts_module
 from . import engines as engines_module
 from . import _lib, ops
 from .contacts import ContactDetector, GeometryTable, differentiable_geometry
+from .stepper import DeviceStepper, _StepFn
 from .transforms import quaternion_to_matrix, so3_exponential_map
 from .utils import Defaults3D, default_device, get_instance
 
@@ -101,6 +102,8 @@ class World3D:
     speculate = True       # evaluate dt, dt/2, dt/4 of the few still-active worlds in ONE round (see _attempt_speculative)
     SPEC_DEPTH = 3
     toc_native = True      # False: the torch-autograd restatement of World.H (TimeOfContact) on the affected worlds
+    device_loop = True     # the per-world step state machine runs on the device (stepper.py / csrc/dsdf_steploop.cu);
+                           # False: the host-driven round loop below (one synchronisation per round)
 
     def __init__(self, bodies, constraints=[], dt=Defaults3D.DT, engine=Defaults3D.ENGINE,
                  contact_callback=Defaults3D.CONTACT, eps=Defaults3D.EPSILON, tol=Defaults3D.TOL,
@@ -182,6 +185,7 @@ class World3D:
         self._f_vectorized = any(getattr(f, 'vectorized', False) for b in self.bodies for f in b.forces)
         self.contact_set = self.detector.new_set()
         self.contact_geo = None
+        self._stepper, self._last_tape = None, None
         with self._on_device():
             while True:
                 self.find_contacts()
@@ -309,12 +313,52 @@ class World3D:
         with self._on_device():                      # kernels launch on the world's device, whatever is current
             return self._step(fixed_dt)
 
-    def _step(self, fixed_dt):
+    def _use_device_loop(self):
+        """The device-resident loop covers the default configuration; plug-in engines, the dense LCP path, the torch
+        restatement of World.H, per-sub-step (vectorised) forces and pre-filter recording use the host-driven loop."""
+        return (self.device_loop and self.device.type == 'cuda' and type(self.engine) is engines_module.PdipmEngine
+                and self.toc_native and not self._f_vectorized and not self.detector.record_prefilter)
+
+    def _snapshot(self):
         st = self.state
-        self._undo = (st.p, st.v, self.contact_set, self.contact_geo, self.t, self.t_host, self.toc_flag.clone(),
-                      self.last_dt, len(self.trajectory), self._any_toc_flag)
-        W, dev = self.W, self.device
+        return (st.p, st.v, self.contact_set, self.contact_geo, self.t, self.t_host, self.toc_flag.clone(),
+                self.last_dt, len(self.trajectory), self._any_toc_flag, self.max_nc)
+
+    def _step(self, fixed_dt):
+        self._undo = self._snapshot()
         self._f_cache = None
+        if self._use_device_loop():
+            had = self._step_device(fixed_dt)
+        else:
+            had = self._step_host(fixed_dt)
+        # host copy of the simulated time handed to non-vectorised force functions: exact for fixed_dt stepping; a
+        # variable-dt step may end early (world.py:134-137), then it is read back from the device (one sync, rare mode)
+        self.t_host = self.t_host + self.dt if fixed_dt else float(self.t.max())
+        self._sync_bodies()
+        self.trajectory.append((self.t if self.batched else float(self.t[0]), self.get_p(), self.v,
+                                self.contact_set, None))
+        return had if self.batched else bool(had[0])
+
+    def _step_device(self, fixed_dt):
+        """world.py:119-139 with the whole sub-step state machine on the device: one autograd node, normally one host
+        synchronisation (the 64-byte control block of stepper.DeviceStepper)."""
+        st = self.state
+        if self._stepper is None:
+            self._stepper = DeviceStepper(self)
+        p, v, geo, last_dt, had = _StepFn.apply(self, fixed_dt, st.p, st.v, self.contact_geo, self.last_dt, st.mass,
+                                                st.Ibody, st.fric, st.rest, self.step_forces())
+        tape = self._last_tape
+        st.p, st.v, self.contact_geo, self.last_dt = p, v, geo, last_dt
+        self.contact_set = tape.final
+        self.max_nc = max(int(self.max_nc), int(self._stepper.max_count))
+        self._any_toc_flag = self._any_toc_flag or tape.any_toc
+        self.stats['rounds'].append(tape.rounds)
+        self.stats.setdefault('syncs', []).append(tape.syncs)
+        self._last_tape = None
+        return had
+
+    def _step_host(self, fixed_dt):
+        W, dev = self.W, self.device
         end_t = (self.t + self.dt) if fixed_dt else None
         dt_try = torch.full((W,), float(self.dt), dtype=F64, device=dev)
         active = torch.ones(W, dtype=torch.uint8, device=dev)
@@ -338,19 +382,19 @@ class World3D:
             if not n_active:
                 break
         self.stats['rounds'].append(rounds)
-        # host copy of the simulated time handed to non-vectorised force functions: exact for fixed_dt stepping; a
-        # variable-dt step may end early (world.py:134-137), then it is read back from the device (one sync, rare mode)
-        self.t_host = self.t_host + self.dt if fixed_dt else float(self.t.max())
-        self._sync_bodies()
-        self.trajectory.append((self.t if self.batched else float(self.t[0]), self.get_p(), self.v,
-                                self.contact_set, None))
-        return had if self.batched else bool(had[0])
+        return had
 
     def undo_step(self):
-        """world.py:106-116."""
+        """world.py:106-116.  The contact capacity may have grown during the undone step: the restored set is brought to
+        the current capacity, and the contact-count bound that sizes the dynamics kernel never shrinks."""
         st = self.state
-        (st.p, st.v, self.contact_set, self.contact_geo, self.t, self.t_host, self.toc_flag, self.last_dt, ntraj,
-         self._any_toc_flag) = self._undo
+        (st.p, st.v, cs, geo, self.t, self.t_host, self.toc_flag, self.last_dt, ntraj,
+         self._any_toc_flag, max_nc) = self._undo
+        if cs.maxc != self.maxc:
+            cs = cs.resized(self.maxc)
+            geo = torch.cat([geo, geo.new_zeros(self.W, self.maxc - geo.shape[1], 10)], 1)
+        self.contact_set, self.contact_geo = cs, geo
+        self.max_nc = max(int(self.max_nc), int(max_nc))
         del self.trajectory[ntraj:]
         self._sync_bodies()
 
@@ -528,7 +572,10 @@ class World3D:
             self.contact_set = self.contact_set.resized(maxc)
             pad = self.contact_geo.new_zeros(self.W, maxc - self.maxc, 10)
             self.contact_geo = torch.cat([self.contact_geo, pad], 1)
-            self.maxc = maxc
+        self._set_capacity(capK, maxc)
+
+    def _set_capacity(self, capK, maxc):
+        self.maxc = maxc
         self.detector = ContactDetector(self.table, self.pairs, self.W, self.nb, self.device, capK=capK, maxc=maxc,
                                         record_prefilter=self.detector.record_prefilter)
 

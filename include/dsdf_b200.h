@@ -274,6 +274,87 @@ int dsdf_contactset_move(int n, int maxc, const long long* idx, const long long*
                          int32_t* count_d, int32_t* status_d, int32_t* body_d, int32_t* face_d,
                          double* abc_d, double* geo_d, void* stream);
 
+/* Loop-mode variants of dsdf_dynamics_solve / dsdf_contacts_detect used by the device-resident step loop below:
+ * CTA w works on VIRTUAL world w (its own dt[w] / poses p[w], outputs at [w]) but reads the state, parameters, current
+ * contacts, shapes and per-world geometry of the real world vmap[w]; ctrl = the loop's control block (every CTA returns
+ * at once when the loop is idle).  vmap == NULL && ctrl == NULL: identical to the plain entry points. */
+int dsdf_dynamics_solve_loop(const double* p, const double* v, const double* mass, const double* Ibody,
+                             const double* fric, const double* rest, const double* f, const double* dt,
+                             const unsigned char* active, const int32_t* count, const int32_t* cbody, const double* cgeo,
+                             const int32_t* eq_rows, int W, int nb, int neq, int maxc, int ncontacts_smem, int fric_dirs,
+                             double eps, int not_improved_lim, int max_iter,
+                             double* x, double* new_v, double* nu, double* lam, double* s, int32_t* status, int32_t* iters,
+                             const int32_t* vmap, int32_t* ctrl, void* stream);
+int dsdf_contacts_detect_loop(const dsdf_body_geom* geom, const int32_t* pairs, int npairs, const double* p,
+                              const double* shape, const unsigned char* active,
+                              int W, int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
+                              int capK, int maxc, int32_t* count, int32_t* cbody, int32_t* cface, double* cabc, double* cgeo,
+                              int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, const int32_t* vmap, const int32_t* ctrl,
+                              void* stream);
+
+/* ------------------------------------------------- device-resident step ----
+ * World.step / World.step_dt (lcp_physics/physics/world.py:119-139, 241-379) as a state machine that lives on the
+ * device: the host launches ROUNDS (one attempt of every world still inside its step: prep -> solve -> move ->
+ * find_contacts -> commit) in bursts and reads one small control block per burst; accept / reject / halve dt /
+ * give up below dt/2^10 / remaining time / time-of-contact flags are decided per world by the commit kernel, which also
+ * writes the TAPE of accepted sub-steps that the reverse sweep consumes.  See csrc/dsdf_steploop.cu.
+ *
+ * All fields are 8 bytes wide (no padding).  Arrays are device memory; (W..) = per real world, (V..) = per virtual world
+ * (V = vcap rows; attempt d of the i-th active world is row d * n_active + i).
+ */
+#define DSDF_STEP_MAX_SLOTS 16
+/* bits of ctrl[0] (abort word): what the host must do before launching further rounds */
+#define DSDF_STEP_CAPK        1   /* a paused world overflowed the candidate list: enlarge capK          */
+#define DSDF_STEP_MAXC        2   /* a paused world found more than maxc contacts: enlarge maxc           */
+#define DSDF_STEP_DYN_SMEM    4   /* a world has more contacts than ncontacts_smem: round voided           */
+#define DSDF_STEP_TAPE        8   /* a paused world accepted more sub-steps than n_slots: add tape slots   */
+#define DSDF_STEP_MAX_ROUNDS 16   /* max_rounds reached with worlds still active                           */
+/* words of the control block (int32[16]) the host reads back */
+#define DSDF_CTRL_ABORT 0
+#define DSDF_CTRL_NACTIVE 1
+#define DSDF_CTRL_MAXCOUNT 3
+#define DSDF_CTRL_ROUNDS 4
+#define DSDF_CTRL_MAXNSUB 5
+#define DSDF_CTRL_ANYTOC 8
+#define DSDF_CTRL_LCPSTATUS 9
+
+typedef struct dsdf_step_slot {      /* tape of the k-th accepted sub-step of every world in this step */
+    double *p_in, *v_in;             /* (W,nb,7), (W,nb,6) state the sub-step started from                         */
+    double *x, *new_v, *p_try;       /* (W,6nb) LCP solution, (W,nb,6) = -x, (W,nb,7) pose after the move          */
+    double *dt_raw, *dt_used;        /* (W) sub-step length; value that entered solve / move (world.py:253-257)    */
+    double *lam, *s;                 /* (W, maxc (2+fd)) multipliers / slacks, reference row order                 */
+    unsigned char *toc_flag_in, *toc_now, *toc_mask;   /* (W), (W), (W,maxc)                                        */
+    int32_t *count, *body, *face;    /* contact set found at the END of the sub-step: (W), (W,maxc,2), (W,maxc)    */
+    double *abc, *geo;               /* (W,maxc,3), (W,maxc,10)                                                    */
+} dsdf_step_slot;
+
+typedef struct dsdf_step_args {
+    int64_t W, nb, neq, maxc, fric_dirs, capK, npairs;
+    int64_t depth;                   /* attempts (dt, dt/2, ..) evaluated at once when <= spec_threshold worlds are active */
+    int64_t spec_threshold, vcap, n_slots, max_iter, max_rounds;
+    int64_t strict, toc_enabled, fixed_dt, detach_b2;
+    double world_dt, eps, tol, fd_eps, body_eps;
+    const dsdf_body_geom* geom; const int32_t* pairs; const int32_t* eq_rows;
+    const double *mass, *Ibody, *fric, *rest, *f, *shape;              /* (W,nb..) constant during the step */
+    double *p, *v, *t, *dt_try, *end_t, *last_dt;                      /* state, updated in place */
+    unsigned char *active, *toc_flag, *had;
+    int32_t* nsub; int64_t* attempts;
+    int32_t *count, *status, *body, *face; double *abc, *geo;          /* current contact set, updated in place */
+    int32_t *vmap, *vidx; double *dt_raw_v, *dt_used_v;                /* (V), (W), (V), (V) */
+    double *x_v, *new_v_v, *nu_v, *lam_v, *s_v, *p_try_v; int32_t *lcp_status_v, *iters_v;
+    int32_t *count_v, *status_v, *body_v, *face_v; double *abc_v, *geo_v;
+    int32_t* ctrl;                                                     /* int32[16] */
+    dsdf_step_slot slots[DSDF_STEP_MAX_SLOTS];
+} dsdf_step_args;
+
+/* Start a step: every world active with dt_try = world_dt, end_t = t + world_dt, control block reset. */
+int dsdf_step_begin(const dsdf_step_args* a, void* stream);
+/* Clear the abort word after the host enlarged a buffer (a may carry new pointers / sizes from here on). */
+int dsdf_step_resume(const dsdf_step_args* a, void* stream);
+/* Launch n_rounds rounds (5 kernels each) without any host synchronisation.  ncontacts_smem: contacts the dynamics
+ * kernel sizes its shared memory for.  a is a HOST pointer; it is passed to the kernels by value. */
+int dsdf_step_rounds(const dsdf_step_args* a, int n_rounds, int ncontacts_smem, void* stream);
+
 #ifdef __cplusplus
 }
 #endif
