@@ -14,17 +14,19 @@ __global__ void __launch_bounds__(128, 5)
 contact_geometry_bwd_kernel(const BodyGeom* __restrict__ geom, const double* __restrict__ p,
                             const double* __restrict__ shape, int nb, double fd_eps, int detach_b2, int maxc,
                             const int* __restrict__ count, const int* __restrict__ cbody, const int* __restrict__ cface,
-                            const double* __restrict__ cabc, const double* __restrict__ ggeo, double* __restrict__ gp) {
+                            const double* __restrict__ cabc, const double* __restrict__ ggeo, double* __restrict__ gp,
+                            const int* __restrict__ wmap) {
     extern __shared__ double part[];          // [maxc][14]
     const int w = blockIdx.x;
+    const int wg = wmap ? wmap[w] : w;        // row w of a compact batch belongs to world wg (shapes, per-world geometry)
     const int nc = min(count[w], maxc);
     for (int item = threadIdx.x; item < nc * 14; item += blockDim.x) {
         const int k = item / 14, j = item % 14;
         const size_t oo = (size_t)w * maxc + k;
         const int i1 = cbody[2 * oo], i2 = cbody[2 * oo + 1];
         const BodyGeom g1 = geom[i1];
-        const SdfShape s1 = body_shape(g1, shape, w, nb, i1);
-        const SdfShape s2 = body_shape(geom[i2], shape, w, nb, i2);
+        const SdfShape s1 = body_shape(g1, shape, wg, nb, i1);
+        const SdfShape s2 = body_shape(geom[i2], shape, wg, nb, i2);
         const double* P1 = p + ((size_t)w * nb + i1) * 7;
         const double* P2 = p + ((size_t)w * nb + i2) * 7;
         const int s1seed = j < 7 ? j : -1, s2seed = j >= 7 ? j - 7 : -1;
@@ -34,8 +36,8 @@ contact_geometry_bwd_kernel(const BodyGeom* __restrict__ geom, const double* __r
         Q4<Dual> q2 = q4<Dual>(D(P2, 0, s2seed), D(P2, 1, s2seed), D(P2, 2, s2seed), D(P2, 3, s2seed));
         V3<Dual> x2 = v3<Dual>(D(P2, 4, s2seed), D(P2, 5, s2seed), D(P2, 6, s2seed));
         const int f = cface[oo];
-        const V3<double> va = load_vert(g1, w, g1.faces[3 * f]), vb = load_vert(g1, w, g1.faces[3 * f + 1]),
-                         vc = load_vert(g1, w, g1.faces[3 * f + 2]);
+        const V3<double> va = load_vert(g1, wg, g1.faces[3 * f]), vb = load_vert(g1, wg, g1.faces[3 * f + 1]),
+                         vc = load_vert(g1, wg, g1.faces[3 * f + 2]);
         const double a = cabc[3 * oo], b = cabc[3 * oo + 1], c = cabc[3 * oo + 2];
         const V3<double> ct = v3<double>(va.x * a + vb.x * b + vc.x * c, va.y * a + vb.y * b + vc.y * c,
                                          va.z * a + vb.z * b + vc.z * c);
@@ -64,14 +66,28 @@ using namespace dsdf;
 
 extern "C" {
 
+int dsdf_contact_geometry_backward_rows(const dsdf_body_geom* geom, const double* p, const double* shape, int W, int nb,
+                                        double fd_eps, int detach_b2, int maxc, const int32_t* count,
+                                        const int32_t* cbody, const int32_t* cface, const double* cabc,
+                                        const double* ggeo, double* gp, const int32_t* wmap, void* stream) {
+    if (W <= 0 || nb <= 0 || maxc <= 0) return -1;
+    const size_t smem = (size_t)maxc * 14 * sizeof(double);
+    static size_t granted = 0;
+    if (smem > 48 * 1024) {
+        cudaError_t e = ensure_smem(contact_geometry_bwd_kernel, smem, &granted);
+        if (e != cudaSuccess) return (int)e;
+    }
+    contact_geometry_bwd_kernel<<<W, 128, smem, (cudaStream_t)stream>>>(reinterpret_cast<const BodyGeom*>(geom), p, shape, nb,
+                                                                    fd_eps, detach_b2, maxc, count, cbody, cface, cabc,
+                                                                    ggeo, gp, wmap);
+    return (int)cudaGetLastError();
+}
+
 int dsdf_contact_geometry_backward(const dsdf_body_geom* geom, const double* p, const double* shape, int W, int nb,
                                    double fd_eps, int detach_b2, int maxc, const int32_t* count, const int32_t* cbody,
                                    const int32_t* cface, const double* cabc, const double* ggeo, double* gp, void* stream) {
-    if (W <= 0 || nb <= 0 || maxc <= 0) return -1;
-    contact_geometry_bwd_kernel<<<W, 128, (size_t)maxc * 14 * sizeof(double), (cudaStream_t)stream>>>(reinterpret_cast<const BodyGeom*>(geom), p, shape, nb,
-                                                                    fd_eps, detach_b2, maxc, count, cbody, cface, cabc,
-                                                                    ggeo, gp);
-    return (int)cudaGetLastError();
+    return dsdf_contact_geometry_backward_rows(geom, p, shape, W, nb, fd_eps, detach_b2, maxc, count, cbody, cface, cabc,
+                                               ggeo, gp, nullptr, stream);
 }
 
 }  // extern "C"

@@ -403,7 +403,7 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
                    double eps, int not_improved_lim, int max_iter,
                    double* __restrict__ xo, double* __restrict__ nvo, double* __restrict__ nuo, double* __restrict__ lamo,
                    double* __restrict__ so, int* __restrict__ status_o, int* __restrict__ iters_o,
-                   const int* __restrict__ vmap, int* __restrict__ ctrl) {
+                   const int* __restrict__ vmap, int* __restrict__ ctrl, int cmin, int last_class) {
     extern __shared__ double smd[];
     // loop mode (ctrl != NULL, dsdf_steploop.cu): CTA w solves virtual world w = one attempt (its own dt[w]) of the real
     // world ws = vmap[w], whose state / parameters / contacts are read in place; outputs are indexed by w
@@ -417,6 +417,9 @@ dyn_forward_kernel(const double* __restrict__ p, const double* __restrict__ v, c
         return;
     }
     DynCtx c = dyn_ctx(smd, L);
+    // contact-count classes: one launch sized for the typical count, one for the few worlds with many contacts (a world
+    // that gave up halving keeps a penetrating state with dozens of contacts; sizing every CTA for it costs occupancy)
+    if (count[ws] <= cmin || (count[ws] > C && !last_class)) return;
     if (count[ws] > C) {                      // more contacts than this launch's shared memory holds
         for (int i = lane; i < nz; i += 32) { xo[(size_t)w * nz + i] = NAN; if (nvo) nvo[(size_t)w * nz + i] = NAN; }
         if (lane == 0) {
@@ -572,13 +575,15 @@ dyn_backward_kernel(const double* __restrict__ p, const double* __restrict__ v, 
                     const double* __restrict__ gnv,
                     double* __restrict__ gp, double* __restrict__ gv, double* __restrict__ gmass, double* __restrict__ gI,
                     double* __restrict__ gfric, double* __restrict__ grest, double* __restrict__ gf,
-                    double* __restrict__ gdt, double* __restrict__ ggeo) {
+                    double* __restrict__ gdt, double* __restrict__ ggeo, int cmin, int last_class) {
     extern __shared__ double smd[];
     const int w = blockIdx.x, lane = threadIdx.x & 31;
     const DynSmem L = dyn_layout(nb, neq, C, fd);
     DynCtx c = dyn_ctx(smd, L);
     const int nz = L.nz, nq = L.nq, per = L.per, niCap = maxc * per;
     const bool masked = active && !active[w];
+    // contact-count classes (see dyn_forward_kernel): masked worlds are written by the first-class launch only
+    if (masked ? cmin >= 0 : (count[w] <= cmin || (count[w] > C && !last_class))) return;
     const bool on = !masked && count[w] <= C;
     if (!on) {
         for (int i = lane; i < nb * 7; i += 32) gp[(size_t)w * nb * 7 + i] = 0.0;
@@ -725,7 +730,7 @@ int dsdf_dynamics_solve_loop(const double* p, const double* v, const double* mas
                              const int32_t* eq_rows, int W, int nb, int neq, int maxc, int ncontacts_smem, int fric_dirs,
                              double eps, int not_improved_lim, int max_iter,
                              double* x, double* new_v, double* nu, double* lam, double* s, int32_t* status, int32_t* iters,
-                             const int32_t* vmap, int32_t* ctrl, void* stream) {
+                             const int32_t* vmap, int32_t* ctrl, int count_min, int last_class, void* stream) {
     size_t smem;
     int C = ncontacts_smem;
     int rc = dyn_check(W, nb, neq, maxc, &C, fric_dirs, &smem);
@@ -735,7 +740,7 @@ int dsdf_dynamics_solve_loop(const double* p, const double* v, const double* mas
     dyn_forward_kernel<<<W, 32, smem, (cudaStream_t)stream>>>(p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody,
                                                               cgeo, eq_rows, nb, neq, maxc, C, fric_dirs, eps,
                                                               not_improved_lim, max_iter, x, new_v, nu, lam, s, status, iters,
-                                                              vmap, ctrl);
+                                                              vmap, ctrl, count_min, last_class);
     return (int)cudaGetLastError();
 }
 
@@ -748,7 +753,29 @@ int dsdf_dynamics_solve(const double* p, const double* v, const double* mass, co
                         void* stream) {
     return dsdf_dynamics_solve_loop(p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody, cgeo, eq_rows, W, nb, neq,
                                     maxc, ncontacts_smem, fric_dirs, eps, not_improved_lim, max_iter, x, new_v, nu, lam, s,
-                                    status, iters, nullptr, nullptr, stream);
+                                    status, iters, nullptr, nullptr, -1, 1, stream);
+}
+
+int dsdf_dynamics_solve_backward_loop(const double* p, const double* v, const double* mass, const double* Ibody,
+                                      const double* fric, const double* rest, const double* f, const double* dt,
+                                      const unsigned char* active, const int32_t* count, const int32_t* cbody,
+                                      const double* cgeo, const int32_t* eq_rows, int W, int nb, int neq, int maxc,
+                                      int ncontacts_smem, int fric_dirs, int stop_contact_grad, int stop_friction_grad,
+                                      const double* x, const double* lam, const double* s, const double* g_new_v,
+                                      double* gp, double* gv, double* gmass, double* gI, double* gfric, double* grest,
+                                      double* gf, double* gdt, double* ggeo, int count_min, int last_class, void* stream) {
+    size_t smem;
+    int C = ncontacts_smem;
+    int rc = dyn_check(W, nb, neq, maxc, &C, fric_dirs, &smem);
+    if (rc) return rc;
+    cudaError_t e = ensure_smem(dyn_backward_kernel, smem, &g_bwd_smem);
+    if (e != cudaSuccess) return (int)e;
+    dyn_backward_kernel<<<W, 32, smem, (cudaStream_t)stream>>>(p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody,
+                                                               cgeo, eq_rows, nb, neq, maxc, C, fric_dirs,
+                                                               stop_contact_grad, stop_friction_grad, x, lam, s, g_new_v, gp,
+                                                               gv, gmass, gI, gfric, grest, gf, gdt, ggeo, count_min,
+                                                               last_class);
+    return (int)cudaGetLastError();
 }
 
 int dsdf_dynamics_solve_backward(const double* p, const double* v, const double* mass, const double* Ibody,
@@ -759,17 +786,10 @@ int dsdf_dynamics_solve_backward(const double* p, const double* v, const double*
                                  const double* x, const double* lam, const double* s, const double* g_new_v,
                                  double* gp, double* gv, double* gmass, double* gI, double* gfric, double* grest,
                                  double* gf, double* gdt, double* ggeo, void* stream) {
-    size_t smem;
-    int C = ncontacts_smem;
-    int rc = dyn_check(W, nb, neq, maxc, &C, fric_dirs, &smem);
-    if (rc) return rc;
-    cudaError_t e = ensure_smem(dyn_backward_kernel, smem, &g_bwd_smem);
-    if (e != cudaSuccess) return (int)e;
-    dyn_backward_kernel<<<W, 32, smem, (cudaStream_t)stream>>>(p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody,
-                                                               cgeo, eq_rows, nb, neq, maxc, C, fric_dirs,
-                                                               stop_contact_grad, stop_friction_grad, x, lam, s, g_new_v, gp,
-                                                               gv, gmass, gI, gfric, grest, gf, gdt, ggeo);
-    return (int)cudaGetLastError();
+    return dsdf_dynamics_solve_backward_loop(p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody, cgeo, eq_rows, W,
+                                             nb, neq, maxc, ncontacts_smem, fric_dirs, stop_contact_grad,
+                                             stop_friction_grad, x, lam, s, g_new_v, gp, gv, gmass, gI, gfric, grest, gf,
+                                             gdt, ggeo, -1, 1, stream);
 }
 
 }  // extern "C"

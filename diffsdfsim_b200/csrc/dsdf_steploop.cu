@@ -36,6 +36,8 @@ step_begin_kernel(const __grid_constant__ Args a) {
         int* c = a.ctrl;
         c[CT_ABORT] = 0; c[CT_NACT] = (int)a.W; c[CT_CURSOR] = 0; c[CT_ROUNDS] = 0; c[CT_MAXNSUB] = 0; c[CT_DEFF] = 1;
         c[CT_NNEXT] = 0; c[CT_ANYTOC] = 0; c[CT_LCPSTAT] = 0; c[CT_NVIRT] = 0; c[CT_PENDING] = 0; c[CT_TICKET] = 0;
+        for (int k = 0; k < DSDF_STEP_MAX_SLOTS; ++k) c[CT_SLOTROWS + k] = 0;
+        c[CT_SLOTROWS] = (int)a.W;
     }
     if (w >= a.W) return;
     a.active[w] = 1;
@@ -111,7 +113,16 @@ step_commit_kernel(const __grid_constant__ Args a) {
             if (acc && win < 0) win = d;
         }
         const int k = a.nsub[w];
-        if (!pause && win >= 0 && k >= a.n_slots) pause |= DSDF_STEP_TAPE;
+        // tape row of this sub-step: slot 0 is indexed by world, later slots hand out rows in commit order
+        int row = w;
+        if (!pause && win >= 0) {
+            if (k >= a.n_slots) pause |= DSDF_STEP_TAPE;
+            else if (k > 0) {
+                if (lane == 0) row = atomicAdd(&c[CT_SLOTROWS + k], 1);
+                row = __shfl_sync(0xffffffffu, row, 0);
+                if (row >= a.slots[k].cap) pause |= DSDF_STEP_TAPE;      // the host clamps the counter before resuming
+            }
+        }
         if (pause) {
             if (lane == 0) { atomicOr(&c[CT_PENDING], pause); atomicAdd(&c[CT_NNEXT], 1); }
         } else if (win < 0) {                                   // every attempt of this round rejected: go on halving
@@ -125,6 +136,7 @@ step_commit_kernel(const __grid_constant__ Args a) {
         } else {
             const int vv = win * n + i;
             const dsdf_step_slot& S = a.slots[k];
+            const size_t r = (size_t)row;
             const int st = a.status_v[vv];
             const bool clean = !(st & DSDF_CON_PENETRATION);
             const int cn = min(a.count_v[vv], maxc), co = min(a.count[w], maxc);
@@ -142,54 +154,59 @@ step_commit_kernel(const __grid_constant__ Args a) {
                     }
                     m = seen ? 0 : 1;
                 }
-                S.toc_mask[(size_t)w * maxc + kk] = m;
+                S.toc_mask[r * maxc + kk] = m;
                 any_toc |= m;
             }
             any_toc = __any_sync(0xffffffffu, any_toc);
+            // the contacts the solve used (the current set, about to be replaced)
+            for (int e = lane; e < co * 2; e += 32) S.body_in[r * maxc * 2 + e] = a.body[(size_t)w * maxc * 2 + e];
+            for (int e = lane; e < co * 10; e += 32) S.geo_in[r * maxc * 10 + e] = a.geo[(size_t)w * maxc * 10 + e];
             __syncwarp();
             // tape + state
             for (int e = lane; e < nb * 7; e += 32) {
                 const size_t o = (size_t)w * nb * 7 + e;
                 const double pt = a.p_try_v[(size_t)vv * nb * 7 + e];
-                S.p_in[o] = a.p[o];
-                S.p_try[o] = pt;
+                S.p_in[r * nb * 7 + e] = a.p[o];
+                S.p_try[r * nb * 7 + e] = pt;
                 a.p[o] = pt;          // H.forward is the identity on dt (world.py:147), so the redone move gives p_try again
             }
             for (int e = lane; e < nz; e += 32) {
                 const size_t o = (size_t)w * nz + e;
                 const double nv = a.new_v_v[(size_t)vv * nz + e];
-                S.v_in[o] = a.v[o];
-                S.x[o] = a.x_v[(size_t)vv * nz + e];
-                S.new_v[o] = nv;
+                S.v_in[r * nz + e] = a.v[o];
+                S.x[r * nz + e] = a.x_v[(size_t)vv * nz + e];
+                S.new_v[r * nz + e] = nv;
                 a.v[o] = nv;
             }
             for (int e = lane; e < co * per; e += 32) {          // multipliers of the contacts the solve used
-                S.lam[(size_t)w * niCap + e] = a.lam_v[(size_t)vv * niCap + e];
-                S.s[(size_t)w * niCap + e] = a.s_v[(size_t)vv * niCap + e];
+                S.lam[r * niCap + e] = a.lam_v[(size_t)vv * niCap + e];
+                S.s[r * niCap + e] = a.s_v[(size_t)vv * niCap + e];
             }
-            // the contact set found at the end of this sub-step: tape slot and current set
+            // the contact set found at the end of this sub-step: tape row and current set
             for (int e = lane; e < cn * 2; e += 32) {
                 const int bv = a.body_v[(size_t)vv * maxc * 2 + e];
-                S.body[(size_t)w * maxc * 2 + e] = bv; a.body[(size_t)w * maxc * 2 + e] = bv;
+                S.body[r * maxc * 2 + e] = bv; a.body[(size_t)w * maxc * 2 + e] = bv;
             }
             for (int e = lane; e < cn; e += 32) {
                 const int fv = a.face_v[(size_t)vv * maxc + e];
-                S.face[(size_t)w * maxc + e] = fv; a.face[(size_t)w * maxc + e] = fv;
+                S.face[r * maxc + e] = fv; a.face[(size_t)w * maxc + e] = fv;
             }
             for (int e = lane; e < cn * 3; e += 32) {
                 const double av = a.abc_v[(size_t)vv * maxc * 3 + e];
-                S.abc[(size_t)w * maxc * 3 + e] = av; a.abc[(size_t)w * maxc * 3 + e] = av;
+                S.abc[r * maxc * 3 + e] = av; a.abc[(size_t)w * maxc * 3 + e] = av;
             }
             for (int e = lane; e < cn * 10; e += 32) {
                 const double gv = a.geo_v[(size_t)vv * maxc * 10 + e];
-                S.geo[(size_t)w * maxc * 10 + e] = gv; a.geo[(size_t)w * maxc * 10 + e] = gv;
+                S.geo[r * maxc * 10 + e] = gv; a.geo[(size_t)w * maxc * 10 + e] = gv;
             }
             if (lane == 0) {
                 const double dtr = a.dt_raw_v[vv], dtu = a.dt_used_v[vv];
-                S.count[w] = a.count_v[vv]; a.count[w] = a.count_v[vv]; a.status[w] = st;
-                S.dt_raw[w] = dtr; S.dt_used[w] = dtu;
-                S.toc_flag_in[w] = a.toc_flag[w];
-                S.toc_now[w] = (unsigned char)any_toc;
+                S.world[r] = w;
+                S.count_in[r] = a.count[w];
+                S.count[r] = a.count_v[vv]; a.count[w] = a.count_v[vv]; a.status[w] = st;
+                S.dt_raw[r] = dtr; S.dt_used[r] = dtu;
+                S.toc_flag_in[r] = a.toc_flag[w];
+                S.toc_now[r] = (unsigned char)any_toc;
                 if (a.toc_enabled && clean) a.toc_flag[w] = (unsigned char)any_toc;   // a give-up accept leaves the flag untouched
                 if (any_toc) { a.last_dt[w] = dtu; c[CT_ANYTOC] = 1; }               // world.py:341 (value of H(dt_) = dt_)
                 const double tn = a.t[w] + dtr;
@@ -203,6 +220,7 @@ step_commit_kernel(const __grid_constant__ Args a) {
                 else a.active[w] = 0;
                 atomicMax(&c[CT_MAXNSUB], k + 1);
                 atomicMax(&c[CT_MAXCOUNT], cn);
+                if (clean) atomicMax(&c[CT_MAXCLEAN], cn);
                 const int ls = a.lcp_status_v[vv];
                 if (ls) atomicOr(&c[CT_LCPSTAT], ls);
             }
@@ -259,17 +277,28 @@ int dsdf_step_resume(const dsdf_step_args* a, void* stream) {
     return (int)cudaGetLastError();
 }
 
-int dsdf_step_rounds(const dsdf_step_args* a, int n_rounds, int ncontacts_smem, void* stream) {
-    if (step_check(a) || n_rounds < 0) return -1;
+int dsdf_step_rounds(const dsdf_step_args* a, int n_rounds, int ncontacts_small, int ncontacts_large, void* stream) {
+    if (step_check(a) || n_rounds < 0 || ncontacts_small <= 0) return -1;
     cudaStream_t st = (cudaStream_t)stream;
     const int W = (int)a->W, nb = (int)a->nb, V = (int)a->vcap;
     for (int r = 0; r < n_rounds; ++r) {
         step_prep_kernel<<<(W + 255) / 256, 256, 0, st>>>(*a);
+        // two contact-count classes: worlds with <= ncontacts_small contacts, and (if any) the rest
+        const bool two = ncontacts_large > ncontacts_small;
         int rc = dsdf_dynamics_solve_loop(a->p, a->v, a->mass, a->Ibody, a->fric, a->rest, a->f, a->dt_used_v, nullptr,
                                           a->count, a->body, a->geo, a->eq_rows, V, nb, (int)a->neq, (int)a->maxc,
-                                          ncontacts_smem, (int)a->fric_dirs, 1e-12, 3, (int)a->max_iter, a->x_v, a->new_v_v,
-                                          a->nu_v, a->lam_v, a->s_v, a->lcp_status_v, a->iters_v, a->vmap, a->ctrl, stream);
+                                          ncontacts_small, (int)a->fric_dirs, 1e-12, 3, (int)a->max_iter, a->x_v, a->new_v_v,
+                                          a->nu_v, a->lam_v, a->s_v, a->lcp_status_v, a->iters_v, a->vmap, a->ctrl, -1,
+                                          two ? 0 : 1, stream);
         if (rc) return rc;
+        if (two) {
+            rc = dsdf_dynamics_solve_loop(a->p, a->v, a->mass, a->Ibody, a->fric, a->rest, a->f, a->dt_used_v, nullptr,
+                                          a->count, a->body, a->geo, a->eq_rows, V, nb, (int)a->neq, (int)a->maxc,
+                                          ncontacts_large, (int)a->fric_dirs, 1e-12, 3, (int)a->max_iter, a->x_v,
+                                          a->new_v_v, a->nu_v, a->lam_v, a->s_v, a->lcp_status_v, a->iters_v, a->vmap,
+                                          a->ctrl, ncontacts_small, 1, stream);
+            if (rc) return rc;
+        }
         step_integrate_kernel<<<(V * nb + 127) / 128, 128, 0, st>>>(*a);
         rc = dsdf_contacts_detect_loop(a->geom, a->pairs, (int)a->npairs, a->p_try_v, a->shape, nullptr, V, nb, a->eps,
                                        a->tol, a->fd_eps, a->body_eps, (int)a->detach_b2, (int)a->capK, (int)a->maxc,

@@ -17,7 +17,9 @@ enum {
     CT_NVIRT,         // virtual worlds of the current round = CT_NACT * CT_DEFF
     CT_PENDING,       // pause bits collected by the commit kernel, promoted to CT_ABORT by its last CTA
     CT_TICKET,        // "last CTA done" ticket of the commit kernel
-    CT_WORDS = 16
+    CT_MAXCLEAN,      // running max of the accepted contact counts of NON-penetrating states
+    CT_SLOTROWS = 16, // + k: rows handed out in tape slot k (k >= 1; slot 0 is indexed by world)
+    CT_WORDS = 16 + 64
 };
 // true when this launch has nothing to do (a previous kernel asked the host for help, or every world is done)
 __device__ __forceinline__ bool loop_idle(const int* ctrl) { return ctrl[CT_ABORT] != 0 || ctrl[CT_NACT] == 0; }

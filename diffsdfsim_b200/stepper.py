@@ -12,6 +12,7 @@
   the state before retrying).
 """
 import ctypes
+import time
 
 import torch
 
@@ -23,13 +24,14 @@ U8 = torch.uint8
 I32 = torch.int32
 BASE_TOL = 1e-6      # lcp_physics/physics/utils.py:43 (World.H.backward, world.py:204)
 
-MAX_SLOTS = 16
+MAX_SLOTS = 64
 STEP_CAPK, STEP_MAXC, STEP_DYN_SMEM, STEP_TAPE, STEP_MAX_ROUNDS = 1, 2, 4, 8, 16
-CT_ABORT, CT_NACT, CT_MAXCOUNT, CT_ROUNDS, CT_MAXNSUB, CT_ANYTOC, CT_LCPSTAT = 0, 1, 3, 4, 5, 8, 9
+CT_ABORT, CT_NACT, CT_MAXCOUNT, CT_ROUNDS, CT_MAXNSUB, CT_ANYTOC, CT_LCPSTAT, CT_MAXCLEAN = 0, 1, 3, 4, 5, 8, 9, 13
+CT_SLOTROWS, CT_WORDS = 16, 16 + MAX_SLOTS
 LCP_FACTOR_FAIL, LCP_INACCURATE, LCP_TOO_LARGE = 4, 8, 16
 
-_SLOT_FIELDS = ['p_in', 'v_in', 'x', 'new_v', 'p_try', 'dt_raw', 'dt_used', 'lam', 's', 'toc_flag_in', 'toc_now',
-                'toc_mask', 'count', 'body', 'face', 'abc', 'geo']
+_SLOT_FIELDS = ['world', 'p_in', 'v_in', 'x', 'new_v', 'p_try', 'dt_raw', 'dt_used', 'lam', 's', 'toc_flag_in', 'toc_now',
+                'toc_mask', 'count_in', 'body_in', 'geo_in', 'count', 'body', 'face', 'abc', 'geo']
 _INT_FIELDS = ['W', 'nb', 'neq', 'maxc', 'fric_dirs', 'capK', 'npairs', 'depth', 'spec_threshold', 'vcap', 'n_slots',
                'max_iter', 'max_rounds', 'strict', 'toc_enabled', 'fixed_dt', 'detach_b2']
 _DBL_FIELDS = ['world_dt', 'eps', 'tol', 'fd_eps', 'body_eps']
@@ -43,13 +45,13 @@ _PTR_FIELDS = ['geom', 'pairs', 'eq_rows', 'mass', 'Ibody', 'fric', 'rest', 'f',
 
 class StepSlot(ctypes.Structure):
     """dsdf_step_slot (include/dsdf_b200.h)."""
-    _fields_ = [(n, ctypes.c_void_p) for n in _SLOT_FIELDS]
+    _fields_ = [('cap', ctypes.c_int64)] + [(n, ctypes.c_void_p) for n in _SLOT_FIELDS]
 
 
 class StepArgs(ctypes.Structure):
     """dsdf_step_args (include/dsdf_b200.h): every field 8 bytes wide, same order."""
     _fields_ = ([(n, ctypes.c_int64) for n in _INT_FIELDS] + [(n, ctypes.c_double) for n in _DBL_FIELDS]
-                + [(n, ctypes.c_void_p) for n in _PTR_FIELDS] + [('slots', StepSlot * MAX_SLOTS)])
+                + [(n, ctypes.c_void_p) for n in _PTR_FIELDS] + [('slots', ctypes.c_void_p)])
 
 
 def _ptr(t):
@@ -57,48 +59,113 @@ def _ptr(t):
 
 
 class TapeSlot:
-    """Device buffers of one dsdf_step_slot."""
+    """Device buffers of one dsdf_step_slot: ``cap`` self-contained rows (one accepted sub-step of one world each)."""
+    F64_FIELDS = dict(p_in=('nb', 7), v_in=('nb', 6), p_try=('nb', 7), x=('nz',), new_v=('nb', 6), dt_raw=(), dt_used=(),
+                      lam=('ni',), s=('ni',), geo_in=('maxc', 10), abc=('maxc', 3), geo=('maxc', 10))
+    I32_FIELDS = dict(world=(), count_in=(), body_in=('maxc', 2), count=(), body=('maxc', 2), face=('maxc',))
+    U8_FIELDS = dict(toc_flag_in=(), toc_now=(), toc_mask=('maxc',))
 
-    def __init__(self, W, nb, maxc, per, dev):
-        e = lambda *s: torch.empty(*s, dtype=F64, device=dev)
-        self.p_in, self.v_in, self.p_try = e(W, nb, 7), e(W, nb, 6), e(W, nb, 7)
-        self.x, self.new_v = e(W, 6 * nb), e(W, nb, 6)
-        self.dt_raw, self.dt_used = torch.zeros(W, dtype=F64, device=dev), torch.zeros(W, dtype=F64, device=dev)
-        self.lam, self.s = e(W, maxc * per), e(W, maxc * per)
-        self.toc_flag_in = torch.zeros(W, dtype=U8, device=dev)
-        self.toc_now = torch.zeros(W, dtype=U8, device=dev)
-        self.toc_mask = torch.zeros(W, maxc, dtype=U8, device=dev)
-        self.cs = ContactSet(W, maxc, dev)           # zero-filled: count = 0 for worlds that never reach this slot
+    def __init__(self, cap, nb, maxc, per, dev):
+        self.cap, self.nb, self.maxc, self.per, self.dev = int(cap), nb, maxc, per, dev
+        self.rows = 0                                   # rows in use (set from the control block after the step)
+        dims = dict(nb=nb, nz=6 * nb, ni=maxc * per, maxc=maxc)
+        for fields, dt in ((self.F64_FIELDS, F64), (self.I32_FIELDS, I32), (self.U8_FIELDS, U8)):
+            for name, shape in fields.items():
+                setattr(self, name, torch.empty((self.cap,) + tuple(dims.get(d, d) for d in shape), dtype=dt, device=dev))
+        self.nbytes = sum(getattr(self, n).numel() * getattr(self, n).element_size()
+                          for n in list(self.F64_FIELDS) + list(self.I32_FIELDS) + list(self.U8_FIELDS))
 
-    def regrown(self, maxc, per):
-        """The same records with room for ``maxc`` contacts per world."""
-        W, nb, dev, old = self.p_in.shape[0], self.p_in.shape[1], self.p_in.device, self.toc_mask.shape[1]
-        n = TapeSlot.__new__(TapeSlot)
-        n.__dict__.update(self.__dict__)
-        n.lam, n.s = (torch.empty(W, maxc * per, dtype=F64, device=dev) for _ in range(2))
-        n.lam[:, :old * per], n.s[:, :old * per] = self.lam, self.s
-        n.toc_mask = torch.zeros(W, maxc, dtype=U8, device=dev)
-        n.toc_mask[:, :old] = self.toc_mask
-        n.cs = self.cs.resized(maxc)
+    def regrown(self, cap, maxc):
+        """The same rows in a slot with room for ``cap`` rows of ``maxc`` contacts."""
+        n = acquire_slot(cap, self.nb, maxc, self.per, self.dev)
+        r, m, per = min(self.cap, cap), self.maxc, self.per
+        for name in list(self.F64_FIELDS) + list(self.I32_FIELDS) + list(self.U8_FIELDS):
+            src, dst = getattr(self, name), getattr(n, name)
+            if name in ('lam', 's'):
+                dst[:r, :m * per] = src[:r]
+            elif src.dim() >= 2 and src.shape[1] == m and name not in ('p_in', 'v_in', 'p_try', 'x', 'new_v'):
+                dst[:r, :m] = src[:r]
+            else:
+                dst[:r] = src[:r]
+        if maxc != m:
+            n.toc_mask[:r, m:] = 0
+        n.rows = self.rows
+        release_slot(self)
         return n
 
     def fill(self, c_slot):
-        for k in ('p_in', 'v_in', 'x', 'new_v', 'p_try', 'dt_raw', 'dt_used', 'lam', 's', 'toc_flag_in', 'toc_now',
-                  'toc_mask'):
+        c_slot.cap = self.cap
+        for k in _SLOT_FIELDS:
             setattr(c_slot, k, _ptr(getattr(self, k)))
-        for k in ('count', 'body', 'face', 'abc', 'geo'):
-            setattr(c_slot, k, _ptr(getattr(self.cs, k)))
+
+    def view(self, n):
+        """The first n rows as a namespace of tensors (what the reverse sweep of this slot reads)."""
+        v = _Rows()
+        for name in list(self.F64_FIELDS) + list(self.I32_FIELDS) + list(self.U8_FIELDS):
+            setattr(v, name, getattr(self, name)[:n])
+        v.maxc = self.maxc
+        return v
+
+
+class _Rows:
+    pass
+
+
+def _pow2(n):
+    return 1 << max(0, int(n) - 1).bit_length()
+
+
+# Tape slots are recycled: a rollout allocates tens of them per step and frees them all after backward; handing the
+# whole group of buffers back and forth costs nothing, whereas the caching allocator fragments on their varying sizes
+# (cudaMalloc in steady state).  Keyed by everything that determines the buffer shapes.
+_SLOT_POOL = {}
+_SLOT_POOL_MAX_BYTES = 48 << 30
+_slot_pool_bytes = 0
+
+
+def acquire_slot(cap, nb, maxc, per, dev):
+    global _slot_pool_bytes
+    key = (int(cap), nb, maxc, per, str(dev))
+    free = _SLOT_POOL.get(key)
+    if free:
+        sl = free.pop()
+        _slot_pool_bytes -= sl.nbytes
+        sl.rows = 0
+        return sl
+    return TapeSlot(cap, nb, maxc, per, dev)
+
+
+def release_slot(sl):
+    global _slot_pool_bytes
+    if _slot_pool_bytes + sl.nbytes > _SLOT_POOL_MAX_BYTES:
+        return
+    _SLOT_POOL.setdefault((sl.cap, sl.nb, sl.maxc, sl.per, str(sl.dev)), []).append(sl)
+    _slot_pool_bytes += sl.nbytes
 
 
 class Tape:
     """Everything one step leaves behind for its reverse sweep."""
-    __slots__ = ('start', 'slots', 'nsub', 'maxsub', 'any_toc', 'maxc', 'C', 'rounds', 'p_out', 'v_out', 'geo_out',
+    __slots__ = ('slots', 'maxsub', 'any_toc', 'maxc', 'C', 'rounds', 'p_out', 'v_out', 'geo_out',
                  'last_dt_out', 'had', 'final', 'f', 'syncs')
+
+    def __del__(self):
+        for sl in getattr(self, 'slots', None) or []:
+            release_slot(sl)
+
+
+_ROWS_HISTORY = {}       # (W, nb, fric_dirs, device) -> high-water mark of the rows used per tape slot
 
 
 class DeviceStepper:
     """Owns the per-world work buffers of the step loop of one ``World3D`` and launches its rounds."""
     INITIAL_SLOTS = 2
+    TIMING = None           # set to {} to accumulate host wall-clock seconds per phase of run() (diagnostics)
+
+    @classmethod
+    def _tick(cls, name, t0):
+        if cls.TIMING is not None:
+            cls.TIMING[name] = cls.TIMING.get(name, 0.0) + time.perf_counter() - t0
+        return time.perf_counter()
 
     def __init__(self, world):
         _lib.lib()
@@ -107,8 +174,9 @@ class DeviceStepper:
         self.depth = world.SPEC_DEPTH if world.speculate else 1
         self.spec_threshold = W // 8 if (world.speculate and W >= 64) else 0
         self.vcap = max(W, self.depth * self.spec_threshold)
-        self.ctrl = torch.zeros(16, dtype=I32, device=dev)
-        self.ctrl_host = torch.zeros(16, dtype=I32).pin_memory()
+        self.ctrl = torch.zeros(CT_WORDS, dtype=I32, device=dev)
+        self.ctrl_host = torch.zeros(CT_WORDS, dtype=I32).pin_memory()
+        self.slot_table = torch.zeros(MAX_SLOTS * ctypes.sizeof(StepSlot), dtype=U8, device=dev)
         self.dt_try = torch.zeros(W, dtype=F64, device=dev)
         self.end_t = torch.zeros(W, dtype=F64, device=dev)
         self.active = torch.zeros(W, dtype=U8, device=dev)
@@ -116,7 +184,8 @@ class DeviceStepper:
         self.vidx = torch.zeros(W, dtype=I32, device=dev)
         self.maxc = None
         self.last_rounds = 1
-        self.max_count = 0
+        self.max_count = 0          # largest accepted contact count so far (any state)
+        self.max_clean = 0          # ... of non-penetrating states: what the bulk of the worlds look like
         self.launches = 0
         self._alloc_virtual(world)
 
@@ -161,14 +230,35 @@ class DeviceStepper:
         a.count_v, a.status_v, a.body_v, a.face_v, a.abc_v, a.geo_v = (_ptr(v.count), _ptr(v.status), _ptr(v.body),
                                                                        _ptr(v.face), _ptr(v.abc), _ptr(v.geo))
         a.ctrl = _ptr(self.ctrl)
+        # the slot table lives in device memory (no limit from the kernel-parameter space); uploaded when it changes
+        table = (StepSlot * len(tape.slots))()
         for k, s in enumerate(tape.slots):
-            s.fill(a.slots[k])
+            s.fill(table[k])
+        raw = torch.frombuffer(bytearray(bytes(table)), dtype=U8)
+        self.slot_table[:raw.numel()].copy_(raw)
+        a.slots = _ptr(self.slot_table)
         return a
 
     def _smem_contacts(self, world):
-        """Contacts the dynamics kernel sizes its shared memory for: the largest accepted count so far + slack."""
-        c = (self.max_count + 2 + 3) // 4 * 4
-        return max(4, min(c, world.maxc, 64))
+        """Contacts the dynamics kernel sizes its shared memory for, as two classes (small, large): the bulk of the
+        worlds (largest non-penetrating count so far + slack) and, if there are any, the few worlds that carry many more
+        (a world that gave up halving keeps a penetrating state with dozens of contacts)."""
+        cap = min(world.maxc, 64)
+        r4 = lambda c: max(4, min((c + 2 + 3) // 4 * 4, cap))
+        small, large = r4(self.max_clean), r4(self.max_count)
+        return small, (large if large > small else small)
+
+    def _hist_key(self, world):
+        return (self.W, self.nb, world.fric_dirs, str(self.dev))
+
+    def _slot_cap(self, k, hist=()):
+        """Rows to allocate for tape slot k: every world reaches slot 0; later slots hold the high-water mark of earlier
+        steps of worlds of this size (rollouts are repeated every optimisation iteration), rounded up to a power of two
+        so that recycled slots fit."""
+        if k == 0:
+            return self.W
+        seen = hist[k] if k < len(hist) else 0
+        return min(self.W, _pow2(max(64, seen + seen // 4)))
 
     def _read_ctrl(self):
         self.ctrl_host.copy_(self.ctrl, non_blocking=True)
@@ -181,27 +271,37 @@ class DeviceStepper:
         per = 2 + world.fric_dirs
         if self.maxc != world.maxc:
             self._alloc_virtual(world)
-        self.max_count = max(self.max_count, int(world.max_nc))
+        if self.max_count == 0:                             # the contacts World3D.__init__ found (a legal, clean state)
+            self.max_clean = int(world.max_nc)
+        self.max_count = max(self.max_count, self.max_clean, int(world.max_nc))
+        t0 = time.perf_counter()
         tape = Tape()
-        tape.start = world.contact_set                      # immutable from here on (the loop works on a clone)
-        tape.slots = [TapeSlot(W, nb, world.maxc, per, dev) for _ in range(self.INITIAL_SLOTS)]
+        hist = _ROWS_HISTORY.get(self._hist_key(world), [])
+        tape.slots = [acquire_slot(self._slot_cap(k, hist), nb, world.maxc, per, dev)
+                      for k in range(max(self.INITIAL_SLOTS, len(hist)))]
         tape.f = f
+        t0 = self._tick('slots', t0)
         st = dict(p=p.detach().clone(), v=v.detach().clone(), t=world.t.clone(), last_dt=last_dt.detach().clone(),
                   toc_flag=world.toc_flag.clone(), had=torch.zeros(W, dtype=U8, device=dev),
                   cur=world.contact_set.clone(), mass=mass, Ibody=Ibody, fric=fric, rest=rest)
         st['cur'].pre_ids = st['cur'].pre_cnt = None
         stream = _lib.stream()
+        t0 = self._tick('state', t0)
         args = self._args(world, fixed_dt, st, tape, f)
+        t0 = self._tick('args', t0)
         _lib.check(_lib.call('dsdf_step_begin', ctypes.byref(args), stream), 'dsdf_step_begin')
         burst = min(max(2, self.last_rounds + 1), 24)
         syncs = 0
         while True:
-            rc = _lib.call('dsdf_step_rounds', ctypes.byref(args), burst, self._smem_contacts(world), stream)
+            rc = _lib.call('dsdf_step_rounds', ctypes.byref(args), burst, *self._smem_contacts(world), stream)
             _lib.check(rc, 'dsdf_step_rounds')
             self.launches += 5 * burst
+            t0 = self._tick('launch', t0)
             c = self._read_ctrl()
+            t0 = self._tick('sync', t0)
             syncs += 1
             self.max_count = max(self.max_count, c[CT_MAXCOUNT])
+            self.max_clean = max(self.max_clean, c[CT_MAXCLEAN])
             ab = c[CT_ABORT]
             if ab & STEP_MAX_ROUNDS:
                 stuck = self.active.nonzero().flatten().tolist()[:8]
@@ -209,9 +309,10 @@ class DeviceStepper:
                                    'use strict_no_penetration=False or a smaller dt'
                                    % (world.max_rounds_per_step, stuck, float(self.dt_try.min())))
             if ab:
-                self._grow(world, ab, tape, st, per)
+                self._grow(world, ab, tape, st, per, c)
                 args = self._args(world, fixed_dt, st, tape, f)
                 _lib.check(_lib.call('dsdf_step_resume', ctypes.byref(args), stream), 'dsdf_step_resume')
+                t0 = self._tick('grow', t0)
                 continue
             if c[CT_NACT] == 0:
                 break
@@ -223,16 +324,26 @@ class DeviceStepper:
         world.engine.last_status_bits = ls
         if ls & LCP_INACCURATE and getattr(world.engine, 'verbose', -1) >= 0:
             print('qpth warning: Returning an inaccurate and potentially incorrect solution.')       # batch.py:165,229
-        tape.nsub, tape.maxsub, tape.any_toc = self.nsub.clone(), c[CT_MAXNSUB], bool(c[CT_ANYTOC])
+        tape.maxsub, tape.any_toc = c[CT_MAXNSUB], bool(c[CT_ANYTOC])
         tape.maxc, tape.C, tape.rounds, tape.syncs = world.maxc, self._smem_contacts(world), c[CT_ROUNDS], syncs
         tape.p_out, tape.v_out, tape.last_dt_out, tape.had = st['p'], st['v'], st['last_dt'], st['had'].bool()
         tape.final = st['cur']
         tape.geo_out = st['cur'].geo.clone()
         world.t, world.toc_flag = st['t'], st['toc_flag']
+        for sl in tape.slots[max(tape.maxsub, 0):]:
+            release_slot(sl)
         del tape.slots[max(tape.maxsub, 0):]
+        for k, sl in enumerate(tape.slots):
+            sl.rows = min(c[CT_SLOTROWS + k], sl.cap)
+        hist = _ROWS_HISTORY.setdefault(self._hist_key(world), [])
+        for k, sl in enumerate(tape.slots):
+            if k >= len(hist):
+                hist.append(sl.rows)
+            hist[k] = max(hist[k], sl.rows)
+        self._tick('finish', t0)
         return tape
 
-    def _grow(self, world, bits, tape, st, per):
+    def _grow(self, world, bits, tape, st, per, c):
         """Enlarge what the paused worlds ran out of (the worlds themselves are untouched and still active)."""
         if bits & STEP_CAPK:
             capK = world.detector.capK
@@ -247,14 +358,26 @@ class DeviceStepper:
             new = min(world.MAX_MAXC, 2 * maxc)
             world._set_capacity(world.detector.capK, new)
             st['cur'] = st['cur'].resized(new)
-            tape.start = tape.start.resized(new)
-            tape.slots = [s.regrown(new, per) for s in tape.slots]
+            tape.slots = [sl.regrown(sl.cap, new) for sl in tape.slots]
             self._alloc_virtual(world)
         if bits & STEP_TAPE:
-            if len(tape.slots) >= MAX_SLOTS:
-                raise RuntimeError('a world accepted more than %d sub-steps inside one step' % MAX_SLOTS)
-            n = min(MAX_SLOTS, 2 * len(tape.slots))
-            tape.slots += [TapeSlot(self.W, self.nb, world.maxc, per, self.dev) for _ in range(n - len(tape.slots))]
+            # a paused world found its slot missing or full: double the full slots (their row counters overshot by the
+            # number of paused worlds: clamp them), and add slots up to the deepest sub-step index seen + 1
+            rows = list(c[CT_SLOTROWS:CT_SLOTROWS + MAX_SLOTS])
+            for k, sl in enumerate(tape.slots):
+                if k > 0 and rows[k] > sl.cap:
+                    if sl.cap >= self.W:
+                        raise RuntimeError('tape slot %d holds every world and is still full' % k)
+                    # rows[k] worlds asked for a row so far: make room for them and as many again
+                    tape.slots[k] = sl.regrown(min(self.W, _pow2(2 * rows[k])), world.maxc)
+                    rows[k] = sl.cap
+            self.ctrl[CT_SLOTROWS:CT_SLOTROWS + MAX_SLOTS].copy_(torch.tensor(rows, dtype=I32), non_blocking=False)
+            if c[CT_MAXNSUB] >= len(tape.slots):
+                if len(tape.slots) >= MAX_SLOTS:
+                    raise RuntimeError('a world accepted more than %d sub-steps inside one step' % MAX_SLOTS)
+                n = min(MAX_SLOTS, len(tape.slots) + 2)
+                tape.slots += [acquire_slot(self._slot_cap(k), self.nb, world.maxc, per, self.dev)
+                               for k in range(len(tape.slots), n)]
         if bits & STEP_DYN_SMEM and self.max_count + 2 > 64:
             raise RuntimeError('more than 62 contacts in one world: beyond the one-warp dynamics kernel')
 
@@ -281,28 +404,33 @@ def _toc_bwd(dt, toc_mask, body, p, v, geo, f, mass, gh):
     return g_dt, gp, gv, ggeo, gf, gm
 
 
-def _geometry_bwd(table, p, shape, cs, ggeo, fd_eps, detach_b2):
+def _geometry_bwd(table, p, shape, cs, ggeo, fd_eps, detach_b2, wmap):
     W, nb = p.shape[0], p.shape[1]
     gp = torch.empty_like(p)
-    rc = _lib.call('dsdf_contact_geometry_backward', table.ptr(), _ptr(p), _ptr(shape), W, nb, fd_eps, int(detach_b2),
-                   cs.maxc, _ptr(cs.count), _ptr(cs.body), _ptr(cs.face), _ptr(cs.abc), _ptr(ggeo), _ptr(gp), _lib.stream())
+    rc = _lib.call('dsdf_contact_geometry_backward_rows', table.ptr(), _ptr(p), _ptr(shape), W, nb, fd_eps, int(detach_b2),
+                   cs.maxc, _ptr(cs.count), _ptr(cs.body), _ptr(cs.face), _ptr(cs.abc), _ptr(ggeo), _ptr(gp), _ptr(wmap),
+                   _lib.stream())
     _lib.check(rc, 'dsdf_contact_geometry_backward')
     return gp
 
 
-def _dyn_bwd(cfg, p, v, mass, Ibody, fric, rest, f, dt, active, cs, x, lam, s, gnv):
+def _dyn_bwd(cfg, p, v, mass, Ibody, fric, rest, f, dt, active, count, body, geo, x, lam, s, gnv):
     W, nb = p.shape[0], p.shape[1]
-    geo = cs.geo
+    maxc = geo.shape[1]
     gp, gv = torch.empty_like(p), torch.empty_like(v)
     gmass, gI = torch.empty_like(mass), torch.empty_like(Ibody)
     gfric, grest, gf = torch.empty_like(fric), torch.empty_like(rest), torch.empty_like(f)
     gdt, ggeo = torch.empty(W, dtype=F64, device=p.device), torch.empty_like(geo)
-    rc = _lib.call('dsdf_dynamics_solve_backward', _ptr(p), _ptr(v), _ptr(mass), _ptr(Ibody), _ptr(fric), _ptr(rest),
-                   _ptr(f), _ptr(dt), _ptr(active), _ptr(cs.count), _ptr(cs.body), _ptr(geo), _ptr(cfg['eq_rows']), W, nb,
-                   cfg['neq'], cs.maxc, cfg['C'], cfg['fric_dirs'], int(cfg['stop_contact_grad']),
-                   int(cfg['stop_friction_grad']), _ptr(x), _ptr(lam), _ptr(s), _ptr(gnv), _ptr(gp), _ptr(gv), _ptr(gmass),
-                   _ptr(gI), _ptr(gfric), _ptr(grest), _ptr(gf), _ptr(gdt), _ptr(ggeo), _lib.stream())
-    _lib.check(rc, 'dsdf_dynamics_solve_backward')
+    small, large = cfg['C']
+    classes = [(small, -1, 1)] if large <= small else [(small, -1, 0), (large, small, 1)]
+    for C, cmin, last in classes:                # contact-count classes, see dsdf_dynamics_solve_backward_loop
+        rc = _lib.call('dsdf_dynamics_solve_backward_loop', _ptr(p), _ptr(v), _ptr(mass), _ptr(Ibody), _ptr(fric),
+                       _ptr(rest), _ptr(f), _ptr(dt), _ptr(active), _ptr(count), _ptr(body), _ptr(geo),
+                       _ptr(cfg['eq_rows']), W, nb, cfg['neq'], maxc, C, cfg['fric_dirs'],
+                       int(cfg['stop_contact_grad']), int(cfg['stop_friction_grad']), _ptr(x), _ptr(lam), _ptr(s),
+                       _ptr(gnv), _ptr(gp), _ptr(gv), _ptr(gmass), _ptr(gI), _ptr(gfric), _ptr(grest), _ptr(gf), _ptr(gdt),
+                       _ptr(ggeo), cmin, last, _lib.stream())
+        _lib.check(rc, 'dsdf_dynamics_solve_backward')
     return gp, gv, gmass, gI, gfric, grest, gf, gdt, ggeo
 
 
@@ -329,61 +457,87 @@ class _StepFn(torch.autograd.Function):
                        stop_contact_grad=world.stop_contact_grad, stop_friction_grad=world.stop_friction_grad,
                        table=world.table, shape=world.shape, detach_b2=world.detach_contact_b2)
         world._last_tape = tape
-        ctx.mark_non_differentiable(tape.had)
-        return tape.p_out, tape.v_out, tape.geo_out, tape.last_dt_out, tape.had
+        outs = (tape.p_out, tape.v_out, tape.geo_out, tape.last_dt_out, tape.had)
+        # the tape must not keep the outputs: output -> grad_fn (this ctx) -> tape -> output would be a reference cycle
+        # that only the cyclic GC frees, holding every rollout's tape alive
+        tape.p_out = tape.v_out = tape.geo_out = tape.last_dt_out = tape.had = None
+        ctx.mark_non_differentiable(outs[4])
+        return outs
 
     @staticmethod
     def backward(ctx, gp, gv, ggeo, glast, _ghad):
+        """Reverse sweep over the tape: slot k holds one row per world that accepted a (k+1)-th sub-step in this step, so
+        slot 0 is processed in place and the later (short) slots on gathered rows of the adjoints."""
         tape, cfg = ctx.tape, ctx.cfg
         mass, Ibody, fric, rest, f = ctx.params
         W = mass.shape[0]
         maxc = tape.maxc
-        gp, gv, glast = gp.contiguous(), gv.contiguous(), glast.contiguous()
+        gp, gv, glast = gp.clone(), gv.clone(), glast.clone()
         if ggeo.shape[1] != maxc:
             ggeo = torch.cat([ggeo, ggeo.new_zeros(W, maxc - ggeo.shape[1], 10)], 1)
-        ggeo = ggeo.contiguous()
+        else:
+            ggeo = ggeo.clone()
         gm, gI = torch.zeros_like(mass), torch.zeros_like(Ibody)
         gfr, gre, gf = torch.zeros_like(fric), torch.zeros_like(rest), torch.zeros_like(f)
-        zero_w = torch.zeros(W, dtype=F64, device=mass.device)
         for k in range(tape.maxsub - 1, -1, -1):
-            S = tape.slots[k]
-            cin = tape.start if k == 0 else tape.slots[k - 1].cs
-            m = tape.nsub > k
-            m_u8 = m.to(U8)
-            m3 = m[:, None, None]
-            gp_in_acc = gnv_acc = None
-            gdt_acc, glast_pass, ggeo_tot, gptry = zero_w, glast, ggeo, gp
+            n = tape.slots[k].rows
+            if n == 0:
+                continue
+            S = tape.slots[k].view(n)
+            if k == 0:
+                idx = wmap = None
+                a_gp, a_gv, a_ggeo, a_glast = gp, gv, ggeo, glast
+                pm, pI, pfr, pre, pf = mass, Ibody, fric, rest, f
+            else:
+                idx = S.world.long()
+                wmap = S.world
+                sel = lambda t: t.index_select(0, idx)
+                a_gp, a_gv, a_ggeo, a_glast = sel(gp), sel(gv), sel(ggeo), sel(glast)
+                pm, pI, pfr, pre, pf = sel(mass), sel(Ibody), sel(fric), sel(rest), sel(f)
+            zero_n = torch.zeros(n, dtype=F64, device=mass.device)
+            gp_in_acc = gnv_acc = dgf = dgm = None
+            gdt_acc, glast_pass, ggeo_tot, gptry = zero_n, a_glast, a_ggeo, a_gp
             if tape.any_toc:
                 # new contacts: p' = move(p, new_v, H(dt_)); H = dsdf_toc_backward (world.py:141-237, 275-341)
-                tn_u8 = S.toc_now * m_u8
-                tn = tn_u8.bool()
-                gpA, gvA, gdtA = _integrate_bwd(S.p_in, S.new_v, S.dt_used, tn_u8, gp)
-                gh = torch.where(tn, gdtA + glast, zero_w)
-                g_dt_B, gp_B, gv_B, ggeo_B, gf_B, gm_B = _toc_bwd(S.dt_used, S.toc_mask, S.cs.body, S.p_try, S.new_v,
-                                                                   S.cs.geo, f, mass, gh)
+                tn = S.toc_now.bool()
+                gpA, gvA, gdtA = _integrate_bwd(S.p_in, S.new_v, S.dt_used, S.toc_now, a_gp)
+                gh = torch.where(tn, gdtA + a_glast, zero_n)
+                g_dt_B, gp_B, gv_B, ggeo_B, gf_B, gm_B = _toc_bwd(S.dt_used, S.toc_mask, S.body, S.p_try, S.new_v, S.geo,
+                                                                   pf, pm, gh)
                 tn3 = tn[:, None, None]
                 gp_in_acc = torch.where(tn3, gpA, torch.zeros_like(gpA))
                 gnv_acc = torch.where(tn3, gvA + gv_B, torch.zeros_like(gvA))
-                gptry = torch.where(tn3, gp_B, gp)
-                ggeo_tot = ggeo + torch.where(tn3, ggeo_B, torch.zeros_like(ggeo_B))
-                gdt_acc = torch.where(tn, g_dt_B, zero_w)
-                glast_pass = torch.where(tn, zero_w, glast)
-                gf = gf + torch.where(tn3, gf_B, torch.zeros_like(gf_B))
-                gm = gm + torch.where(tn[:, None], gm_B, torch.zeros_like(gm_B))
-            gptry = gptry + _geometry_bwd(cfg['table'], S.p_try, cfg['shape'], S.cs, ggeo_tot.contiguous(), 1e-3,
-                                          cfg['detach_b2'])
-            gp2, gv2, gdt2 = _integrate_bwd(S.p_in, S.new_v, S.dt_used, m_u8, gptry.contiguous())
-            gnv = gv + gv2 if gnv_acc is None else gv + gv2 + gnv_acc      # masked worlds: gv2 = 0, gv passes through
-            gp3, gv3, gm3, gI3, gfr3, gre3, gf3, gdt3, ggeo3 = _dyn_bwd(cfg, S.p_in, S.v_in, mass, Ibody, fric, rest, f,
-                                                                       S.dt_used, m_u8, cin, S.x, S.lam, S.s,
-                                                                       gnv.contiguous())
+                gptry = torch.where(tn3, gp_B, a_gp)
+                ggeo_tot = a_ggeo + torch.where(tn3, ggeo_B, torch.zeros_like(ggeo_B))
+                gdt_acc = torch.where(tn, g_dt_B, zero_n)
+                glast_pass = torch.where(tn, zero_n, a_glast)
+                dgf = torch.where(tn3, gf_B, torch.zeros_like(gf_B))
+                dgm = torch.where(tn[:, None], gm_B, torch.zeros_like(gm_B))
+            gptry = gptry + _geometry_bwd(cfg['table'], S.p_try, cfg['shape'], S, ggeo_tot.contiguous(), 1e-3,
+                                          cfg['detach_b2'], wmap)
+            gp2, gv2, gdt2 = _integrate_bwd(S.p_in, S.new_v, S.dt_used, None, gptry.contiguous())
+            gnv = a_gv + gv2 if gnv_acc is None else a_gv + gv2 + gnv_acc
+            gp3, gv3, gm3, gI3, gfr3, gre3, gf3, gdt3, ggeo3 = _dyn_bwd(cfg, S.p_in, S.v_in, pm, pI, pfr, pre, pf,
+                                                                       S.dt_used, None, S.count_in, S.body_in, S.geo_in,
+                                                                       S.x, S.lam, S.s, gnv.contiguous())
             gp_new = gp2 + gp3 if gp_in_acc is None else gp2 + gp3 + gp_in_acc
             gdt_tot = gdt_acc + gdt2 + gdt3
-            glast = torch.where(m, glast_pass + torch.where(S.toc_flag_in.bool(), -gdt_tot, zero_w), glast)
-            gp = torch.where(m3, gp_new, gp)
-            gv = gv3
-            ggeo = torch.where(m3, ggeo3, ggeo)
-            gm, gI, gfr, gre, gf = gm + gm3, gI + gI3, gfr + gfr3, gre + gre3, gf + gf3
+            glast_new = glast_pass + torch.where(S.toc_flag_in.bool(), -gdt_tot, zero_n)
+            if dgf is not None:
+                gf3, gm3 = gf3 + dgf, gm3 + dgm
+            if k == 0:
+                gp, gv, ggeo, glast = gp_new, gv3, ggeo3, glast_new
+                gm, gI, gfr, gre, gf = gm + gm3, gI + gI3, gfr + gfr3, gre + gre3, gf + gf3
+            else:                                   # rows of one slot belong to distinct worlds: plain scatters
+                gp.index_copy_(0, idx, gp_new)
+                gv.index_copy_(0, idx, gv3)
+                ggeo.index_copy_(0, idx, ggeo3)
+                glast.index_copy_(0, idx, glast_new)
+                gm.index_add_(0, idx, gm3)
+                gI.index_add_(0, idx, gI3)
+                gfr.index_add_(0, idx, gfr3)
+                gre.index_add_(0, idx, gre3)
+                gf.index_add_(0, idx, gf3)
         if ggeo.shape[1] != ctx.geo_in_maxc:
             ggeo = ggeo[:, :ctx.geo_in_maxc]
         return None, None, gp, gv, ggeo, glast, gm, gI, gfr, gre, gf

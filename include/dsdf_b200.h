@@ -163,6 +163,13 @@ int dsdf_contact_geometry_backward(const dsdf_body_geom* geom, const double* p, 
                                    double fd_eps, int detach_b2, int maxc, const int32_t* count, const int32_t* cbody,
                                    const int32_t* cface, const double* cabc, const double* ggeo, double* gp, void* stream);
 
+/* Same for a compact batch of rows: row w carries the poses / contacts of world wmap[w], whose shapes and per-world
+ * meshes / grids are used (wmap == NULL: row = world). */
+int dsdf_contact_geometry_backward_rows(const dsdf_body_geom* geom, const double* p, const double* shape, int W, int nb,
+                                        double fd_eps, int detach_b2, int maxc, const int32_t* count,
+                                        const int32_t* cbody, const int32_t* cface, const double* cabc,
+                                        const double* ggeo, double* gp, const int32_t* wmap, void* stream);
+
 /* ------------------------------------------------------------- dynamics ----
  * Replaces the matrix assembly of PdipmEngine.solve_dynamics (lcp_physics/physics/engines.py:31-79) with
  * World3D.M/Jc/Jf (sdf_physics/physics3d/world.py:48-101), orthogonal (physics3d/utils.py:247-256) and
@@ -284,7 +291,20 @@ int dsdf_dynamics_solve_loop(const double* p, const double* v, const double* mas
                              const int32_t* eq_rows, int W, int nb, int neq, int maxc, int ncontacts_smem, int fric_dirs,
                              double eps, int not_improved_lim, int max_iter,
                              double* x, double* new_v, double* nu, double* lam, double* s, int32_t* status, int32_t* iters,
-                             const int32_t* vmap, int32_t* ctrl, void* stream);
+                             const int32_t* vmap, int32_t* ctrl, int count_min, int last_class, void* stream);
+/* count_min / last_class: contact-count classes.  A launch sized for ncontacts_smem contacts solves the worlds with
+ * count_min < count <= ncontacts_smem and leaves the others untouched (last_class = 1: worlds above ncontacts_smem are
+ * reported DSDF_LCP_TOO_LARGE instead), so a batch is covered by a launch for the typical count plus one for the few
+ * worlds with many contacts.  (-1, 1) = every world, the plain entry points' behaviour.  In the backward, masked
+ * (inactive) worlds are written by the count_min < 0 launch only. */
+int dsdf_dynamics_solve_backward_loop(const double* p, const double* v, const double* mass, const double* Ibody,
+                                      const double* fric, const double* rest, const double* f, const double* dt,
+                                      const unsigned char* active, const int32_t* count, const int32_t* cbody,
+                                      const double* cgeo, const int32_t* eq_rows, int W, int nb, int neq, int maxc,
+                                      int ncontacts_smem, int fric_dirs, int stop_contact_grad, int stop_friction_grad,
+                                      const double* x, const double* lam, const double* s, const double* g_new_v,
+                                      double* gp, double* gv, double* gmass, double* gI, double* gfric, double* grest,
+                                      double* gf, double* gdt, double* ggeo, int count_min, int last_class, void* stream);
 int dsdf_contacts_detect_loop(const dsdf_body_geom* geom, const int32_t* pairs, int npairs, const double* p,
                               const double* shape, const unsigned char* active,
                               int W, int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
@@ -302,14 +322,15 @@ int dsdf_contacts_detect_loop(const dsdf_body_geom* geom, const int32_t* pairs, 
  * All fields are 8 bytes wide (no padding).  Arrays are device memory; (W..) = per real world, (V..) = per virtual world
  * (V = vcap rows; attempt d of the i-th active world is row d * n_active + i).
  */
-#define DSDF_STEP_MAX_SLOTS 16
+#define DSDF_STEP_MAX_SLOTS 64
 /* bits of ctrl[0] (abort word): what the host must do before launching further rounds */
 #define DSDF_STEP_CAPK        1   /* a paused world overflowed the candidate list: enlarge capK          */
 #define DSDF_STEP_MAXC        2   /* a paused world found more than maxc contacts: enlarge maxc           */
 #define DSDF_STEP_DYN_SMEM    4   /* a world has more contacts than ncontacts_smem: round voided           */
-#define DSDF_STEP_TAPE        8   /* a paused world accepted more sub-steps than n_slots: add tape slots   */
+#define DSDF_STEP_TAPE        8   /* a paused world found its tape slot missing or full: add / enlarge slots (the host
+                                     clamps the slot's row counter to its capacity before resuming)           */
 #define DSDF_STEP_MAX_ROUNDS 16   /* max_rounds reached with worlds still active                           */
-/* words of the control block (int32[16]) the host reads back */
+/* words of the control block (int32[16 + DSDF_STEP_MAX_SLOTS]) the host reads back; word 16 + k = rows used in tape slot k */
 #define DSDF_CTRL_ABORT 0
 #define DSDF_CTRL_NACTIVE 1
 #define DSDF_CTRL_MAXCOUNT 3
@@ -317,15 +338,19 @@ int dsdf_contacts_detect_loop(const dsdf_body_geom* geom, const int32_t* pairs, 
 #define DSDF_CTRL_MAXNSUB 5
 #define DSDF_CTRL_ANYTOC 8
 #define DSDF_CTRL_LCPSTATUS 9
+#define DSDF_CTRL_MAXCLEAN 13
 
-typedef struct dsdf_step_slot {      /* tape of the k-th accepted sub-step of every world in this step */
-    double *p_in, *v_in;             /* (W,nb,7), (W,nb,6) state the sub-step started from                         */
-    double *x, *new_v, *p_try;       /* (W,6nb) LCP solution, (W,nb,6) = -x, (W,nb,7) pose after the move          */
-    double *dt_raw, *dt_used;        /* (W) sub-step length; value that entered solve / move (world.py:253-257)    */
-    double *lam, *s;                 /* (W, maxc (2+fd)) multipliers / slacks, reference row order                 */
-    unsigned char *toc_flag_in, *toc_now, *toc_mask;   /* (W), (W), (W,maxc)                                        */
-    int32_t *count, *body, *face;    /* contact set found at the END of the sub-step: (W), (W,maxc,2), (W,maxc)    */
-    double *abc, *geo;               /* (W,maxc,3), (W,maxc,10)                                                    */
+typedef struct dsdf_step_slot {      /* tape of the k-th accepted sub-step of this step: one self-contained ROW per world  */
+    int64_t cap;                     /* rows allocated.  Slot 0: row = world (cap = W); slot k > 0: rows are handed out  */
+    int32_t* world;                  /* (cap) world of each row          in commit order, ctrl[16 + k] counts them      */
+    double *p_in, *v_in;             /* (cap,nb,7), (cap,nb,6) state the sub-step started from                           */
+    double *x, *new_v, *p_try;       /* (cap,6nb) LCP solution, (cap,nb,6) = -x, (cap,nb,7) pose after the move          */
+    double *dt_raw, *dt_used;        /* (cap) sub-step length; value that entered solve / move (world.py:253-257)        */
+    double *lam, *s;                 /* (cap, maxc (2+fd)) multipliers / slacks, reference row order                     */
+    unsigned char *toc_flag_in, *toc_now, *toc_mask;   /* (cap), (cap), (cap,maxc)                                        */
+    int32_t *count_in, *body_in; double* geo_in;       /* contacts the solve used: (cap), (cap,maxc,2), (cap,maxc,10)     */
+    int32_t *count, *body, *face;    /* contact set found at the END of the sub-step: (cap), (cap,maxc,2), (cap,maxc)    */
+    double *abc, *geo;               /* (cap,maxc,3), (cap,maxc,10)                                                      */
 } dsdf_step_slot;
 
 typedef struct dsdf_step_args {
@@ -343,17 +368,18 @@ typedef struct dsdf_step_args {
     int32_t *vmap, *vidx; double *dt_raw_v, *dt_used_v;                /* (V), (W), (V), (V) */
     double *x_v, *new_v_v, *nu_v, *lam_v, *s_v, *p_try_v; int32_t *lcp_status_v, *iters_v;
     int32_t *count_v, *status_v, *body_v, *face_v; double *abc_v, *geo_v;
-    int32_t* ctrl;                                                     /* int32[16] */
-    dsdf_step_slot slots[DSDF_STEP_MAX_SLOTS];
+    int32_t* ctrl;                                                     /* int32[16 + DSDF_STEP_MAX_SLOTS] */
+    const dsdf_step_slot* slots;                                       /* DEVICE array of n_slots tape slots */
 } dsdf_step_args;
 
 /* Start a step: every world active with dt_try = world_dt, end_t = t + world_dt, control block reset. */
 int dsdf_step_begin(const dsdf_step_args* a, void* stream);
 /* Clear the abort word after the host enlarged a buffer (a may carry new pointers / sizes from here on). */
 int dsdf_step_resume(const dsdf_step_args* a, void* stream);
-/* Launch n_rounds rounds (5 kernels each) without any host synchronisation.  ncontacts_smem: contacts the dynamics
- * kernel sizes its shared memory for.  a is a HOST pointer; it is passed to the kernels by value. */
-int dsdf_step_rounds(const dsdf_step_args* a, int n_rounds, int ncontacts_smem, void* stream);
+/* Launch n_rounds rounds (5-6 kernels each) without any host synchronisation.  ncontacts_small / ncontacts_large:
+ * contacts the dynamics kernel sizes its shared memory for, in two classes (large <= small: one launch).
+ * a is a HOST pointer; it is passed to the kernels by value. */
+int dsdf_step_rounds(const dsdf_step_args* a, int n_rounds, int ncontacts_small, int ncontacts_large, void* stream);
 
 #ifdef __cplusplus
 }
