@@ -136,12 +136,12 @@ def run_ours(args):
     for _ in range(args.warmup):
         loss, grads, world = gpu_iteration(spec, dev, args.sim_steps, device)
         allreduce(loss, grads)
-    # ---- device-resident timing ("value") with per-entry-point CUDA events
+    # ---- device-resident timing ("value"): parameters already in HBM, no per-call profiling
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     barrier()
-    _lib.reset_counters(profile=True)
+    _lib.reset_counters(profile=False)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
@@ -151,7 +151,7 @@ def run_ours(args):
     barrier()
     ms = e0.elapsed_time(e1)
     launches = _lib.kernel_launches()
-    prof = _lib.profile_summary()
+    syncs_per_step = sum(world.stats.get('syncs', [0])) / max(len(world.stats.get('syncs', [0])), 1)
     attempts = float(world.stats['attempts'].double().mean()) / args.sim_steps
     # ---- end-to-end timing: pinned host -> device inputs, device -> host loss and gradients, every step
     _lib.reset_counters(profile=False)
@@ -170,6 +170,8 @@ def run_ours(args):
     barrier()
     ms_e2e = e2.elapsed_time(e3)
     sampler.stop_flag = True
+    # ---- separate profiling pass (NOT part of any reported throughput): per-kernel device time of one iteration
+    prof = kernel_profile(spec, dev, args.sim_steps, device) if rank == 0 else {}
     final_pos = world.bodies[-1].pos.detach().cpu()
     final_grads = {k: v.detach().cpu() for k, v in grads.items()}
     rounds_last = float(sum(world.stats['rounds']))
@@ -193,6 +195,8 @@ def run_ours(args):
     # dominant entry point by measured device time
     top = max(prof.items(), key=lambda kv: kv[1][1]) if prof else ('none', (1, 0.0))
     roof = roofline(top[0], top[1], W, spec, peaks, which, attempts)
+    fma = fma_peaks(device)
+    busy_ms = sum(v[1] for v in prof.values())
     line = {
         'metric': METRIC, 'value': units / (ms / 1e3), 'unit': UNIT, 'n_gpus': world_size, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak',
@@ -207,7 +211,13 @@ def run_ours(args):
         'gpu_launches': launches,
         'clocks': sampler.summary(),
         'roofline': roof,
-        'kernel_ms_per_step': {k: v[1] / args.steps for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+        'kernel_ms_per_step': {k: round(v[1], 3) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+        'kernel_launches_per_step': {k: v[0] for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])},
+        'profile_note': 'kernel_ms_per_step / kernel_launches_per_step come from ONE extra iteration run after the timed '
+                        'regions with CUDA events around every launch (on the launching stream); value and e2e are timed '
+                        'without them.  library_kernel_ms / ms_per_step = %.2f' % (busy_ms / (ms / args.steps)),
+        'host_syncs_per_world_step_call': syncs_per_step,
+        'fma_peaks': fma,
     }
     if per_rank is not None:
         line['per_rank'] = {'columns': ['ms_per_step', 'ms_per_step_e2e', 'rounds_per_iteration'], 'rows': per_rank,
@@ -218,6 +228,38 @@ def run_ours(args):
         line['secondary'] = secondary
     line['_final'] = (final_pos, final_grads)
     return line
+
+
+def kernel_profile(spec, params_dev, sim_steps, device):
+    """name -> (launches, total ms) of one optimisation iteration: the round kernels from the library's own event timing
+    (dsdf_step_profile), the reverse-sweep / set-up entry points from events around the ctypes calls."""
+    import ctypes
+    from diffsdfsim_b200 import _lib
+    lib = _lib.lib()
+    _lib.reset_counters(profile=True)
+    lib.dsdf_step_profile(1)
+    gpu_iteration(spec, params_dev, sim_steps, device)
+    prof = {k: v for k, v in _lib.profile_summary().items() if k not in ('dsdf_step_rounds',)}
+    ms, n = (ctypes.c_double * 5)(), (ctypes.c_int32 * 5)()
+    lib.dsdf_step_profile_read(ms, n)
+    lib.dsdf_step_profile(0)
+    _lib.reset_counters(profile=False)
+    for name, t, k in zip(['step_prep_kernel', 'dyn_forward_kernel', 'step_integrate_kernel', 'contacts_kernel',
+                           'step_commit_kernel'], ms, n):
+        prof[name] = (int(k), float(t))
+    return prof
+
+
+def fma_peaks(device):
+    """Measured FP64 / FP32 FMA rate of this GPU (dsdf_fma_peaks: dependent-chain microbenchmark)."""
+    import ctypes
+    from diffsdfsim_b200 import _lib
+    scratch = torch.empty(4 << 20, dtype=torch.uint8, device=device)
+    d, f = ctypes.c_double(0), ctypes.c_double(0)
+    rc = _lib.lib().dsdf_fma_peaks(1 << 14, scratch.data_ptr(), ctypes.byref(d), ctypes.byref(f),
+                                   torch.cuda.current_stream().cuda_stream)
+    return {'fp64_tflops': d.value, 'fp32_tflops': f.value, 'how': 'dsdf_fma_peaks: 8 independent FMA chains / thread, '
+            '8 CTAs x 256 threads per SM, CUDA events'} if rc == 0 else None
 
 
 def secondary_workloads(device, reps=3):
@@ -233,16 +275,18 @@ def secondary_workloads(device, reps=3):
     def timed(build, steps, leaf_key):
         best = None
         for _ in range(reps):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             torch.cuda.synchronize()
-            t0 = time.time()
+            e0.record()
             params, world = build()
             loss = 0.
             for _ in range(steps):
                 world.step(fixed_dt=True)
                 loss = loss + (world.bodies[-1].pos ** 2).sum() + (world.bodies[-1].v ** 2).sum()
             loss.backward()
+            e1.record()
             torch.cuda.synchronize()
-            dt = time.time() - t0
+            dt = e0.elapsed_time(e1) / 1e3
             assert torch.isfinite(params[leaf_key].grad).all()
             best = dt if best is None else min(best, dt)
         return world.W * steps / best, best
@@ -358,7 +402,7 @@ def roofline(name, stat, W, spec, peaks, which, attempts):
         # compulsory: read Q, p, G, h, A, F rows of the ACTIVE problem (~10 contacts) + write x, lam, s
         nia = 100
         per_world = 8 * (nz * nz + nz + nia * nz + nia + 6 * nz + nia * nia + nz + 2 * nia)
-    elif name == 'dsdf_contacts_detect':
+    elif name in ('dsdf_contacts_detect', 'contacts_kernel'):
         # per world and search direction: poses + the candidate/contact lists; shared meshes count once per launch
         per_world = 2 * 7 * 8 * 2 + 300 * 4 * 2 + 16 * (4 + 8 + 24 + 80)
         shared = 176000 * 12 + 89646 * 24 + 1200 * 12 + 726 * 24
@@ -366,8 +410,10 @@ def roofline(name, stat, W, spec, peaks, which, attempts):
         return {'kernel': name, 'bound': 'hbm', 'achieved': alg / 1e9 / (avg_ms / 1e3), 'peak': peaks['hbm_gbs'],
                 'unit': 'GB/s', 'frac': alg / 1e9 / (avg_ms / 1e3) / peaks['hbm_gbs'], 'traffic': ncu_traffic('contacts_kernel'),
                 'peak_source': which, 'avg_launch_ms': avg_ms, 'algorithmic_bytes_per_launch': alg,
+                'traffic_source': 'committed ncu capture (profiles/ncu_traffic.json), not measured in this run',
                 'note': 'shared L2-resident meshes: not an HBM-bound kernel on this workload; its limits are latency, '
-                        'barriers and FP64 issue (DESIGN.md s4)', 'ncu': ncu_counters('contacts_kernel')}
+                        'barriers and FP64 issue (DESIGN.md s4); avg_launch_ms averages full-width and nearly empty rounds',
+                'ncu': ncu_counters('contacts_kernel')}
     else:
         per_world = 8 * (nz * nz + ni * nz)
     alg = per_world * W

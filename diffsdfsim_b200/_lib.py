@@ -45,6 +45,9 @@ SIGNATURES = {
     'dsdf_step_begin': (c_i, [c_p, c_p]),
     'dsdf_step_resume': (c_i, [c_p, c_p]),
     'dsdf_step_rounds': (c_i, [c_p, c_i, c_i, c_i, c_p]),
+    'dsdf_step_profile': (c_i, [c_i]),
+    'dsdf_step_profile_read': (c_i, [c_p, c_p]),
+    'dsdf_fma_peaks': (c_i, [c_i, c_p, c_p, c_p, c_p]),
 }
 
 

@@ -24,10 +24,29 @@
 #include "dsdf_integrate.cuh"
 #include "dsdf_steploop.cuh"
 #include "../../include/dsdf_b200.h"
+#include <vector>
 
 namespace dsdf {
 
 typedef dsdf_step_args Args;
+
+// Optional per-kernel device timing of the rounds (dsdf_step_profile): CUDA events on the launching stream around every
+// launch of a round, summed per phase when read.  Off by default; the timed benchmark pass runs without it.
+enum { PHASE_PREP = 0, PHASE_DYN, PHASE_MOVE, PHASE_CONTACTS, PHASE_COMMIT, PHASE_COUNT };
+static bool g_profile = false;
+static std::vector<cudaEvent_t> g_events[PHASE_COUNT];      // start, end, start, end, ...
+struct PhaseTimer {
+    int phase; cudaStream_t st;
+    PhaseTimer(int ph, cudaStream_t s) : phase(ph), st(s) { mark(); }
+    ~PhaseTimer() { mark(); }
+    void mark() {
+        if (!g_profile) return;
+        cudaEvent_t e;
+        if (cudaEventCreate(&e) != cudaSuccess) return;
+        cudaEventRecord(e, st);
+        g_events[phase].push_back(e);
+    }
+};
 
 __global__ void __launch_bounds__(256)
 step_begin_kernel(const __grid_constant__ Args a) {
@@ -282,7 +301,8 @@ int dsdf_step_rounds(const dsdf_step_args* a, int n_rounds, int ncontacts_small,
     cudaStream_t st = (cudaStream_t)stream;
     const int W = (int)a->W, nb = (int)a->nb, V = (int)a->vcap;
     for (int r = 0; r < n_rounds; ++r) {
-        step_prep_kernel<<<(W + 255) / 256, 256, 0, st>>>(*a);
+        { PhaseTimer t(PHASE_PREP, st); step_prep_kernel<<<(W + 255) / 256, 256, 0, st>>>(*a); }
+        PhaseTimer* td = new PhaseTimer(PHASE_DYN, st);
         // two contact-count classes: worlds with <= ncontacts_small contacts, and (if any) the rest
         const bool two = ncontacts_large > ncontacts_small;
         int rc = dsdf_dynamics_solve_loop(a->p, a->v, a->mass, a->Ibody, a->fric, a->rest, a->f, a->dt_used_v, nullptr,
@@ -290,24 +310,50 @@ int dsdf_step_rounds(const dsdf_step_args* a, int n_rounds, int ncontacts_small,
                                           ncontacts_small, (int)a->fric_dirs, 1e-12, 3, (int)a->max_iter, a->x_v, a->new_v_v,
                                           a->nu_v, a->lam_v, a->s_v, a->lcp_status_v, a->iters_v, a->vmap, a->ctrl, -1,
                                           two ? 0 : 1, stream);
-        if (rc) return rc;
+        if (rc) { delete td; return rc; }
         if (two) {
             rc = dsdf_dynamics_solve_loop(a->p, a->v, a->mass, a->Ibody, a->fric, a->rest, a->f, a->dt_used_v, nullptr,
                                           a->count, a->body, a->geo, a->eq_rows, V, nb, (int)a->neq, (int)a->maxc,
                                           ncontacts_large, (int)a->fric_dirs, 1e-12, 3, (int)a->max_iter, a->x_v,
                                           a->new_v_v, a->nu_v, a->lam_v, a->s_v, a->lcp_status_v, a->iters_v, a->vmap,
                                           a->ctrl, ncontacts_small, 1, stream);
-            if (rc) return rc;
+            if (rc) { delete td; return rc; }
         }
-        step_integrate_kernel<<<(V * nb + 127) / 128, 128, 0, st>>>(*a);
+        delete td;
+        { PhaseTimer t(PHASE_MOVE, st); step_integrate_kernel<<<(V * nb + 127) / 128, 128, 0, st>>>(*a); }
+        PhaseTimer* tc = new PhaseTimer(PHASE_CONTACTS, st);
         rc = dsdf_contacts_detect_loop(a->geom, a->pairs, (int)a->npairs, a->p_try_v, a->shape, nullptr, V, nb, a->eps,
                                        a->tol, a->fd_eps, a->body_eps, (int)a->detach_b2, (int)a->capK, (int)a->maxc,
                                        a->count_v, a->body_v, a->face_v, a->abc_v, a->geo_v, a->status_v, nullptr, nullptr,
                                        a->vmap, a->ctrl, stream);
+        delete tc;
         if (rc) return rc;
-        step_commit_kernel<<<(W + 3) / 4, 128, 0, st>>>(*a);
+        { PhaseTimer t(PHASE_COMMIT, st); step_commit_kernel<<<(W + 3) / 4, 128, 0, st>>>(*a); }
     }
     return (int)cudaGetLastError();
+}
+
+int dsdf_step_profile(int enable) {
+    g_profile = enable != 0;
+    return 0;
+}
+
+int dsdf_step_profile_read(double* ms_out, int32_t* launches_out) {
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return (int)e;
+    for (int ph = 0; ph < PHASE_COUNT; ++ph) {
+        double tot = 0.0;
+        std::vector<cudaEvent_t>& v = g_events[ph];
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, v[i], v[i + 1]) == cudaSuccess) tot += ms;
+        }
+        if (ms_out) ms_out[ph] = tot;
+        if (launches_out) launches_out[ph] = (int32_t)(v.size() / 2);
+        for (cudaEvent_t ev : v) cudaEventDestroy(ev);
+        v.clear();
+    }
+    return 0;
 }
 
 }  // extern "C"

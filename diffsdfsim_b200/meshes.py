@@ -129,3 +129,75 @@ def mesh_inertia(verts, faces):
     A = np.stack([a, b, c], axis=2)                       # columns a,b,c
     C = np.einsum('f,fij,jk,flk->il', det, A, canon, A)
     return (np.trace(C) * np.eye(3) - C) / vol
+
+
+def surface_nets(grid, iso=0.0):
+    """Closed, outward-wound triangle mesh of the ``iso`` level set of an (R,R,R) grid sampled on [-1,1]^3.
+
+    Stands in for the iso-surface extraction the reference runs on grid / neural SDF bodies at construction time
+    (``ev_sdf_utils.marching_cubes`` on the res^3 samples, sdf_physics/physics3d/bodies.py:652-712 -- a third-party CUDA
+    extension that is not available offline; vertex / face ordering of that extension is unspecified, so meshes are
+    hot-path INPUTS handed identically to reference, oracle and CUDA path).  Naive surface nets: one
+    vertex per sign-changing cell (mean of its edge crossings), one quad per sign-changing interior grid edge, wound so
+    that normals point towards increasing values.  Returns (verts (V,3) float64 in [-1,1]^3, faces (F,3) int32).
+    """
+    g = np.asarray(grid, dtype=np.float64) - iso
+    R = g.shape[0]
+    n = R - 1
+    corner = {}
+    for dx in (0, 1):
+        for dy in (0, 1):
+            for dz in (0, 1):
+                corner[(dx, dy, dz)] = g[dx:n + dx, dy:n + dy, dz:n + dz]
+    inside = {k: v < 0 for k, v in corner.items()}
+    n_in = sum(v.astype(np.int8) for v in inside.values())
+    active = (n_in > 0) & (n_in < 8)
+    acc = np.zeros((n, n, n, 3))
+    cnt = np.zeros((n, n, n))
+    for a in corner:
+        for ax in range(3):
+            if a[ax] == 1:
+                continue
+            b = tuple(1 if i == ax else a[i] for i in range(3))
+            cross = inside[a] != inside[b]
+            den = np.where(cross, corner[a] - corner[b], 1.0)
+            t = np.where(cross, corner[a] / den, 0.0)
+            for i in range(3):
+                acc[..., i] += np.where(cross, a[i] + (t if i == ax else 0.0), 0.0)
+            cnt += cross
+    vid = -np.ones((n, n, n), dtype=np.int64)
+    vid[active] = np.arange(int(active.sum()))
+    ijk = np.stack(np.meshgrid(np.arange(n), np.arange(n), np.arange(n), indexing='ij'), -1)
+    pos = (ijk + acc / np.maximum(cnt, 1)[..., None])[active]
+    verts = pos / (R - 1) * 2.0 - 1.0
+    faces = []
+    s = g < 0
+    for ax in range(3):
+        u, v = (ax + 1) % 3, (ax + 2) % 3
+        # grid edges along `ax` from node q to q + e_ax, with 1 <= q_u, q_v <= R-2 (four cells around them exist)
+        sl0 = [slice(None)] * 3
+        sl1 = [slice(None)] * 3
+        sl0[ax], sl1[ax] = slice(0, n), slice(1, R)
+        sl0[u] = sl1[u] = slice(1, n)
+        sl0[v] = sl1[v] = slice(1, n)
+        a_in, b_in = s[tuple(sl0)], s[tuple(sl1)]
+        change = a_in != b_in
+        q = np.argwhere(change)                          # offsets: q_ax in [0,n), q_u, q_v in [0, n-1) -> +1
+        if q.shape[0] == 0:
+            continue
+        q[:, u] += 1
+        q[:, v] += 1
+        out_pos = a_in[change]                           # inside -> outside along +ax: normal = +ax
+
+        def cell(du, dv):
+            c = q.copy()
+            c[:, u] += du
+            c[:, v] += dv
+            return vid[c[:, 0], c[:, 1], c[:, 2]]
+        A, B, C, D = cell(-1, -1), cell(0, -1), cell(0, 0), cell(-1, 0)      # counter-clockwise seen from +ax
+        t1 = np.where(out_pos[:, None], np.stack([A, B, C], 1), np.stack([A, C, B], 1))
+        t2 = np.where(out_pos[:, None], np.stack([A, C, D], 1), np.stack([A, D, C], 1))
+        faces += [t1, t2]
+    faces = np.concatenate(faces).astype(np.int32) if faces else np.zeros((0, 3), np.int32)
+    assert faces.min(initial=0) >= 0, 'surface touches the grid boundary'
+    return verts, faces

@@ -43,8 +43,13 @@ def make_bodies(spec, device=None, params=None, W=1):
     n = len(spec['bodies'])
     for i, b in enumerate(spec['bodies']):
         last = i == n - 1
-        kw = dict(vel=params['vel'] if (last and 'vel' in params) else b['vel'],
-                  mass=params['mass'] if (last and 'mass' in params) else b['mass'],
+        vel = params['vel'] if (last and 'vel' in params) else b['vel']
+        mass = params['mass'] if (last and 'mass' in params) else b['mass']
+        if 'vel_all' in params:                    # (W,nb,6) / (W,nb): per-world initial velocities / masses of EVERY body
+            vel = params['vel_all'][:, i]
+        if 'mass_all' in params:
+            mass = params['mass_all'][:, i]
+        kw = dict(vel=vel, mass=mass,
                   restitution=b['restitution'],
                   fric_coeff=params['fric_coeff'] if 'fric_coeff' in params else b['fric_coeff'], device=device)
         pos = params['pos'] if (last and 'pos' in params) else b['pos']
@@ -56,16 +61,12 @@ def make_bodies(spec, device=None, params=None, W=1):
         elif k == 'cylinder':
             ob = B.SDFCylinder(pos, b['rad'], b['height'], max_tri_length=b['max_tri_length'], **kw)
         elif k == 'grid':
-            g = b['grid']
-            grid = baked_grid(g['res'], g['kind'], g.get('seed', 0)) if isinstance(g, dict) else g
-            m = b['mesh']
-            r = m['radius']
-            mesh = meshes.icosphere(r, m.get('subdivisions', 3))
+            grid, mesh = grid_array(b), grid_mesh(b)
             if last and 'grid' in params:          # per-world grids (W,R,R,R) and, optionally, per-world vertices
                 grid = params['grid']
                 if 'verts' in params:
-                    mesh = (params['verts'], mesh[1])
-            inertia = params['inertia'] if (last and 'inertia' in params) else 2 / 5 * r ** 2 * np.eye(3)
+                    mesh = (params['verts'], params.get('faces', mesh[1]))
+            inertia = params['inertia'] if (last and 'inertia' in params) else grid_unit_inertia(b)
             ob = B.SDFGrid3D(pos, b['scale'], grid, mesh, inertia=inertia, **kw)
         else:
             raise ValueError(k)
@@ -155,8 +156,54 @@ def inertia_fitting(dims=(1.0, 0.5, 0.25), torque=(1.0, 0.5, 0.25), until=0.3, m
                  axis_locks=[(0, 3), (0, 4), (0, 5)], steps=steps, time_of_contact_diff=False)
 
 
+_GRID_CACHE = {}
+
+
+def grid_array(b):
+    """(R,R,R) float64 samples of a grid body's SDF: an explicit array, or a recipe dict(res, kind, seed)."""
+    g = b['grid']
+    if not isinstance(g, dict):
+        return np.asarray(g, dtype=np.float64)
+    key = (g['res'], g['kind'], g.get('seed', 0))
+    if key not in _GRID_CACHE:
+        _GRID_CACHE[key] = baked_grid(*key)
+    return _GRID_CACHE[key]
+
+
+def grid_mesh(b):
+    """(verts, faces) of a grid body in its body frame: the iso-surface of its own grid (mesh=dict(kind='isosurface'),
+    what the reference extracts with marching cubes, bodies.py:652-712) or an icosphere of the given radius."""
+    m = b['mesh']
+    if m.get('kind') == 'isosurface':
+        from . import meshes
+        g = b['grid']
+        key = ('mesh', id(g) if not isinstance(g, dict) else (g['res'], g['kind'], g.get('seed', 0)), float(b['scale']))
+        hit = _GRID_CACHE.get(key)
+        if hit is None or (not isinstance(g, dict) and hit[2] is not g):
+            v, f = meshes.surface_nets(grid_array(b))
+            hit = (v * float(b['scale']), f, g)
+            _GRID_CACHE[key] = hit
+        return hit[0], hit[1]
+    from . import meshes
+    return meshes.icosphere(m['radius'], m.get('subdivisions', 3))
+
+
+def grid_unit_inertia(b):
+    """Unit-mass body-frame inertia of a grid body: volume integrals of its mesh (bodies.py:380-395) for iso-surface
+    meshes, the solid-sphere closed form for the icosphere stand-ins."""
+    m = b['mesh']
+    if m.get('kind') == 'isosurface':
+        from . import meshes
+        return meshes.mesh_inertia(*grid_mesh(b))
+    return 2 / 5 * m['radius'] ** 2 * np.eye(3)
+
+
 def baked_grid(res=32, kind='ellipsoid', seed=0):
-    """A res^3 float64 SDF grid on [-1,1]^3 standing in for a decoded IGR latent (no checkpoints offline)."""
+    """A res^3 float64 SDF grid on [-1,1]^3 standing in for a decoded IGR latent (no checkpoints offline).
+    kind 'igr': a seeded random-init IGR-style decoder sampled on the lattice (igr.py)."""
+    if kind == 'igr':
+        from . import igr
+        return igr.random_shape_grid(seed, res)
     t = np.linspace(-1.0, 1.0, res)
     X, Y, Z = np.meshgrid(t, t, t, indexing='ij')
     if kind == 'sphere':
@@ -182,3 +229,46 @@ def grid_on_pole(res=32, floor=(10.0, 1.0, 10.0), drop=2.62, steps=12, floor_tri
                        restitution=0.0, gravity=True, mesh=dict(subdivisions=3, radius=0.6)))
     nc = [(0, 1)] if with_floor else []
     return scene(bodies, no_contact=nc, steps=steps)
+
+
+def cow_on_pole(grid=None, res=64, seed=0, floor=(50.0, 1.0, 50.0), floor_tri=0.1, scale=2.0, drop=6.0, steps=33):
+    """BASELINE config 4 as the reference demo builds it (demos/demo_meshsdf.py:121-142, TIME = 1.1 s = 33 steps):
+    pinned 50x1x50 floor, pinned pole SDFCylinder((pi/2,0,0, 0.35,1,0), r 0.2, h 2) with add_no_contact(pole, floor),
+    and a grid-SDF body of scale 2 dropped from [0,6,0] (friction 0.15, restitution 0) whose res^3 grid is baked from a
+    seeded random-init IGR-style decoder (igr.py) -- or handed in as ``grid`` -- and whose mesh is that grid's iso-surface.
+    The demo's loss is |pos - [0, 0.64, 0]|^2 after the rollout (:88)."""
+    q = [math.cos(math.pi / 4), math.sin(math.pi / 4), 0.0, 0.0]
+    g = grid if grid is not None else dict(res=res, kind='igr', seed=seed)
+    return scene([
+        body('box', [0, -floor[1] / 2, 0], dims=list(floor), pinned=True, fric_coeff=0.15, restitution=0.0,
+             max_tri_length=floor_tri),
+        body('cylinder', q + [0.35, 1.0, 0.0], rad=0.2, height=2.0, pinned=True, fric_coeff=0.15, restitution=0.5),
+        body('grid', [0.0, drop, 0.0], grid=g, scale=scale, fric_coeff=0.15, restitution=0.0, gravity=True,
+             mesh=dict(kind='isosurface')),
+    ], no_contact=[(0, 1)], steps=steps)
+
+
+def mixed16(seed=0, steps=12, spacing=1.3, speed=1.0, gravity=False, subdivisions=3, tri=0.15):
+    """BASELINE config 3 shape: 16 mixed primitives per world -- spheres r in [0.2,0.5], boxes dims in [0.3,0.8],
+    cylinders r in [0.2,0.4], h in [0.4,0.8] -- on a jittered 4 x 2 x 2 lattice inside a ~4 m cube
+    with random velocities ~ N(0, speed), free-floating (no gravity), colliding with each other.  The 16 shapes are drawn
+    once per seed (meshes shared by all worlds); per-world parameters are the masses / initial velocities handed to
+    make_bodies.  Every one of the 120 body pairs is a candidate (broad phase + both search directions)."""
+    rng = np.random.RandomState(seed)
+    bodies = []
+    for i in range(16):
+        ix, iy, iz = i % 4, (i // 4) % 2, i // 8
+        pos = (np.array([ix - 1.5, iy - 0.5, iz - 0.5]) * spacing + 0.08 * (rng.rand(3) - 0.5)).tolist()
+        vel = [0.0, 0.0, 0.0] + (speed * rng.randn(3)).tolist()
+        kw = dict(vel=vel, fric_coeff=0.3, restitution=0.5, gravity=gravity, mass=float(0.5 + rng.rand()))
+        kind = i % 3
+        if kind == 0:
+            bodies.append(body('sphere', pos, rad=float(0.2 + 0.3 * rng.rand()), mesh=dict(subdivisions=subdivisions), **kw))
+        elif kind == 1:
+            bodies.append(body('box', pos, dims=(0.3 + 0.5 * rng.rand(3)).tolist(), max_tri_length=tri, **kw))
+        else:
+            a = rng.rand() * math.pi
+            q = [math.cos(a / 2), math.sin(a / 2), 0.0, 0.0]
+            bodies.append(body('cylinder', q + pos, rad=float(0.2 + 0.2 * rng.rand()), height=float(0.4 + 0.4 * rng.rand()),
+                               max_tri_length=tri, **kw))
+    return scene(bodies, steps=steps)

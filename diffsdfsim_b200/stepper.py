@@ -293,9 +293,12 @@ class DeviceStepper:
         burst = min(max(2, self.last_rounds + 1), 24)
         syncs = 0
         while True:
-            rc = _lib.call('dsdf_step_rounds', ctypes.byref(args), burst, *self._smem_contacts(world), stream)
+            small, large = self._smem_contacts(world)
+            rc = _lib.call('dsdf_step_rounds', ctypes.byref(args), burst, small, large, stream)
             _lib.check(rc, 'dsdf_step_rounds')
-            self.launches += 5 * burst
+            nk = burst * (6 if large > small else 5)         # kernels of this burst (bench.py's gpu_launches)
+            self.launches += nk
+            _lib.LAUNCHES['step_round_kernels'] = _lib.LAUNCHES.get('step_round_kernels', 0) + nk
             t0 = self._tick('launch', t0)
             c = self._read_ctrl()
             t0 = self._tick('sync', t0)

@@ -380,6 +380,15 @@ int dsdf_step_resume(const dsdf_step_args* a, void* stream);
  * contacts the dynamics kernel sizes its shared memory for, in two classes (large <= small: one launch).
  * a is a HOST pointer; it is passed to the kernels by value. */
 int dsdf_step_rounds(const dsdf_step_args* a, int n_rounds, int ncontacts_small, int ncontacts_large, void* stream);
+/* Diagnostics: per-kernel device time of the rounds.  dsdf_step_profile(1) makes dsdf_step_rounds bracket every launch
+ * with CUDA events on its stream; dsdf_step_profile_read synchronises, writes the summed milliseconds and launch counts
+ * of the five phases [prep, dynamics, move, contacts, commit] (host arrays of 5) and clears the events. */
+int dsdf_step_profile(int enable);
+int dsdf_step_profile_read(double* ms_out, int32_t* launches_out);
+
+/* Measured FMA peaks of this device (dependent-chain microbenchmark, 8 chains per thread): the roofline denominators
+ * for the FP64-bound stepping kernels.  scratch: >= 2.5 MB of device memory.  Outputs are host pointers (TFLOP/s). */
+int dsdf_fma_peaks(int iters, void* scratch, double* fp64_tflops, double* fp32_tflops, void* stream);
 
 #ifdef __cplusplus
 }

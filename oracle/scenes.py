@@ -25,8 +25,7 @@ def mesh_for(b):
     if k == 'cylinder':
         return meshes.cylinder_mesh(b['rad'], b['height'], 32, b['max_tri_length'])
     if k == 'grid':
-        m = b['mesh']
-        return meshes.icosphere(m['radius'], m.get('subdivisions', 3))
+        return scenes.grid_mesh(b)
     raise ValueError(k)
 
 
@@ -48,10 +47,8 @@ def shape_for(b, mass):
         I = mass * torch.diag(torch.stack([(3 * r ** 2 + h ** 2) / 12, (3 * r ** 2 + h ** 2) / 12, r ** 2 / 2]))
         return S.CYLINDER, [r / sc, h / sc], sc, I
     if k == 'grid':
-        g = b['grid']
-        grid = tens(scenes.baked_grid(g['res'], g['kind'], g.get('seed', 0))) if isinstance(g, dict) else tens(g)
-        r = b['mesh']['radius']
-        return S.GRID, [grid], tens(b['scale']), 2 / 5 * mass * r ** 2 * torch.eye(3, dtype=F64)
+        grid = tens(scenes.grid_array(b))
+        return S.GRID, [grid], tens(b['scale']), mass * tens(scenes.grid_unit_inertia(b))
     raise ValueError(k)
 
 
@@ -62,11 +59,15 @@ def build(spec, params=None, max_iter=10, **world_kw):
     for i, b in enumerate(spec['bodies']):
         last = i == n - 1
         mass = params['mass'] if (last and 'mass' in params) else tens(float(b['mass']))
+        if 'mass_all' in params:
+            mass = params['mass_all'][i]
         fric = params['fric_coeff'] if ('fric_coeff' in params) else tens(float(b['fric_coeff']))
         kind, sp, scale, I = shape_for(b, mass)
         verts, faces = mesh_for(b)
         pos = params['pos'] if (last and 'pos' in params) else tens(b['pos'])
         vel = params['vel'] if (last and 'vel' in params) else tens(b['vel'])
+        if 'vel_all' in params:
+            vel = params['vel_all'][i]
         ob = Body(kind, sp, scale, torch.as_tensor(verts, dtype=F64), torch.as_tensor(np.asarray(faces)).long(),
                   pos, vel, mass, I, b['restitution'], fric)
         if b['gravity']:

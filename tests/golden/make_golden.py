@@ -62,10 +62,14 @@ def build_reference(spec, params=None):
     for i, b in enumerate(spec['bodies']):
         last = i == n - 1
         mass = params['mass'] if (last and 'mass' in params) else float(b['mass'])
+        if 'mass_all' in params:
+            mass = params['mass_all'][i]
         fric = params['fric_coeff'] if 'fric_coeff' in params else float(b['fric_coeff'])
         verts, faces = mesh_for(b)
         pos = params['pos'] if (last and 'pos' in params) else torch.tensor(b['pos'], dtype=F64)
         vel = params['vel'] if (last and 'vel' in params) else torch.tensor(b['vel'], dtype=F64)
+        if 'vel_all' in params:
+            vel = params['vel_all'][i]
         kw = dict(vel=vel, mass=mass, restitution=b['restitution'], fric_coeff=fric)
         k = b['kind']
         if k == 'box':
@@ -76,11 +80,14 @@ def build_reference(spec, params=None):
             ob = _inject(rb.SDFCylinder, verts, faces)(pos, b['rad'], b['height'], custom_mesh=True,
                                                        custom_inertia=True, **kw)
         elif k == 'grid':
-            g = b['grid']
-            grid = torch.tensor(scenes.baked_grid(g['res'], g['kind'], g.get('seed', 0)), dtype=F64)
-            r = b['mesh']['radius']
-            cls = _inject(rb.SDFGrid3D, verts, faces,
-                          inertia=lambda m, r=r: 2 / 5 * m * r ** 2 * torch.eye(3, dtype=F64))
+            grid = torch.tensor(scenes.grid_array(b), dtype=F64)
+            if b['mesh'].get('kind') == 'isosurface':
+                # the reference integrates the inertia of the injected mesh itself (bodies.py:380-395)
+                cls = _inject(rb.SDFGrid3D, verts, faces)
+            else:
+                r = b['mesh']['radius']
+                cls = _inject(rb.SDFGrid3D, verts, faces,
+                              inertia=lambda m, r=r: 2 / 5 * m * r ** 2 * torch.eye(3, dtype=F64))
             ob = cls(pos, b['scale'], grid, **kw)
         else:
             raise ValueError(k)
@@ -185,13 +192,21 @@ def pack(out):
 
 def golden_scene(name, spec, leaves):
     params = {k: torch.tensor(v, dtype=F64, requires_grad=True) for k, v in leaves.items()}
-    world, out, loss, lcps = rollout_reference(spec, params)
+    world, out, loss, lcps = rollout_reference(spec, params, record_lcp=len(spec['bodies']) <= 6)
     d = pack(out)
     d['loss'] = float(loss)
     loss.backward()
     for k, t in params.items():
         d['grad_' + k] = t.grad.numpy().copy()
         d['leaf_' + k] = t.detach().numpy().copy()
+    for b, rb_ in zip(spec['bodies'], world.bodies):
+        if b['kind'] == 'grid' and b['mesh'].get('kind') == 'isosurface':
+            # the grid is a fixture (float32 is exact: igr.random_shape_grid rounds through it); the reference's own
+            # volume-integral inertia of the injected mesh pins meshes.mesh_inertia
+            d['grid_f32'] = scenes.grid_array(b).astype(np.float32)
+            assert np.array_equal(d['grid_f32'].astype(np.float64), scenes.grid_array(b))
+            d['ref_inertia'] = rb_.ang_inertia.detach().numpy().copy()
+            d['ref_mass'] = float(rb_.mass)
     # the largest recorded LCP instance, for the operator-level golden
     if lcps:
         big = max(lcps, key=lambda a: a[2].shape[1])
@@ -203,7 +218,7 @@ def golden_scene(name, spec, leaves):
           {k: d['grad_' + k].tolist() for k in leaves})
 
 
-from specs import SCENES  # noqa: E402
+from specs import SCENES, default_leaves  # noqa: E402
 
 
 def golden_sdf():
@@ -233,4 +248,5 @@ if __name__ == '__main__':
             golden_sdf()
         else:
             mk, leaves = SCENES[n]
-            golden_scene(n, mk(), leaves)
+            spec = mk()
+            golden_scene(n, spec, default_leaves(spec, leaves))

@@ -13,4 +13,25 @@ SCENES = {
     # config-3 shape: several free bodies + pinned floor, every pair searched (pins pair order and multi-pair contact rows)
     'mixed_primitives': (lambda: scenes.mixed_primitives(steps=8),
                          dict(mass=1.2, vel=[0.0, 0.0, 0.0, 0.2, -1.0, 0.1])),
+    # ---- BASELINE configurations at their named sizes
+    # config 1: sphere dropped from 5 m with 5 m/s sideways on the 20x1x20 floor (176 000 faces), 100 steps
+    # (experiments/trajectory_fitting/optim_sphere.py:78-111)
+    'c1_bouncing_sphere': (lambda: scenes.bouncing_sphere(rad=1.0, height=5.0, vel=(0, 0, 0, 5.0, 0, 0), floor=(20.0, 1.0, 20.0),
+                                                          steps=100, floor_tri=0.1, subdivisions=4),
+                           dict(fric_coeff=0.25, vel=[0.0, 0.0, 0.0, 5.0, 0.0, 0.0], pos=[0.0, 5.0, 0.0])),
+    # config 3 shape at size: 16 mixed primitives, every pair searched (nz = 96, no equality rows)
+    'c3_mixed16': (lambda: scenes.mixed16(seed=0, steps=12, spacing=1.05, speed=2.0), dict(mass_all=None, vel_all=None)),
+    # config 4 as the demo builds it: 64^3 grid baked from a random-init IGR-style decoder, 50x1x50 floor, scale 2, 33 steps
+    'c4_cow_on_pole': (lambda grid=None: scenes.cow_on_pole(grid=grid, res=64, seed=1, steps=33),
+                       dict(mass=1.0, fric_coeff=0.15, pos=[0.0, 6.0, 0.0])),
 }
+
+
+def default_leaves(spec, leaves):
+    """Leaves given as None take the spec's own values (per-body arrays for the *_all parameters)."""
+    out = dict(leaves)
+    if out.get('mass_all', 0) is None:
+        out['mass_all'] = [float(b['mass']) for b in spec['bodies']]
+    if out.get('vel_all', 0) is None:
+        out['vel_all'] = [list(b['vel']) for b in spec['bodies']]
+    return out
