@@ -71,7 +71,8 @@ step_prep_kernel(const __grid_constant__ Args a) {
     const int* c = a.ctrl;
     if (loop_idle(c)) return;
     const int n = c[CT_NACT];
-    const int deff = (a.depth > 1 && n <= a.spec_threshold) ? (int)a.depth : 1;
+    int deff = (a.depth > 1 && n <= a.spec_threshold) ? (int)a.depth : 1;
+    if (a.depth2 > deff && n <= a.spec_threshold2) deff = (int)a.depth2;
     const int w = blockIdx.x * blockDim.x + threadIdx.x;
     if (w == 0) { a.ctrl[CT_DEFF] = deff; a.ctrl[CT_NVIRT] = n * deff; }
     if (w >= a.W || !a.active[w]) return;
@@ -274,9 +275,9 @@ using namespace dsdf;
 extern "C" {
 
 static int step_check(const dsdf_step_args* a) {
-    if (!a || a->W <= 0 || a->nb <= 0 || a->maxc <= 0 || a->vcap < a->W || a->depth < 1 || a->depth > 8 || !a->ctrl) return -1;
+    if (!a || a->W <= 0 || a->nb <= 0 || a->maxc <= 0 || a->vcap < a->W || a->depth < 1 || a->depth > 16 || !a->ctrl) return -1;
     if (a->n_slots < 1 || a->n_slots > DSDF_STEP_MAX_SLOTS) return -1;
-    if (a->depth * a->spec_threshold > a->vcap) return -1;
+    if (a->depth * a->spec_threshold > a->vcap || a->depth2 > 16 || a->depth2 * a->spec_threshold2 > a->vcap) return -1;
     return 0;
 }
 

@@ -32,7 +32,8 @@ LCP_FACTOR_FAIL, LCP_INACCURATE, LCP_TOO_LARGE = 4, 8, 16
 
 _SLOT_FIELDS = ['world', 'p_in', 'v_in', 'x', 'new_v', 'p_try', 'dt_raw', 'dt_used', 'lam', 's', 'toc_flag_in', 'toc_now',
                 'toc_mask', 'count_in', 'body_in', 'geo_in', 'count', 'body', 'face', 'abc', 'geo']
-_INT_FIELDS = ['W', 'nb', 'neq', 'maxc', 'fric_dirs', 'capK', 'npairs', 'depth', 'spec_threshold', 'vcap', 'n_slots',
+_INT_FIELDS = ['W', 'nb', 'neq', 'maxc', 'fric_dirs', 'capK', 'npairs', 'depth', 'spec_threshold', 'depth2',
+               'spec_threshold2', 'vcap', 'n_slots',
                'max_iter', 'max_rounds', 'strict', 'toc_enabled', 'fixed_dt', 'detach_b2']
 _DBL_FIELDS = ['world_dt', 'eps', 'tol', 'fd_eps', 'body_eps']
 _PTR_FIELDS = ['geom', 'pairs', 'eq_rows', 'mass', 'Ibody', 'fric', 'rest', 'f', 'shape',
@@ -173,7 +174,11 @@ class DeviceStepper:
         W, dev = self.W, self.dev
         self.depth = world.SPEC_DEPTH if world.speculate else 1
         self.spec_threshold = W // 8 if (world.speculate and W >= 64) else 0
-        self.vcap = max(W, self.depth * self.spec_threshold)
+        # second level: when hardly any world is left, try six halvings at once (a world that ends up giving up at
+        # dt / 2^10 then needs two rounds instead of four)
+        self.depth2 = world.SPEC_DEPTH2 if (world.speculate and world.SPEC_DEPTH2 > self.depth) else 0
+        self.spec_threshold2 = W // 32 if (self.depth2 and W >= 64) else 0
+        self.vcap = max(W, self.depth * self.spec_threshold, self.depth2 * self.spec_threshold2)
         self.ctrl = torch.zeros(CT_WORDS, dtype=I32, device=dev)
         self.ctrl_host = torch.zeros(CT_WORDS, dtype=I32).pin_memory()
         self.slot_table = torch.zeros(MAX_SLOTS * ctypes.sizeof(StepSlot), dtype=U8, device=dev)
@@ -209,6 +214,7 @@ class DeviceStepper:
         a.W, a.nb, a.neq, a.maxc, a.fric_dirs = self.W, self.nb, world.num_constraints, world.maxc, world.fric_dirs
         a.capK, a.npairs = world.detector.capK, world.detector.npairs
         a.depth, a.spec_threshold, a.vcap, a.n_slots = self.depth, self.spec_threshold, self.vcap, len(tape.slots)
+        a.depth2, a.spec_threshold2 = self.depth2, self.spec_threshold2
         a.max_iter, a.max_rounds = world.engine.max_iter, world.max_rounds_per_step
         a.strict, a.toc_enabled = int(world.strict_no_pen), int(world.time_of_contact_diff)
         a.fixed_dt, a.detach_b2 = int(fixed_dt), int(world.detach_contact_b2)

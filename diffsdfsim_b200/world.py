@@ -101,6 +101,7 @@ class World3D:
     max_rounds_per_step = 256
     speculate = True       # evaluate dt, dt/2, dt/4 of the few still-active worlds in ONE round (see _attempt_speculative)
     SPEC_DEPTH = 3
+    SPEC_DEPTH2 = 6        # device loop only: halvings tried at once when <= W/32 worlds are still active
     toc_native = True      # False: the torch-autograd restatement of World.H (TimeOfContact) on the affected worlds
     device_loop = True     # the per-world step state machine runs on the device (stepper.py / csrc/dsdf_steploop.cu);
                            # False: the host-driven round loop below (one synchronisation per round)

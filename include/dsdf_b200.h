@@ -356,7 +356,9 @@ typedef struct dsdf_step_slot {      /* tape of the k-th accepted sub-step of th
 typedef struct dsdf_step_args {
     int64_t W, nb, neq, maxc, fric_dirs, capK, npairs;
     int64_t depth;                   /* attempts (dt, dt/2, ..) evaluated at once when <= spec_threshold worlds are active */
-    int64_t spec_threshold, vcap, n_slots, max_iter, max_rounds;
+    int64_t spec_threshold;
+    int64_t depth2, spec_threshold2; /* a second, deeper level for the nearly empty rounds (depth2 >= depth, threshold2 <= threshold) */
+    int64_t vcap, n_slots, max_iter, max_rounds;
     int64_t strict, toc_enabled, fixed_dt, detach_b2;
     double world_dt, eps, tol, fd_eps, body_eps;
     const dsdf_body_geom* geom; const int32_t* pairs; const int32_t* eq_rows;

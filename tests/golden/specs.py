@@ -35,3 +35,15 @@ def default_leaves(spec, leaves):
     if out.get('vel_all', 0) is None:
         out['vel_all'] = [list(b['vel']) for b in spec['bodies']]
     return out
+
+
+def make_spec(name, g=None):
+    """Spec of a golden scene; a grid committed with the golden file (float32, exact) replaces the bake recipe so that
+    every machine sees bit-identical geometry."""
+    mk, leaves = SCENES[name]
+    if g is not None and 'grid_f32' in getattr(g, 'files', g):
+        import numpy as np
+        spec = mk(grid=np.asarray(g['grid_f32'], dtype=np.float64))
+    else:
+        spec = mk()
+    return spec, default_leaves(spec, leaves)
