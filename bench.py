@@ -42,7 +42,9 @@ def parse():
     ap.add_argument('--cpu-sim-steps', type=int, default=0, help='0 = --sim-steps')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-sdf-query', action='store_true', help='skip the SDF-query HBM-roofline microbenchmark')
-    ap.add_argument('--no-secondary', action='store_true', help='skip the config-4 / config-5 secondary workloads')
+    ap.add_argument('--no-secondary', action='store_true', help='skip the config-3 / 4 / 5 secondary workloads')
+    ap.add_argument('--strong-total', type=int, default=65536,
+                    help='total worlds of the strong-scaling pass (config 5; 0 = skip)')
     return ap.parse_args()
 
 
@@ -182,6 +184,9 @@ def run_ours(args):
         dist.all_gather(allr, mine)
         per_rank = [[round(float(x), 2) for x in r] for r in allr]
     ms, ms_e2e = D.max_over_ranks([ms, ms_e2e], device)
+    strong = None
+    if args.strong_total > 0:
+        strong = strong_scaling_pass(args, spec, device, rank, world_size, barrier, allreduce)
     sdfq = None
     if rank == 0 and not args.no_sdf_query:
         sdfq = sdf_query_roofline(device)
@@ -222,12 +227,40 @@ def run_ours(args):
     if per_rank is not None:
         line['per_rank'] = {'columns': ['ms_per_step', 'ms_per_step_e2e', 'rounds_per_iteration'], 'rows': per_rank,
                             'note': 'ranks step DIFFERENT worlds (seed = rank); the job time is the slowest rank'}
+    if strong is not None:
+        line['strong_scaling'] = strong
     if sdfq is not None:
         line['sdf_query'] = sdfq
     if secondary is not None:
         line['secondary'] = secondary
     line['_final'] = (final_pos, final_grads)
     return line
+
+
+def strong_scaling_pass(args, spec, device, rank, world_size, barrier, allreduce):
+    """BASELINE config 5 as written: a FIXED total of `--strong-total` box-on-plane worlds sharded over the ranks (each rank
+    owns total / N worlds), one optimisation iteration (30 World3D.step + backward + the one NCCL all-reduce of loss and
+    shared-parameter gradients), device-timed, max over ranks.  Reported next to the weak-scaling headline so that both
+    curves can be read from the N = 1, 2, 4, 8 lines."""
+    from diffsdfsim_b200 import distributed as D
+    total = args.strong_total
+    lo, hi = D.shard_range(total, rank, world_size)
+    host = make_params(total, torch.device('cpu'), seed=12345)
+    dev = {k: v[lo:hi].to(device) for k, v in host.items()}
+    loss, grads, _ = gpu_iteration(spec, dev, args.sim_steps, device)        # warm-up (allocator, tape pool)
+    allreduce(loss, grads)
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    loss, grads, _ = gpu_iteration(spec, dev, args.sim_steps, device)
+    allreduce(loss, grads)
+    e1.record()
+    barrier()
+    ms = D.max_over_ranks([e0.elapsed_time(e1)], device)[0]
+    return {'worlds_total': total, 'worlds_per_gpu': hi - lo, 'n_gpus': world_size, 'ms_per_iteration': ms,
+            'value': total * args.sim_steps / (ms / 1e3), 'unit': UNIT, 'scaling': 'strong',
+            'workload': 'config 5: %d box-on-plane worlds in total, sharded over %d GPU(s), fwd+bwd + NCCL all-reduce'
+                        % (total, world_size)}
 
 
 def kernel_profile(spec, params_dev, sim_steps, device):
@@ -262,17 +295,17 @@ def fma_peaks(device):
             '8 CTAs x 256 threads per SM, CUDA events'} if rc == 0 else None
 
 
-def secondary_workloads(device, reps=3):
-    """world-steps/s (forward + backward, device-resident parameters) of the other BASELINE shapes at their full sizes,
-    for context next to the headline: config 4 (256 worlds, per-world 64^3 SDF grids and per-world meshes, grid body
-    falling on a pinned pole over a floor, 12 steps) and config 5's per-GPU share (8192 worlds of the inertia-fitting
-    scene: box under X/Y/Z constraints spun up by a torque, no contacts, 60 steps)."""
+def secondary_workloads(device, reps=2):
+    """world-steps/s (forward + backward, device-resident parameters, CUDA-event timed, best of `reps`) of the other
+    BASELINE configurations at their named sizes: config 4 (256 worlds, per-world IGR-decoder grids and meshes, 33 steps),
+    config 3 (1024 worlds x 16 mixed primitives, 200 steps) and config 5's per-GPU share of the inertia-fitting scene
+    (8192 worlds, box under X/Y/Z constraints spun up by a torque, no contacts, 60 steps)."""
     import numpy as np
     from diffsdfsim_b200 import meshes, scenes
     F64 = torch.float64
     out = {}
 
-    def timed(build, steps, leaf_key):
+    def timed(build, steps, leaf_key, reps=reps):
         best = None
         for _ in range(reps):
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -292,24 +325,39 @@ def secondary_workloads(device, reps=3):
         return world.W * steps / best, best
 
     g = torch.Generator().manual_seed(0)
+    # ---- config 4 as named: 256 worlds, each with its own 64^3 grid baked from its own random-init IGR-style decoder and
+    # its own iso-surface mesh; pinned 50x1x50 floor (1.04 M faces, shared), pinned pole, scale 2, drop from y = 6, 33 steps
     W, R = 256, 64
-    radii = (0.5 + 0.2 * torch.rand(W, generator=g, dtype=F64)).numpy()
-    t = np.linspace(-1.0, 1.0, R)
-    X, Y, Z = np.meshgrid(t, t, t, indexing='ij')
-    base = np.sqrt(X * X + Y * Y + Z * Z)
-    grids = torch.as_tensor(np.stack([base - r for r in radii])).to(device)
-    verts = torch.as_tensor(np.stack([meshes.icosphere(float(r), 3)[0] for r in radii])).to(device)
-    inertia = torch.stack([2 / 5 * float(r) ** 2 * torch.eye(3, dtype=F64) for r in radii]).to(device)
-    pos = torch.tensor([[0.0, float(r) + 2.03, 0.0] for r in radii], dtype=F64, device=device)
-    spec4 = scenes.grid_on_pole(res=R, steps=12, with_floor=True)
+    pw = scenes.per_world_grid_bodies(W, res=R, seed0=1000, scale=2.0, device=device)
+    spec4 = scenes.cow_on_pole(grid=pw['grid'][0].cpu().numpy(), steps=33)
+    pos = torch.tensor([0.0, 6.0, 0.0], dtype=F64, device=device).expand(W, 3).contiguous()
 
     def build4():
-        params = dict(pos=pos.detach().requires_grad_(True), grid=grids, verts=verts, inertia=inertia)
+        params = dict(pos=pos.detach().clone().requires_grad_(True), **pw)
         return params, scenes.build_world(spec4, device=device, params=params)
-    v, secs = timed(build4, 12, 'pos')
-    out['grid_on_pole'] = {'value': v, 'unit': UNIT, 'worlds': W, 'steps': 12, 'seconds': secs,
-                           'workload': 'config 4 shape: per-world 64^3 f64 grids + per-world meshes (642 v / 1280 f), '
-                                       'pinned pole + floor'}
+    v, secs = timed(build4, 33, 'pos')
+    out['cow_on_pole'] = {'value': v, 'unit': UNIT, 'worlds': W, 'steps': 33, 'seconds': secs,
+                          'workload': 'config 4 as named (demos/demo_meshsdf.py:121-142): per-world 64^3 f64 grids baked from '
+                                      'random-init IGR-style decoders (8x128, skip_in [4], softplus beta 100) + per-world '
+                                      'iso-surface meshes (%d..%d faces), scale 2, pinned pole + 50x1x50 floor (1 040 000 faces), '
+                                      '33 steps, fwd+bwd' % (int(pw['nfaces'].min()), int(pw['nfaces'].max()))}
+    # ---- config 3: 1024 worlds x 16 mixed primitives (120 body pairs), 200 steps, gradients w.r.t. every body's initial
+    # velocity and mass
+    W3, S3 = 1024, 200
+    spec3 = scenes.mixed16(seed=0, steps=S3, spacing=1.05, speed=2.0)
+    vel0 = torch.tensor([b['vel'] for b in spec3['bodies']], dtype=F64)
+    mass0 = torch.tensor([b['mass'] for b in spec3['bodies']], dtype=F64)
+    vel3 = (vel0[None] + 0.2 * torch.randn(W3, 16, 6, generator=g, dtype=F64) * (vel0[None] != 0)).to(device)
+    mass3 = (mass0[None] * (0.9 + 0.2 * torch.rand(W3, 16, generator=g, dtype=F64))).to(device)
+
+    def build3():
+        params = dict(vel_all=vel3.detach().clone().requires_grad_(True), mass_all=mass3.detach().clone().requires_grad_(True))
+        return params, scenes.build_world(spec3, device=device, params=params)
+    v, secs = timed(build3, S3, 'vel_all', reps=1)
+    out['mixed16'] = {'value': v, 'unit': UNIT, 'worlds': W3, 'steps': S3, 'seconds': secs,
+                      'workload': 'config 3: 16 mixed primitives (spheres / boxes / cylinders) per world, free-floating with '
+                                  'random velocities (SURVEY s8d C3, no-gravity variant), all 120 pairs searched, 200-step '
+                                  'rollout + backward to every initial velocity and mass'}
     W5 = 8192
     mass = (0.5 + torch.rand(W5, generator=g, dtype=F64)).to(device)
     spec5 = scenes.inertia_fitting(steps=60)

@@ -126,8 +126,11 @@ class SDF3D(Body3D):
         device = kw.get('device')
         self.scale = as_batched(scale, 0, device)
         self.shape = as_batched(shape, 1, device)
-        verts, faces = mesh
+        # mesh = (verts, faces) or, for per-world topologies, (verts (B,Vmax,3), faces (B,Fmax,3), nverts (B,), nfaces (B,))
+        verts, faces = mesh[0], mesh[1]
         self.verts, self.faces = _mesh_tensors(verts, faces, device)
+        if len(mesh) == 4:
+            self.nverts_w, self.nfaces_w = mesh[2], mesh[3]
         self.sdf_grid = sdf_grid
         super().__init__(pos, **kw)
 

@@ -15,9 +15,9 @@ _GEOM_DTYPE = np.dtype([('kind', 'i4'), ('nverts', 'i4'), ('nfaces', 'i4'), ('re
                         ('faces', 'u8'), ('grid', 'u8'), ('vstride', 'i8'), ('gstride', 'i8'),
                         ('cell_lo', 'f8', (3,)), ('cell_inv', 'f8'), ('cell_dims', 'i4', (3,)), ('has_cells', 'i4'),
                         ('fcell_start', 'u8'), ('fcell_items', 'u8'), ('vcell_start', 'u8'), ('vcell_items', 'u8'),
-                        ('max_face_rad', 'f8')],
+                        ('max_face_rad', 'f8'), ('fstride', 'i8'), ('nfaces_w', 'u8'), ('nverts_w', 'u8')],
                        align=True)
-assert _GEOM_DTYPE.itemsize == 144
+assert _GEOM_DTYPE.itemsize == 168
 
 
 _CELL_CACHE = {}
@@ -90,6 +90,16 @@ class GeometryTable:
             if per_world:
                 assert verts.shape[0] == W
             nverts = verts.shape[-2]
+            # per-world topology: faces (W,F,3) padded to a common F, with the true counts per world
+            fstride, nf_ptr, nv_ptr = 0, 0, 0
+            if faces.dim() == 3:
+                assert per_world and faces.shape[0] == W, 'per-world faces need per-world vertices'
+                nf = getattr(b, 'nfaces_w', None)
+                nv = getattr(b, 'nverts_w', None)
+                nf = (torch.full((W,), faces.shape[1]) if nf is None else torch.as_tensor(nf)).to(device=device, dtype=torch.int32)
+                nv = (torch.full((W,), nverts) if nv is None else torch.as_tensor(nv)).to(device=device, dtype=torch.int32)
+                self.keep += [nf, nv]
+                fstride, nf_ptr, nv_ptr = faces.shape[1] * 3, nf.data_ptr(), nv.data_ptr()
             grid = getattr(b, 'sdf_grid', None)
             res, gptr, gstride = 0, 0, 0
             if grid is not None:
@@ -105,9 +115,9 @@ class GeometryTable:
                 lo, inv, dims, dev_arrays, max_rad = cached_cell_index(verts.cpu().numpy(), faces.cpu().numpy(), device)
                 self.keep += dev_arrays
                 cell = (lo, inv, dims, 1) + tuple(a.data_ptr() for a in dev_arrays)
-            rows[i] = (b.kind, nverts, faces.shape[0], res, verts.data_ptr(), faces.data_ptr(), gptr,
-                       nverts * 3 if per_world else 0, gstride) + cell + (max_rad,)
-            self.nfaces.append(int(faces.shape[0]))
+            rows[i] = (b.kind, nverts, faces.shape[-2], res, verts.data_ptr(), faces.data_ptr(), gptr,
+                       nverts * 3 if per_world else 0, gstride) + cell + (max_rad, fstride, nf_ptr, nv_ptr)
+            self.nfaces.append(int(faces.shape[-2]))
         self.rows = rows
         self.dev = torch.from_numpy(rows.view(np.uint8).copy()).to(device)
 

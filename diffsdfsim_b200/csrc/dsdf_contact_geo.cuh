@@ -19,7 +19,20 @@ struct BodyGeom {                 // mirrors dsdf_body_geom in include/dsdf_b200
     int cell_dims[3], has_cells;
     const int *fcell_start, *fcell_items, *vcell_start, *vcell_items;
     double max_face_rad;          // max_f max_i |centroid_f - v_i|; 0 = unknown (no fp32 pre-filter)
+    // per-world topology (bodies whose mesh differs from world to world, e.g. iso-surfaces of per-world SDF grids):
+    // world w uses faces + w*fstride, nfaces_w[w] faces and nverts_w[w] vertices; NULL / 0 = shared topology
+    long long fstride;
+    const int *nfaces_w, *nverts_w;
 };
+
+// the geometry of body g as world w sees it (topology pointers / counts resolved; vertices stay strided, see load_vert)
+__device__ __forceinline__ BodyGeom world_geom(const BodyGeom& g, int w) {
+    BodyGeom r = g;
+    r.faces = g.faces + (size_t)w * g.fstride;
+    if (g.nfaces_w) r.nfaces = g.nfaces_w[w];
+    if (g.nverts_w) r.nverts = g.nverts_w[w];
+    return r;
+}
 
 // One out-of-line copy of the SDF evaluation for the whole contact kernel: inlining it at ~30 call sites made the
 // kernel 575 KB of SASS, far beyond the instruction cache (ncu: 18 % of stall samples "no_instructions").

@@ -873,7 +873,8 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
         }
         int ov = 0;
         PH_MARK(-1);
-        if (hit) ov = any_vertex_in_cube(geom[bi], wg, qi, xi, qj, xj, sj) && any_vertex_in_cube(geom[bj], wg, qj, xj, qi, xi, si);
+        if (hit) ov = any_vertex_in_cube(world_geom(geom[bi], wg), wg, qi, xi, qj, xj, sj) &&
+                      any_vertex_in_cube(world_geom(geom[bj], wg), wg, qj, xj, qi, xi, si);
         PH_MARK(PH_OVERLAP);
         if (!ov) {
             if (pre_cnt && tid == 0) { pre_cnt[(size_t)w * ndirs + 2 * pair] = -1; pre_cnt[(size_t)w * ndirs + 2 * pair + 1] = -1; }
@@ -882,7 +883,7 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
         for (int rev = 0; rev < 2; ++rev) {
             const int d = 2 * pair + rev;
             const int i1 = rev ? bj : bi, i2 = rev ? bi : bj;
-            const BodyGeom g1 = geom[i1];
+            const BodyGeom g1 = world_geom(geom[i1], wg);
             const SdfShape s1 = body_shape(g1, shape, wg, nb, i1);
             const SdfShape s2 = body_shape(geom[i2], shape, wg, nb, i2);
             const Q4<double> q1 = rev ? qj : qi, q2 = rev ? qi : qj;

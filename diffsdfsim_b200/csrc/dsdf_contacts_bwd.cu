@@ -24,7 +24,7 @@ contact_geometry_bwd_kernel(const BodyGeom* __restrict__ geom, const double* __r
         const int k = item / 14, j = item % 14;
         const size_t oo = (size_t)w * maxc + k;
         const int i1 = cbody[2 * oo], i2 = cbody[2 * oo + 1];
-        const BodyGeom g1 = geom[i1];
+        const BodyGeom g1 = world_geom(geom[i1], wg);
         const SdfShape s1 = body_shape(g1, shape, wg, nb, i1);
         const SdfShape s2 = body_shape(geom[i2], shape, wg, nb, i2);
         const double* P1 = p + ((size_t)w * nb + i1) * 7;

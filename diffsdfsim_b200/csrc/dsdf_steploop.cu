@@ -55,6 +55,7 @@ step_begin_kernel(const __grid_constant__ Args a) {
         int* c = a.ctrl;
         c[CT_ABORT] = 0; c[CT_NACT] = (int)a.W; c[CT_CURSOR] = 0; c[CT_ROUNDS] = 0; c[CT_MAXNSUB] = 0; c[CT_DEFF] = 1;
         c[CT_NNEXT] = 0; c[CT_ANYTOC] = 0; c[CT_LCPSTAT] = 0; c[CT_NVIRT] = 0; c[CT_PENDING] = 0; c[CT_TICKET] = 0;
+        c[CT_CONSTAT] = 0;
         for (int k = 0; k < DSDF_STEP_MAX_SLOTS; ++k) c[CT_SLOTROWS + k] = 0;
         c[CT_SLOTROWS] = (int)a.W;
     }
@@ -243,6 +244,7 @@ step_commit_kernel(const __grid_constant__ Args a) {
                 if (clean) atomicMax(&c[CT_MAXCLEAN], cn);
                 const int ls = a.lcp_status_v[vv];
                 if (ls) atomicOr(&c[CT_LCPSTAT], ls);
+                if (st & DSDF_CON_HULL3D) atomicOr(&c[CT_CONSTAT], DSDF_CON_HULL3D);
             }
         }
     }

@@ -18,6 +18,7 @@ enum {
     CT_PENDING,       // pause bits collected by the commit kernel, promoted to CT_ABORT by its last CTA
     CT_TICKET,        // "last CTA done" ticket of the commit kernel
     CT_MAXCLEAN,      // running max of the accepted contact counts of NON-penetrating states
+    CT_CONSTAT,       // OR of the contact status words of the accepted sub-steps of this step (DSDF_CON_HULL3D ...)
     CT_SLOTROWS = 16, // + k: rows handed out in tape slot k (k >= 1; slot 0 is indexed by world)
     CT_WORDS = 16 + 64
 };

@@ -66,6 +66,8 @@ def make_bodies(spec, device=None, params=None, W=1):
                 grid = params['grid']
                 if 'verts' in params:
                     mesh = (params['verts'], params.get('faces', mesh[1]))
+                    if 'nverts' in params:             # per-world topologies, padded to common sizes
+                        mesh = mesh + (params['nverts'], params['nfaces'])
             inertia = params['inertia'] if (last and 'inertia' in params) else grid_unit_inertia(b)
             ob = B.SDFGrid3D(pos, b['scale'], grid, mesh, inertia=inertia, **kw)
         else:
@@ -272,3 +274,39 @@ def mixed16(seed=0, steps=12, spacing=1.3, speed=1.0, gravity=False, subdivision
             bodies.append(body('cylinder', q + pos, rad=float(0.2 + 0.2 * rng.rand()), height=float(0.4 + 0.4 * rng.rand()),
                                max_tri_length=tri, **kw))
     return scene(bodies, steps=steps)
+
+
+def per_world_grid_bodies(W, res=64, seed0=0, scale=2.0, device=None):
+    """Per-world geometry of ``W`` config-4 bodies: W seeded random-init IGR-style decoders baked to (W,res,res,res) grids,
+    the iso-surface mesh of each grid (vertex / face arrays padded to the largest, true counts alongside) and the
+    unit-mass inertia of each mesh.  Returns the ``params`` entries make_bodies understands for the LAST body:
+    grid, verts, faces, nverts, nfaces, inertia (torch tensors on ``device``)."""
+    import torch
+    from . import igr, meshes
+    grids, vs, fs, Is = [], [], [], []
+    for w in range(W):
+        seed = seed0 + w
+        while True:                      # a fresh decoder occasionally has no (or a clipped) zero level set: draw again
+            g = igr.random_shape_grid(seed, res, latent_scale=0.15, device=device or 'cpu')
+            try:
+                v, f = meshes.surface_nets(g)
+            except AssertionError:
+                f = []
+            if len(f) >= 200:
+                break
+            seed += 100003
+        v = v * scale
+        grids.append(g)
+        vs.append(v)
+        fs.append(f)
+        Is.append(meshes.mesh_inertia(v, f))
+    V, F = max(v.shape[0] for v in vs), max(f.shape[0] for f in fs)
+    verts = np.zeros((W, V, 3))
+    faces = np.zeros((W, F, 3), dtype=np.int32)
+    for w in range(W):
+        verts[w, :vs[w].shape[0]] = vs[w]
+        faces[w, :fs[w].shape[0]] = fs[w]
+    t = lambda a, dt=torch.float64: torch.as_tensor(np.asarray(a), dtype=dt, device=device)
+    return dict(grid=t(np.stack(grids)), verts=t(verts), faces=t(faces, torch.int32),
+                nverts=t([v.shape[0] for v in vs], torch.int32), nfaces=t([f.shape[0] for f in fs], torch.int32),
+                inertia=t(np.stack(Is)))

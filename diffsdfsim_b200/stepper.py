@@ -27,7 +27,9 @@ BASE_TOL = 1e-6      # lcp_physics/physics/utils.py:43 (World.H.backward, world.
 MAX_SLOTS = 64
 STEP_CAPK, STEP_MAXC, STEP_DYN_SMEM, STEP_TAPE, STEP_MAX_ROUNDS = 1, 2, 4, 8, 16
 CT_ABORT, CT_NACT, CT_MAXCOUNT, CT_ROUNDS, CT_MAXNSUB, CT_ANYTOC, CT_LCPSTAT, CT_MAXCLEAN = 0, 1, 3, 4, 5, 8, 9, 13
+CT_CONSTAT = 14
 CT_SLOTROWS, CT_WORDS = 16, 16 + MAX_SLOTS
+CON_HULL3D = 4
 LCP_FACTOR_FAIL, LCP_INACCURATE, LCP_TOO_LARGE = 4, 8, 16
 
 _SLOT_FIELDS = ['world', 'p_in', 'v_in', 'x', 'new_v', 'p_try', 'dt_raw', 'dt_used', 'lam', 's', 'toc_flag_in', 'toc_now',
@@ -331,6 +333,13 @@ class DeviceStepper:
         if ls & LCP_TOO_LARGE:
             raise _lib.DsdfLibraryError('dynamics kernel: a world had more contacts than its shared memory holds')
         world.engine.last_status_bits = ls
+        if c[CT_CONSTAT] & CON_HULL3D:
+            # contacts.py:126-152 runs a 3-D Qhull on such clusters; the device filter keeps all their points instead
+            world.stats['hull3d_steps'] = world.stats.get('hull3d_steps', 0) + 1
+            if world.stats['hull3d_steps'] == 1:
+                import warnings
+                warnings.warn('a normal cluster of more than 4 non-coplanar contact points was kept unfiltered '
+                              '(DSDF_CON_HULL3D): the reference would reduce it to its 3-D convex hull vertices')
         if ls & LCP_INACCURATE and getattr(world.engine, 'verbose', -1) >= 0:
             print('qpth warning: Returning an inaccurate and potentially incorrect solution.')       # batch.py:165,229
         tape.maxsub, tape.any_toc = c[CT_MAXNSUB], bool(c[CT_ANYTOC])

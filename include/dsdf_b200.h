@@ -128,6 +128,11 @@ typedef struct dsdf_body_geom {
      * cheap conservative fp32 bound, faces whose centroid is provably farther than this radius + eps from the other
      * body; everything that survives goes through the exact fp64 test, so results are unchanged. */
     double max_face_rad;
+    /* Per-world topology, for bodies whose mesh differs from world to world (iso-surfaces of per-world SDF grids):
+     * world w uses faces + w*face_world_stride, nfaces_w[w] faces and nverts_w[w] vertices (nfaces / nverts above are then
+     * the allocated maxima).  0 / NULL = one topology shared by all worlds. */
+    long long face_world_stride;
+    const int32_t *nfaces_w, *nverts_w;
 } dsdf_body_geom;
 
 /* per-world contact status bits (int32) */
@@ -339,6 +344,7 @@ int dsdf_contacts_detect_loop(const dsdf_body_geom* geom, const int32_t* pairs, 
 #define DSDF_CTRL_ANYTOC 8
 #define DSDF_CTRL_LCPSTATUS 9
 #define DSDF_CTRL_MAXCLEAN 13
+#define DSDF_CTRL_CONSTATUS 14
 
 typedef struct dsdf_step_slot {      /* tape of the k-th accepted sub-step of this step: one self-contained ROW per world  */
     int64_t cap;                     /* rows allocated.  Slot 0: row = world (cap = W); slot k > 0: rows are handed out  */
