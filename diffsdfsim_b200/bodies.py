@@ -163,6 +163,17 @@ class SDF3D(Body3D):
         return res if len(res) > 1 else res[0]
 
 
+def _check_custom(custom_mesh, custom_inertia):
+    """The reference's defaults are custom_mesh = custom_inertia = False (physics3d/utils.py:56-57): bodies are meshed by
+    128^3 marching cubes (a third-party CUDA extension) and their inertia integrated over that mesh.  Here meshes are
+    hot-path INPUTS: the primitives generate the reference's ``custom_mesh=True`` lattices and closed-form inertias unless
+    ``mesh=`` is passed.  Asking explicitly for the marching-cubes variants is an error rather than a silent difference."""
+    if custom_mesh is False or custom_inertia is False:
+        raise NotImplementedError('custom_mesh=False / custom_inertia=False (marching-cubes mesh + mesh-integrated inertia) '
+                                  'are not built: pass mesh=(verts, faces) (e.g. meshes.surface_nets of a sampled SDF) and, '
+                                  'for grid bodies, inertia=meshes.mesh_inertia(...)')
+
+
 class SDFBox(SDF3D):
     """bodies.py:778-854."""
     kind = BOX
@@ -170,6 +181,7 @@ class SDFBox(SDF3D):
     def __init__(self, pos, dims, vel=(0, 0, 0, 0, 0, 0), mass=1, restitution=Defaults3D.RESTITUTION,
                  fric_coeff=Defaults3D.FRIC_COEFF, eps=Defaults3D.EPSILON, custom_mesh=True, custom_inertia=True,
                  mesh=None, max_tri_length=0.1, device=None, **_ignored):
+        _check_custom(custom_mesh, custom_inertia)
         self.dims = as_batched(dims, 1, device)
         scale = self.dims.max(dim=1)[0] * 1.5 / 2
         if mesh is None:
@@ -196,6 +208,7 @@ class SDFSphere(SDF3D):
     def __init__(self, pos, rad, vel=(0, 0, 0, 0, 0, 0), mass=1, restitution=Defaults3D.RESTITUTION,
                  fric_coeff=Defaults3D.FRIC_COEFF, eps=Defaults3D.EPSILON, custom_mesh=True, custom_inertia=True,
                  mesh=None, subdivisions=4, device=None, **_ignored):
+        _check_custom(custom_mesh, custom_inertia)
         self.rad = as_batched(rad, 0, device)
         scale = self.rad * 1.5
         if mesh is None:
@@ -217,6 +230,7 @@ class SDFCylinder(SDF3D):
     def __init__(self, pos, rad, height, vel=(0, 0, 0, 0, 0, 0), mass=1, restitution=Defaults3D.RESTITUTION,
                  fric_coeff=Defaults3D.FRIC_COEFF, eps=Defaults3D.EPSILON, custom_mesh=True, custom_inertia=True,
                  mesh=None, numsegs=32, max_tri_length=0.1, device=None, **_ignored):
+        _check_custom(custom_mesh, custom_inertia)
         self.rad, self.height = as_batched(rad, 0, device), as_batched(height, 0, device)
         assert self.rad.shape[0] == 1 and self.height.shape[0] == 1, 'per-world cylinder sizes: pass mesh= explicitly'
         scale = torch.max(self.rad, self.height / 2) * 1.5

@@ -136,6 +136,12 @@ step_commit_kernel(const __grid_constant__ Args a) {
         const int k = a.nsub[w];
         // tape row of this sub-step: slot 0 is indexed by world, later slots hand out rows in commit order
         int row = w;
+        if (!pause && win >= 0 && k >= a.n_slots && a.slots_final) {
+            // no tape left for this world (it keeps giving up at dt / 2^10 and would need hundreds of sub-steps): it leaves
+            // the step here, with its time behind the others, and is reported
+            if (lane == 0) { a.active[w] = 0; atomicOr(&c[CT_CONSTAT], DSDF_CON_STALLED); }
+            win = -2;
+        }
         if (!pause && win >= 0) {
             if (k >= a.n_slots) pause |= DSDF_STEP_TAPE;
             else if (k > 0) {
@@ -146,6 +152,7 @@ step_commit_kernel(const __grid_constant__ Args a) {
         }
         if (pause) {
             if (lane == 0) { atomicOr(&c[CT_PENDING], pause); atomicAdd(&c[CT_NNEXT], 1); }
+        } else if (win == -2) {                                 // stalled (above)
         } else if (win < 0) {                                   // every attempt of this round rejected: go on halving
             if (lane == 0) {
                 double dn = a.dt_try[w];

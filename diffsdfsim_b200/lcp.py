@@ -62,6 +62,7 @@ def lcp_backward_raw(Q, G, A, F, x, nu, lam, s, gz, nineq_w=None, need=(True,) *
     ni = G.shape[1]
     neq = A.shape[1] if A is not None and A.numel() > 0 else 0
     dev = Q.device
+    gz = gz.contiguous()
     mk = lambda flag, *shape: torch.empty(*shape, dtype=F64, device=dev) if flag else None
     dQ, dp, dG, dh = mk(need[0], B, nz, nz), mk(need[1], B, nz), mk(need[2], B, ni, nz), mk(need[3], B, ni)
     dA, db = mk(need[4] and neq, B, neq, nz), mk(need[5] and neq, B, neq)
@@ -69,7 +70,7 @@ def lcp_backward_raw(Q, G, A, F, x, nu, lam, s, gz, nineq_w=None, need=(True,) *
     status = torch.zeros(B, dtype=torch.int32, device=dev)
     ws = torch.empty(L.dsdf_lcp_workspace_bytes(B, nz, neq, ni) // 8 + 1, dtype=F64, device=dev)
     rc = _lib.call('dsdf_lcp_backward', _lib.ptr(Q), _lib.ptr(G), _lib.ptr(A) if neq else None, _lib.ptr(F), _lib.ptr(nineq_w),
-                             _lib.ptr(x), _lib.ptr(nu), _lib.ptr(lam), _lib.ptr(s), _lib.ptr(gz.contiguous()),
+                             _lib.ptr(x), _lib.ptr(nu), _lib.ptr(lam), _lib.ptr(s), _lib.ptr(gz),
                              B, nz, neq, ni, int(nineq_smem), _lib.ptr(dQ), _lib.ptr(dp), _lib.ptr(dG), _lib.ptr(dh), _lib.ptr(dA),
                              _lib.ptr(db), _lib.ptr(dF), _lib.ptr(status), _lib.ptr(ws), _lib.stream())
     _lib.check(rc, 'dsdf_lcp_backward')

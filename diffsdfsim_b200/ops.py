@@ -46,8 +46,9 @@ class _SdfQuery(torch.autograd.Function):
         W, N = pts.shape[0], pts.shape[1]
         gpts = torch.empty_like(pts)
         gdir = _c(gdir) if (want_dir and gdir is not None and gdir.numel()) else None
+        gsdf = _c(gsdf)                  # contiguous copies stay bound to locals until the launch has been enqueued
         rc = _lib.call('dsdf_sdf_query_backward', kind, _lib.ptr(shape), _lib.ptr(grid) if kind == 3 else None, res, stride,
-                                       _lib.ptr(pts), W, N, _lib.ptr(_c(gsdf)), _lib.ptr(gdir), _lib.ptr(gpts),
+                                       _lib.ptr(pts), W, N, _lib.ptr(gsdf), _lib.ptr(gdir), _lib.ptr(gpts),
                                        _lib.stream())
         _lib.check(rc, 'dsdf_sdf_query_backward')
         return gpts, None, None, None, None
@@ -84,8 +85,9 @@ class _Integrate(torch.autograd.Function):
         W, nb = p.shape[0], p.shape[1]
         gp, gv = torch.empty_like(p), torch.empty_like(v)
         gdt = torch.empty(W, nb, dtype=F64, device=p.device)
+        g = _c(g)
         rc = _lib.call('dsdf_integrate_backward', _lib.ptr(p), _lib.ptr(v), _lib.ptr(dt), _lib.ptr(active), W, nb,
-                                       _lib.ptr(_c(g)), _lib.ptr(gp), _lib.ptr(gv), _lib.ptr(gdt), _lib.stream())
+                                       _lib.ptr(g), _lib.ptr(gp), _lib.ptr(gv), _lib.ptr(gdt), _lib.stream())
         _lib.check(rc, 'dsdf_integrate_backward')
         return gp, gv, gdt.sum(1), None
 

@@ -29,13 +29,13 @@ STEP_CAPK, STEP_MAXC, STEP_DYN_SMEM, STEP_TAPE, STEP_MAX_ROUNDS = 1, 2, 4, 8, 16
 CT_ABORT, CT_NACT, CT_MAXCOUNT, CT_ROUNDS, CT_MAXNSUB, CT_ANYTOC, CT_LCPSTAT, CT_MAXCLEAN = 0, 1, 3, 4, 5, 8, 9, 13
 CT_CONSTAT = 14
 CT_SLOTROWS, CT_WORDS = 16, 16 + MAX_SLOTS
-CON_HULL3D = 4
+CON_HULL3D, CON_STALLED = 4, 16
 LCP_FACTOR_FAIL, LCP_INACCURATE, LCP_TOO_LARGE = 4, 8, 16
 
 _SLOT_FIELDS = ['world', 'p_in', 'v_in', 'x', 'new_v', 'p_try', 'dt_raw', 'dt_used', 'lam', 's', 'toc_flag_in', 'toc_now',
                 'toc_mask', 'count_in', 'body_in', 'geo_in', 'count', 'body', 'face', 'abc', 'geo']
 _INT_FIELDS = ['W', 'nb', 'neq', 'maxc', 'fric_dirs', 'capK', 'npairs', 'depth', 'spec_threshold', 'depth2',
-               'spec_threshold2', 'vcap', 'n_slots',
+               'spec_threshold2', 'vcap', 'n_slots', 'slots_final',
                'max_iter', 'max_rounds', 'strict', 'toc_enabled', 'fixed_dt', 'detach_b2']
 _DBL_FIELDS = ['world_dt', 'eps', 'tol', 'fd_eps', 'body_eps']
 _PTR_FIELDS = ['geom', 'pairs', 'eq_rows', 'mass', 'Ibody', 'fric', 'rest', 'f', 'shape',
@@ -138,6 +138,13 @@ def acquire_slot(cap, nb, maxc, per, dev):
     return TapeSlot(cap, nb, maxc, per, dev)
 
 
+def clear_slot_pool():
+    """Drop every recycled tape slot (their memory returns to the caching allocator)."""
+    global _slot_pool_bytes
+    _SLOT_POOL.clear()
+    _slot_pool_bytes = 0
+
+
 def release_slot(sl):
     global _slot_pool_bytes
     if _slot_pool_bytes + sl.nbytes > _SLOT_POOL_MAX_BYTES:
@@ -217,6 +224,7 @@ class DeviceStepper:
         a.capK, a.npairs = world.detector.capK, world.detector.npairs
         a.depth, a.spec_threshold, a.vcap, a.n_slots = self.depth, self.spec_threshold, self.vcap, len(tape.slots)
         a.depth2, a.spec_threshold2 = self.depth2, self.spec_threshold2
+        a.slots_final = int(len(tape.slots) >= MAX_SLOTS)
         a.max_iter, a.max_rounds = world.engine.max_iter, world.max_rounds_per_step
         a.strict, a.toc_enabled = int(world.strict_no_pen), int(world.time_of_contact_diff)
         a.fixed_dt, a.detach_b2 = int(fixed_dt), int(world.detach_contact_b2)
@@ -314,6 +322,11 @@ class DeviceStepper:
             self.max_count = max(self.max_count, c[CT_MAXCOUNT])
             self.max_clean = max(self.max_clean, c[CT_MAXCLEAN])
             ab = c[CT_ABORT]
+            if ab & STEP_MAX_ROUNDS and not world.strict_no_pen:
+                # the reference would go on sub-stepping at dt / 2^10; leave these worlds where they are (reported)
+                world.stats['stalled'] = world.stats.get('stalled', 0) + int(c[CT_NACT])
+                self.active.zero_()
+                break
             if ab & STEP_MAX_ROUNDS:
                 stuck = self.active.nonzero().flatten().tolist()[:8]
                 raise RuntimeError('step did not complete in %d attempts: worlds %s keep penetrating (dt < %.3g); '
@@ -333,6 +346,8 @@ class DeviceStepper:
         if ls & LCP_TOO_LARGE:
             raise _lib.DsdfLibraryError('dynamics kernel: a world had more contacts than its shared memory holds')
         world.engine.last_status_bits = ls
+        if c[CT_CONSTAT] & CON_STALLED:
+            world.stats['stalled'] = world.stats.get('stalled', 0) + 1
         if c[CT_CONSTAT] & CON_HULL3D:
             # contacts.py:126-152 runs a 3-D Qhull on such clusters; the device filter keeps all their points instead
             world.stats['hull3d_steps'] = world.stats.get('hull3d_steps', 0) + 1
@@ -390,10 +405,8 @@ class DeviceStepper:
                     tape.slots[k] = sl.regrown(min(self.W, _pow2(2 * rows[k])), world.maxc)
                     rows[k] = sl.cap
             self.ctrl[CT_SLOTROWS:CT_SLOTROWS + MAX_SLOTS].copy_(torch.tensor(rows, dtype=I32), non_blocking=False)
-            if c[CT_MAXNSUB] >= len(tape.slots):
-                if len(tape.slots) >= MAX_SLOTS:
-                    raise RuntimeError('a world accepted more than %d sub-steps inside one step' % MAX_SLOTS)
-                n = min(MAX_SLOTS, len(tape.slots) + 2)
+            if c[CT_MAXNSUB] >= len(tape.slots) and len(tape.slots) < MAX_SLOTS:
+                n = min(MAX_SLOTS, max(len(tape.slots) + 2, len(tape.slots) * 3 // 2))
                 tape.slots += [acquire_slot(self._slot_cap(k), self.nb, world.maxc, per, self.dev)
                                for k in range(len(tape.slots), n)]
         if bits & STEP_DYN_SMEM and self.max_count + 2 > 64:

@@ -86,12 +86,14 @@ class TimeOfContactNative(torch.autograd.Function):
     def backward(ctx, gh):
         dt_, p_try, new_v, geo, f, mass, toc_mask, cbody = ctx.saved_tensors
         W, nb, maxc = p_try.shape[0], p_try.shape[1], geo.shape[1]
-        c = lambda t: t.contiguous()
+        # contiguous copies stay bound to locals until the launch has been enqueued
+        dt_, toc_mask, cbody, p_try, new_v, geo, f, mass, gh = [t.contiguous() for t in
+                                                                (dt_, toc_mask, cbody, p_try, new_v, geo, f, mass, gh)]
         g_dt, gp, gv = torch.empty_like(dt_), torch.empty_like(p_try), torch.empty_like(new_v)
         ggeo, gf, gm = torch.empty_like(geo), torch.empty_like(f), torch.empty_like(mass)
-        rc = _lib.call('dsdf_toc_backward', W, nb, maxc, _lib.ptr(c(dt_)), _lib.ptr(c(toc_mask)), _lib.ptr(c(cbody)),
-                       _lib.ptr(c(p_try)), _lib.ptr(c(new_v)), _lib.ptr(c(geo)), _lib.ptr(c(f)), _lib.ptr(c(mass)),
-                       _lib.ptr(c(gh)), BASE_TOL, _lib.ptr(g_dt), _lib.ptr(gp), _lib.ptr(gv), _lib.ptr(ggeo),
+        rc = _lib.call('dsdf_toc_backward', W, nb, maxc, _lib.ptr(dt_), _lib.ptr(toc_mask), _lib.ptr(cbody),
+                       _lib.ptr(p_try), _lib.ptr(new_v), _lib.ptr(geo), _lib.ptr(f), _lib.ptr(mass),
+                       _lib.ptr(gh), BASE_TOL, _lib.ptr(g_dt), _lib.ptr(gp), _lib.ptr(gv), _lib.ptr(ggeo),
                        _lib.ptr(gf), _lib.ptr(gm), _lib.stream())
         _lib.check(rc, 'dsdf_toc_backward')
         return g_dt, gp, gv, ggeo, gf, gm, None, None
@@ -203,6 +205,11 @@ class World3D:
     def v(self):
         v = self.state.v.reshape(self.W, -1)
         return v if self.batched else v[0]
+
+    @v.setter
+    def v(self, new_v):
+        """The reference's drivers write ``world.v = world.v.detach().clone()`` before ``set_v`` (optim_sphere.py:172-175)."""
+        self.set_v(new_v)
 
     def get_v(self):
         return self.v
@@ -328,6 +335,7 @@ class World3D:
     def _step(self, fixed_dt):
         self._undo = self._snapshot()
         self._f_cache = None
+        t_start = self.t if self.batched else float(self.t[0])
         if self._use_device_loop():
             had = self._step_device(fixed_dt)
         else:
@@ -336,8 +344,10 @@ class World3D:
         # variable-dt step may end early (world.py:134-137), then it is read back from the device (one sync, rare mode)
         self.t_host = self.t_host + self.dt if fixed_dt else float(self.t.max())
         self._sync_bodies()
-        self.trajectory.append((self.t if self.batched else float(self.t[0]), self.get_p(), self.v,
-                                self.contact_set, None))
+        # one entry per step(), stamped like the reference's entries with the time the step STARTED (world.py:372-379
+        # appends (self.t, ...) before self.t += dt; the reference appends once per accepted sub-step, we record the
+        # state at the end of the whole step -- see INTEGRATION.md)
+        self.trajectory.append((t_start, self.get_p(), self.v, self.contact_set, None))
         return had if self.batched else bool(had[0])
 
     def _step_device(self, fixed_dt):

@@ -140,6 +140,7 @@ typedef struct dsdf_body_geom {
 #define DSDF_CON_OVERFLOW       2   /* more contacts than maxc */
 #define DSDF_CON_HULL3D         4   /* a non-planar normal cluster of > 4 points was kept unfiltered */
 #define DSDF_CON_PENETRATION    8   /* some pen > tol: the step attempt will be rejected (world.py:270) */
+#define DSDF_CON_STALLED       16   /* (step loop, ctrl[14] only) a world exhausted the tape slots of one step and left it early */
 
 /* Replaces World.find_contacts (lcp_physics/physics/world.py:396-399) with FWContactHandler
  * (sdf_physics/physics3d/contacts.py:221-272): broad phase (AABB of each body's rotated cube of half side
@@ -364,7 +365,10 @@ typedef struct dsdf_step_args {
     int64_t depth;                   /* attempts (dt, dt/2, ..) evaluated at once when <= spec_threshold worlds are active */
     int64_t spec_threshold;
     int64_t depth2, spec_threshold2; /* a second, deeper level for the nearly empty rounds (depth2 >= depth, threshold2 <= threshold) */
-    int64_t vcap, n_slots, max_iter, max_rounds;
+    int64_t vcap, n_slots;
+    int64_t slots_final;             /* 1: n_slots cannot grow any more -- a world that needs a further slot is STALLED: it
+                                        leaves the step early (its time stays behind) and DSDF_CON_STALLED is reported */
+    int64_t max_iter, max_rounds;
     int64_t strict, toc_enabled, fixed_dt, detach_b2;
     double world_dt, eps, tol, fd_eps, body_eps;
     const dsdf_body_geom* geom; const int32_t* pairs; const int32_t* eq_rows;
