@@ -45,6 +45,36 @@ def trajectory_loss(world, world_target):
     return loss if world.batched else loss[0]
 
 
+def run_world_fixed_dt(world, run_time, detach_2nd_bounce=False):
+    """experiments/trajectory_fitting/optim_sphere.py:163-177: step with fixed dt until ``run_time``; with
+    ``detach_2nd_bounce`` the second step of every bounce (the second consecutive step that had contacts) is undone and
+    the state detached, so that only the first contact step of each bounce is differentiated.  Every world of a batch
+    keeps its own contact-step counter; the undo / detach is applied to the worlds whose counter fires."""
+    W, dev = world.W, world.device
+    num_contact_steps = torch.zeros(W, dtype=torch.int64, device=dev)
+    n_steps = 0
+    # a single world follows the reference's `while world.t < run_time` on the simulated time itself (the sum of its
+    # accepted sub-steps); a batch steps in lock-step on the host clock
+    now = (lambda: float(world.t[0])) if W == 1 else (lambda: world.t_host)
+    while now() < run_time:
+        had = world.step(fixed_dt=True)
+        had = had if isinstance(had, torch.Tensor) else torch.tensor([had], device=dev)
+        n_steps += 1
+        if not detach_2nd_bounce:
+            continue
+        num_contact_steps = num_contact_steps + had.to(torch.int64)
+        fire = had & (num_contact_steps > 1)
+        if bool(fire.any()):                                 # (one host read per step, like the reference's own `if`)
+            if W == 1:
+                world.undo_step()
+                world.detach_state()
+            else:
+                world.undo_step(fire)
+                world.detach_state(fire)
+            num_contact_steps = torch.where(fire, torch.zeros_like(num_contact_steps), num_contact_steps)
+    return n_steps
+
+
 def pointcloud_sdf_loss(body, points_world, pos=None, rot=None):
     """(sum of squared SDF values of the observed points inside the body's cube, number of such points).
 

@@ -395,18 +395,44 @@ class World3D:
         self.stats['rounds'].append(rounds)
         return had
 
-    def undo_step(self):
-        """world.py:106-116.  The contact capacity may have grown during the undone step: the restored set is brought to
-        the current capacity, and the contact-count bound that sizes the dynamics kernel never shrinks."""
+    def undo_step(self, mask=None):
+        """world.py:106-116.  ``mask`` (optional (W,) bool tensor, batched extension): undo the last step only for those
+        worlds -- the others keep their new state (used by the per-world detach-2nd-bounce logic of the fitting drivers).
+        The contact capacity may have grown during the undone step: the restored set is brought to the current capacity,
+        and the contact-count bound that sizes the dynamics kernel never shrinks."""
         st = self.state
-        (st.p, st.v, cs, geo, self.t, self.t_host, self.toc_flag, self.last_dt, ntraj,
-         self._any_toc_flag, max_nc) = self._undo
+        (p0, v0, cs, geo, t0, t_host0, toc0, last0, ntraj, any_toc0, max_nc) = self._undo
         if cs.maxc != self.maxc:
             cs = cs.resized(self.maxc)
             geo = torch.cat([geo, geo.new_zeros(self.W, self.maxc - geo.shape[1], 10)], 1)
-        self.contact_set, self.contact_geo = cs, geo
         self.max_nc = max(int(self.max_nc), int(max_nc))
-        del self.trajectory[ntraj:]
+        if mask is None:
+            st.p, st.v, self.contact_set, self.contact_geo = p0, v0, cs, geo
+            self.t, self.t_host, self.toc_flag, self.last_dt, self._any_toc_flag = t0, t_host0, toc0, last0, any_toc0
+            del self.trajectory[ntraj:]
+        else:
+            m = mask.to(self.device).bool()
+            m3 = m[:, None, None]
+            st.p, st.v = torch.where(m3, p0, st.p), torch.where(m3, v0, st.v)
+            self.contact_geo = torch.where(m3, geo, self.contact_geo)
+            idx = torch.arange(self.W, device=self.device)
+            with self._on_device():
+                self.contact_set = self.contact_set.clone().scatter_from(cs, idx, idx, m.to(torch.uint8))
+            self.t = torch.where(m, t0, self.t)
+            self.toc_flag = torch.where(m, toc0, self.toc_flag)
+            self.last_dt = torch.where(m, last0, self.last_dt)
+        self._sync_bodies()
+
+    def detach_state(self, mask=None):
+        """Cut the autograd history of the poses and velocities (of the masked worlds): what the reference drivers do with
+        ``world.v = world.v.detach().clone(); world.set_v(world.v); world.set_p(cat(b.p.detach()))``
+        (experiments/trajectory_fitting/optim_sphere.py:172-175)."""
+        st = self.state
+        if mask is None:
+            st.p, st.v = st.p.detach().clone(), st.v.detach().clone()
+        else:
+            m3 = mask.to(self.device).bool()[:, None, None]
+            st.p, st.v = torch.where(m3, st.p.detach(), st.p), torch.where(m3, st.v.detach(), st.v)
         self._sync_bodies()
 
     def _attempt(self, active, dt_try, end_t):

@@ -240,12 +240,64 @@ def golden_sdf():
     print('sdf_query', {k: v.shape for k, v in d.items()})
 
 
+def reference_function(path, name, namespace):
+    """Compile ONE function of a reference script without importing the script (the experiment drivers import sacred,
+    tensorboard, pyrender ... at module level): the function's own source, unmodified, executed in `namespace`."""
+    import ast
+    src = open(os.path.join('/root/reference', path)).read()
+    for node in ast.parse(src).body:
+        if isinstance(node, ast.FunctionDef) and node.name == name:
+            node.decorator_list = []
+            mod = ast.Module(body=[node], type_ignores=[])
+            exec(compile(mod, path, 'exec'), namespace)
+            return namespace[name]
+    raise KeyError(name)
+
+
+def golden_detach_2nd_bounce():
+    """The reference's own run_world_fixed_dt(detach_2nd_bounce=True) (experiments/trajectory_fitting/optim_sphere.py:
+    163-177) on a bouncing sphere: final state, number of steps, gradients of |final pos|^2 + |final v|^2 w.r.t. the
+    initial position and velocity (only the first contact step of every bounce is differentiated)."""
+    import io, contextlib
+    run = reference_function('experiments/trajectory_fitting/optim_sphere.py', 'run_world_fixed_dt', {'torch': torch})
+    spec = scenes.bouncing_sphere(floor=(4.0, 1.0, 4.0), steps=0, floor_tri=0.2, height=0.75, subdivisions=3,
+                                  vel=(0, 0, 0, 1.0, 0, 0.3))
+    d = {}
+    for flag in (False, True):
+        pos = torch.tensor([0.0, 0.75, 0.0], dtype=F64, requires_grad=True)
+        vel = torch.tensor([0.0, 0.0, 0.0, 1.0, 0.0, 0.3], dtype=F64, requires_grad=True)
+        world = build_reference(spec, dict(pos=pos, vel=vel))
+        obj = world.bodies[-1]
+        terms, step = [], world.step
+
+        def recording_step(fixed_dt=False):      # the loss is collected after every step() the reference's loop issues
+            had = step(fixed_dt=fixed_dt)
+            terms.append((obj.pos ** 2).sum() + 0.1 * (world.v[-6:] ** 2).sum())
+            return had
+        world.step = recording_step
+        with contextlib.redirect_stdout(io.StringIO()):
+            run(world, 0.8, detach_2nd_bounce=flag)
+        loss = sum(terms)
+        loss.backward()
+        d[k_ := ('detach' if flag else 'plain') + '_nsteps'] = len(terms)
+        k = 'detach' if flag else 'plain'
+        d[k + '_p'] = torch.cat([b.p for b in world.bodies]).detach().numpy()
+        d[k + '_v'] = world.v.detach().numpy()
+        d[k + '_t'] = float(world.t)
+        d[k + '_loss'] = float(loss)
+        d[k + '_gpos'], d[k + '_gvel'] = pos.grad.numpy().copy(), vel.grad.numpy().copy()
+        print('detach_2nd_bounce', flag, 't', float(world.t), 'loss', float(loss), pos.grad.tolist(), vel.grad.tolist())
+    np.savez_compressed(os.path.join(HERE, 'detach_2nd_bounce.npz'), **d)
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     names = sys.argv[1:] or (list(SCENES) + ['sdf_query'])
     for n in names:
         if n == 'sdf_query':
             golden_sdf()
+        elif n == 'detach_2nd_bounce':
+            golden_detach_2nd_bounce()
         else:
             mk, leaves = SCENES[n]
             spec = mk()

@@ -74,3 +74,38 @@ def test_pointcloud_sdf_loss_matches_oracle_query():
     assert int(n) == int(mask.sum())
     np.testing.assert_allclose(float(loss), float(ref), rtol=1e-12)
     np.testing.assert_allclose(pose.grad.cpu().numpy(), pose_c.grad.numpy(), rtol=1e-8, atol=1e-10)
+
+
+@pytest.mark.parametrize('flag', [False, True])
+def test_run_world_fixed_dt_matches_the_reference_function(flag):
+    """losses.run_world_fixed_dt vs the reference's OWN run_world_fixed_dt (experiments/trajectory_fitting/optim_sphere.py:
+    163-177, executed unmodified on the reference World3D by tests/golden/make_golden.py): number of step() calls,
+    final state, and the gradients of a loss collected after every step -- with detach_2nd_bounce the second contact
+    step of a bounce is undone and the history cut there."""
+    import os
+    from diffsdfsim_b200 import scenes
+    from diffsdfsim_b200.losses import run_world_fixed_dt
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'detach_2nd_bounce.npz'))
+    k = 'detach' if flag else 'plain'
+    spec = scenes.bouncing_sphere(floor=(4.0, 1.0, 4.0), steps=0, floor_tri=0.2, height=0.75, subdivisions=3,
+                                  vel=(0, 0, 0, 1.0, 0, 0.3))
+    pos = torch.tensor([[0.0, 0.75, 0.0]], dtype=F64, device='cuda', requires_grad=True)
+    vel = torch.tensor([[0.0, 0.0, 0.0, 1.0, 0.0, 0.3]], dtype=F64, device='cuda', requires_grad=True)
+    world = scenes.build_world(spec, device='cuda', params=dict(pos=pos, vel=vel))
+    terms, step = [], world.step
+
+    def recording_step(fixed_dt=False):
+        had = step(fixed_dt=fixed_dt)
+        terms.append((world.bodies[-1].pos ** 2).sum() + 0.1 * (world.bodies[-1].v ** 2).sum())
+        return had
+    world.step = recording_step
+    run_world_fixed_dt(world, 0.8, detach_2nd_bounce=flag)
+    assert len(terms) == int(g[k + '_nsteps'])
+    loss = sum(terms)
+    loss.backward()
+    np.testing.assert_allclose(world.get_p().detach().cpu().numpy().reshape(-1), g[k + '_p'], atol=1e-9, rtol=0)
+    np.testing.assert_allclose(world.v.detach().cpu().numpy().reshape(-1), g[k + '_v'], atol=1e-7, rtol=0)
+    np.testing.assert_allclose(float(loss), float(g[k + '_loss']), rtol=1e-8)
+    for name, leaf in (('gpos', pos), ('gvel', vel)):
+        ref = g[k + '_' + name]
+        np.testing.assert_allclose(leaf.grad.cpu().numpy().reshape(-1), ref, rtol=1e-5, atol=1e-6 * max(1e-9, np.abs(ref).max()))
