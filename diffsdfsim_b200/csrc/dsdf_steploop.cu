@@ -313,22 +313,34 @@ int dsdf_step_rounds(const dsdf_step_args* a, int n_rounds, int ncontacts_small,
     for (int r = 0; r < n_rounds; ++r) {
         { PhaseTimer t(PHASE_PREP, st); step_prep_kernel<<<(W + 255) / 256, 256, 0, st>>>(*a); }
         PhaseTimer* td = new PhaseTimer(PHASE_DYN, st);
-        // two contact-count classes: worlds with <= ncontacts_small contacts, and (if any) the rest
-        const bool two = ncontacts_large > ncontacts_small;
-        int rc = dsdf_dynamics_solve_loop(a->p, a->v, a->mass, a->Ibody, a->fric, a->rest, a->f, a->dt_used_v, nullptr,
-                                          a->count, a->body, a->geo, a->eq_rows, V, nb, (int)a->neq, (int)a->maxc,
-                                          ncontacts_small, (int)a->fric_dirs, 1e-12, 3, (int)a->max_iter, a->x_v, a->new_v_v,
-                                          a->nu_v, a->lam_v, a->s_v, a->lcp_status_v, a->iters_v, a->vmap, a->ctrl, -1,
-                                          two ? 0 : 1, stream);
-        if (rc) { delete td; return rc; }
-        if (two) {
-            rc = dsdf_dynamics_solve_loop(a->p, a->v, a->mass, a->Ibody, a->fric, a->rest, a->f, a->dt_used_v, nullptr,
-                                          a->count, a->body, a->geo, a->eq_rows, V, nb, (int)a->neq, (int)a->maxc,
-                                          ncontacts_large, (int)a->fric_dirs, 1e-12, 3, (int)a->max_iter, a->x_v,
-                                          a->new_v_v, a->nu_v, a->lam_v, a->s_v, a->lcp_status_v, a->iters_v, a->vmap,
-                                          a->ctrl, ncontacts_small, 1, stream);
-            if (rc) { delete td; return rc; }
+        // contact-count classes: worlds with <= ncontacts_small contacts, and (if any) the rest; worlds with many bodies,
+        // or more contacts than the one-warp kernel holds, go to the one-CTA kernel (dsdf_dynsolve_big.cu)
+        int rc = 0;
+        auto warp_class = [&](int C, int cmin, int last) {
+            return dsdf_dynamics_solve_loop(a->p, a->v, a->mass, a->Ibody, a->fric, a->rest, a->f, a->dt_used_v, nullptr,
+                                            a->count, a->body, a->geo, a->eq_rows, V, nb, (int)a->neq, (int)a->maxc, C,
+                                            (int)a->fric_dirs, 1e-12, 3, (int)a->max_iter, a->x_v, a->new_v_v, a->nu_v,
+                                            a->lam_v, a->s_v, a->lcp_status_v, a->iters_v, a->vmap, a->ctrl, cmin, last, stream);
+        };
+        auto big_class = [&](int C, int cmin) {
+            return dsdf_dynamics_big_solve(a->p, a->v, a->mass, a->Ibody, a->fric, a->rest, a->f, a->dt_used_v, nullptr,
+                                           a->count, a->body, a->geo, a->eq_rows, V, nb, (int)a->neq, (int)a->maxc, C,
+                                           (int)a->fric_dirs, 1e-12, 3, (int)a->max_iter, a->x_v, a->new_v_v, a->nu_v,
+                                           a->lam_v, a->s_v, a->lcp_status_v, a->iters_v, a->vmap, a->ctrl, cmin, 1,
+                                           a->dyn_ws, stream);
+        };
+        if (a->dyn_mode == 1) {
+            rc = big_class(ncontacts_large, -1);
+        } else {
+            const int wl = ncontacts_large > 64 ? 64 : ncontacts_large;          // largest class of the one-warp kernel
+            const int ws_ = ncontacts_small > wl ? wl : ncontacts_small;
+            const bool beyond = a->dyn_mode == 2 && ncontacts_large > 64;
+            const bool two = wl > ws_;
+            rc = warp_class(ws_, -1, (two || beyond) ? 0 : 1);
+            if (!rc && two) rc = warp_class(wl, ws_, beyond ? 0 : 1);
+            if (!rc && beyond) rc = big_class(ncontacts_large, 64);
         }
+        if (rc) { delete td; return rc; }
         delete td;
         { PhaseTimer t(PHASE_MOVE, st); step_integrate_kernel<<<(V * nb + 127) / 128, 128, 0, st>>>(*a); }
         PhaseTimer* tc = new PhaseTimer(PHASE_CONTACTS, st);

@@ -310,3 +310,30 @@ def per_world_grid_bodies(W, res=64, seed0=0, scale=2.0, device=None):
     return dict(grid=t(np.stack(grids)), verts=t(verts), faces=t(faces, torch.int32),
                 nverts=t([v.shape[0] for v in vs], torch.int32), nfaces=t([f.shape[0] for f in fs], torch.int32),
                 inertia=t(np.stack(Is)))
+
+
+def mixed16_floor(seed=0, steps=6, spacing=1.5, floor=(8.0, 1.0, 8.0), floor_tri=0.25, subdivisions=3, tri=0.15, gap=0.01):
+    """The gravity + floor variant of config 3: the 16 mixed primitives of ``mixed16`` set down on a
+    pinned floor slab (4 x 4 layout, ``gap`` above it), gravity on, small random drift.  Boxes rest on 4 + 4 corner
+    contacts, lying cylinders on line contacts, spheres on point contacts: ~80-100 simultaneous contacts per world
+    (nz = 102, 6 equality rows) -- beyond the 64-contact cap of the one-warp dynamics kernel, so this scene runs on
+    dsdf_dynsolve_big.cu.  Body 0 is the floor; per-world masses / velocities via 'mass_all' / 'vel_all' (17 rows)."""
+    rng = np.random.RandomState(seed)
+    bodies = [body('box', [0, -floor[1] / 2, 0], dims=list(floor), pinned=True, fric_coeff=0.3, restitution=0.2,
+                   max_tri_length=floor_tri)]
+    for i in range(16):
+        ix, iz = i % 4, i // 4
+        x, z = (ix - 1.5) * spacing + 0.05 * (rng.rand() - 0.5), (iz - 1.5) * spacing + 0.05 * (rng.rand() - 0.5)
+        vel = [0.0, 0.0, 0.0] + (0.3 * rng.randn(3) * np.array([1.0, 0.0, 1.0])).tolist()
+        kw = dict(vel=vel, fric_coeff=0.3, restitution=0.2, gravity=True, mass=float(0.5 + rng.rand()))
+        kind = i % 3
+        if kind == 0:
+            r = float(0.2 + 0.3 * rng.rand())
+            bodies.append(body('sphere', [x, r + gap, z], rad=r, mesh=dict(subdivisions=subdivisions), **kw))
+        elif kind == 1:
+            d = (0.3 + 0.5 * rng.rand(3)).tolist()
+            bodies.append(body('box', [x, d[1] / 2 + gap, z], dims=d, max_tri_length=tri, **kw))
+        else:
+            r, h = float(0.2 + 0.2 * rng.rand()), float(0.4 + 0.4 * rng.rand())
+            bodies.append(body('cylinder', [x, r + gap, z], rad=r, height=h, max_tri_length=tri, **kw))   # axis = z: lying
+    return scene(bodies, steps=steps)

@@ -242,6 +242,31 @@ int dsdf_dynamics_solve_backward(const double* p, const double* v, const double*
                                  double* gp, double* gv, double* gmass, double* gI, double* gfric, double* grest,
                                  double* gf, double* gdt, double* ggeo, void* stream);
 
+/* The same solver for LARGE worlds -- many bodies and / or hundreds of contacts -- one CTA per world: shared memory holds
+ * what scales with the bodies (free block of the reduced KKT matrix, <= ~120 free velocity components), a caller-provided
+ * global workspace of dsdf_dynamics_big_workspace_bytes(W, ...) bytes holds what scales with the contacts (no cap on
+ * their number), per-body contact lists exploit the body-pair block sparsity of G Q^-1 G'.  Same arguments and semantics
+ * as dsdf_dynamics_solve_loop / dsdf_dynamics_solve_backward_loop (csrc/dsdf_dynsolve_big.cu). */
+size_t dsdf_dynamics_big_smem_bytes(int nb, int neq, int ncontacts, int fric_dirs);
+size_t dsdf_dynamics_big_workspace_bytes(int W, int nb, int neq, int ncontacts, int fric_dirs);
+int dsdf_dynamics_big_solve(const double* p, const double* v, const double* mass, const double* Ibody,
+                            const double* fric, const double* rest, const double* f, const double* dt,
+                            const unsigned char* active, const int32_t* count, const int32_t* cbody, const double* cgeo,
+                            const int32_t* eq_rows, int W, int nb, int neq, int maxc, int ncontacts, int fric_dirs,
+                            double eps, int not_improved_lim, int max_iter,
+                            double* x, double* new_v, double* nu, double* lam, double* s, int32_t* status, int32_t* iters,
+                            const int32_t* vmap, int32_t* ctrl, int count_min, int last_class, double* workspace,
+                            void* stream);
+int dsdf_dynamics_big_solve_backward(const double* p, const double* v, const double* mass, const double* Ibody,
+                                     const double* fric, const double* rest, const double* f, const double* dt,
+                                     const unsigned char* active, const int32_t* count, const int32_t* cbody,
+                                     const double* cgeo, const int32_t* eq_rows, int W, int nb, int neq, int maxc,
+                                     int ncontacts, int fric_dirs, int stop_contact_grad, int stop_friction_grad,
+                                     const double* x, const double* lam, const double* s, const double* g_new_v,
+                                     double* gp, double* gv, double* gmass, double* gI, double* gfric, double* grest,
+                                     double* gf, double* gdt, double* ggeo, int count_min, int last_class,
+                                     double* workspace, void* stream);
+
 /* ------------------------------------------------------ step bookkeeping ----
  * Replaces the accept / reject / halve-dt / remaining-time / time-of-contact control flow of World.step_dt and
  * World.step (lcp_physics/physics/world.py:119-139, 241-356) for all worlds after one attempt
@@ -370,6 +395,8 @@ typedef struct dsdf_step_args {
                                         leaves the step early (its time stays behind) and DSDF_CON_STALLED is reported */
     int64_t max_iter, max_rounds;
     int64_t strict, toc_enabled, fixed_dt, detach_b2;
+    int64_t dyn_mode;                /* 0: one-warp dynamics kernel only (<= 64 contacts); 1: the one-CTA kernel for every
+                                        world (many bodies); 2: one-warp kernel up to 64 contacts, one-CTA kernel above */
     double world_dt, eps, tol, fd_eps, body_eps;
     const dsdf_body_geom* geom; const int32_t* pairs; const int32_t* eq_rows;
     const double *mass, *Ibody, *fric, *rest, *f, *shape;              /* (W,nb..) constant during the step */
@@ -380,6 +407,7 @@ typedef struct dsdf_step_args {
     int32_t *vmap, *vidx; double *dt_raw_v, *dt_used_v;                /* (V), (W), (V), (V) */
     double *x_v, *new_v_v, *nu_v, *lam_v, *s_v, *p_try_v; int32_t *lcp_status_v, *iters_v;
     int32_t *count_v, *status_v, *body_v, *face_v; double *abc_v, *geo_v;
+    double* dyn_ws;                                                    /* workspace of the one-CTA dynamics kernel (V worlds) */
     int32_t* ctrl;                                                     /* int32[16 + DSDF_STEP_MAX_SLOTS] */
     const dsdf_step_slot* slots;                                       /* DEVICE array of n_slots tape slots */
 } dsdf_step_args;

@@ -21,6 +21,8 @@ SCENES = {
                            dict(fric_coeff=0.25, vel=[0.0, 0.0, 0.0, 5.0, 0.0, 0.0], pos=[0.0, 5.0, 0.0])),
     # config 3 shape at size: 16 mixed primitives, every pair searched (nz = 96, no equality rows)
     'c3_mixed16': (lambda: scenes.mixed16(seed=0, steps=12, spacing=1.05, speed=2.0), dict(mass_all=None, vel_all=None)),
+    # config 3, gravity + floor variant: 16 primitives resting on a pinned floor, ~100 simultaneous contacts (nz = 102)
+    'c3_mixed16_floor': (lambda: scenes.mixed16_floor(seed=0, steps=6), dict(mass_all=None, vel_all=None)),
     # config 4 as the demo builds it: 64^3 grid baked from a random-init IGR-style decoder, 50x1x50 floor, scale 2, 33 steps
     'c4_cow_on_pole': (lambda grid=None: scenes.cow_on_pole(grid=grid, res=64, seed=1, steps=33),
                        dict(mass=1.0, fric_coeff=0.15, pos=[0.0, 6.0, 0.0])),

@@ -22,7 +22,10 @@ F64 = torch.float64
 TOL = {'box_on_plane': (1e-8, 1e-5), 'bouncing_sphere': (1e-8, 1e-4), 'grid_on_pole': (1e-8, 1e-4),
        'box_tilted': (2e-2, None), 'mixed_primitives': (1e-6, 5e-3),
        # BASELINE configurations at their named sizes (see tests/test_oracle_golden.py for the tolerances)
-       'c1_bouncing_sphere': (5e-6, 5e-3), 'c3_mixed16': (1e-6, 1e-5), 'c4_cow_on_pole': (1e-6, 1e-5)}
+       'c1_bouncing_sphere': (5e-6, 5e-3), 'c3_mixed16': (1e-6, 1e-5), 'c4_cow_on_pole': (1e-6, 1e-5),
+       # ~75 simultaneous contacts (760 inequality rows): the reference's 10 interior-point iterations leave residuals of
+       # ~1e-4 in the velocities, so algebraically equivalent solvers differ by that much (attempt counts stay identical)
+       'c3_mixed16_floor': (2e-5, 1e-2)}
 
 
 def _params(leaves, g, W=1):
@@ -64,7 +67,7 @@ def test_single_world_rollout_matches_reference_golden(name):
         print('  per-step pose drift vs the reference:', ' '.join('%.1e' % d[0] for d in drift))
         print('  solver attempts (ours / reference):', tries_log, [int(t) for t in g['tries']])
     np.testing.assert_allclose(float(loss), float(g['loss']),
-                               rtol={'box_tilted': 1e-2, 'mixed_primitives': 1e-5, 'c3_mixed16': 1e-5}.get(name, 1e-6))
+                               rtol={'box_tilted': 1e-2, 'mixed_primitives': 1e-5, 'c3_mixed16': 1e-5, 'c3_mixed16_floor': 1e-5}.get(name, 1e-6))
     if grtol is None:
         return
     loss.backward()
