@@ -140,7 +140,7 @@ __device__ __forceinline__ bool face_is_candidate(const BodyGeom& g1, int w, int
 // A face can only pass if sdf2(centroid) < rad_f + eps <= max_face_rad + eps, and the analytic SDFs are exact distance
 // fields (1-Lipschitz), so a single-precision evaluation with a margin far above its rounding error discards the
 // clearly-far faces first.  Survivors -- every true candidate among them -- still take the exact fp64 test.
-struct Pre32 { float R[9], t[3]; float a, b, c, scale, thresh; int kind; bool on; };
+struct Pre32 { float R[9], t[3]; float a, b, c, scale, thresh, margin, eps; int kind; bool on; };
 
 __device__ __forceinline__ Pre32 make_pre32(const BodyGeom& g1, const SdfShape& s2, Q4<double> q1, V3<double> x1,
                                             Q4<double> q2, V3<double> x2, double eps) {
@@ -160,28 +160,38 @@ __device__ __forceinline__ Pre32 make_pre32(const BodyGeom& g1, const SdfShape& 
     const double ext = 1.0 / g1.cell_inv * (g1.cell_dims[0] + g1.cell_dims[1] + g1.cell_dims[2]);
     const double margin = 1e-4 * (1.0 + amax + ext + s2.scale);
     P.thresh = (float)(g1.max_face_rad * 1.001 + eps + margin);
+    P.margin = (float)margin;
+    P.eps = (float)eps;
     return P;
 }
-// true = provably not a candidate
-__device__ __forceinline__ bool pre32_reject(const Pre32& P, float cx, float cy, float cz) {
+// Single-precision SDF of body 2 at the centroid (cx,cy,cz) given in body 1's frame, times scale; `sure_ok` = the point
+// is clearly inside body 2's cube and clearly away from the places where the reference's direction vanishes (sphere
+// centre, cylinder axis), so that "small distance" alone decides the exact candidate test.
+__device__ __forceinline__ float pre32_dist(const Pre32& P, float cx, float cy, float cz, bool& sure_ok) {
     const float px = P.R[0] * cx + P.R[1] * cy + P.R[2] * cz + P.t[0];
     const float py = P.R[3] * cx + P.R[4] * cy + P.R[5] * cz + P.t[1];
     const float pz = P.R[6] * cx + P.R[7] * cy + P.R[8] * cz + P.t[2];
     const float is = 1.0f / P.scale;
     const float ux = px * is, uy = py * is, uz = pz * is;
+    const float lim = P.scale - P.margin;
+    sure_ok = fabsf(px) < lim && fabsf(py) < lim && fabsf(pz) < lim;
     float d;
     if (P.kind == DSDF_SDF_BOX) {
         const float qx = fabsf(ux) - 0.5f * P.a, qy = fabsf(uy) - 0.5f * P.b, qz = fabsf(uz) - 0.5f * P.c;
         const float ox = fmaxf(qx, 0.f), oy = fmaxf(qy, 0.f), oz = fmaxf(qz, 0.f);
         d = sqrtf(ox * ox + oy * oy + oz * oz) + fminf(fmaxf(qx, fmaxf(qy, qz)), 0.f);
     } else if (P.kind == DSDF_SDF_SPHERE) {
-        d = sqrtf(ux * ux + uy * uy + uz * uz) - P.a;
+        const float r = sqrtf(ux * ux + uy * uy + uz * uz);
+        d = r - P.a;
+        sure_ok = sure_ok && r > 1e-3f;
     } else {                                                    // cylinder along local z
-        const float q0 = sqrtf(ux * ux + uy * uy) - P.a, q1 = fabsf(uz) - 0.5f * P.b;
+        const float rho = sqrtf(ux * ux + uy * uy);
+        const float q0 = rho - P.a, q1 = fabsf(uz) - 0.5f * P.b;
         const float o0 = fmaxf(q0, 0.f), o1 = fmaxf(q1, 0.f);
         d = sqrtf(o0 * o0 + o1 * o1) + fminf(fmaxf(q0, q1), 0.f);
+        sure_ok = sure_ok && rho > 1e-3f;
     }
-    return d * P.scale > P.thresh;
+    return d * P.scale;
 }
 
 // Centroid candidate pass of one search direction into the shared list ids[0..capK) (unsorted); returns the count
@@ -222,14 +232,29 @@ __device__ int gather_candidates(const BodyGeom& g1, int w, const SdfShape& s2, 
                 for (int k0 = s; k0 < e; k0 += 32) {
                     const int k = k0 + lane;
                     const int f = k < e ? g1.fcell_items[k] : 0;
-                    bool test = k < e;
+                    bool test = k < e, sure = false;
                     if (test && P32.on) {
+                        // single precision decides the CLEAR cases both ways (far: not a candidate; well inside the
+                        // threshold, as every face under a resting body is: a candidate); only the band of width
+                        // 2 * margin around sdf = rad + eps takes the exact fp64 test, so the result set is unchanged
                         const V3<double> a = load_vert(g1, w, g1.faces[3 * f]), b = load_vert(g1, w, g1.faces[3 * f + 1]),
                                          c = load_vert(g1, w, g1.faces[3 * f + 2]);
-                        test = !pre32_reject(P32, (float)((a.x + b.x + c.x) * (1.0 / 3.0)), (float)((a.y + b.y + c.y) * (1.0 / 3.0)),
-                                             (float)((a.z + b.z + c.z) * (1.0 / 3.0)));
+                        const float ax = (float)a.x, ay = (float)a.y, az = (float)a.z, bx = (float)b.x, by = (float)b.y,
+                                    bz = (float)b.z, cx = (float)c.x, cy = (float)c.y, cz = (float)c.z;
+                        const float mx = (float)((a.x + b.x + c.x) * (1.0 / 3.0)), my = (float)((a.y + b.y + c.y) * (1.0 / 3.0)),
+                                    mz = (float)((a.z + b.z + c.z) * (1.0 / 3.0));
+                        bool ok;
+                        const float d = pre32_dist(P32, mx, my, mz, ok);
+                        if (d > P32.thresh) test = false;
+                        else {
+                            const float ra = (ax - mx) * (ax - mx) + (ay - my) * (ay - my) + (az - mz) * (az - mz);
+                            const float rb = (bx - mx) * (bx - mx) + (by - my) * (by - my) + (bz - mz) * (bz - mz);
+                            const float rc = (cx - mx) * (cx - mx) + (cy - my) * (cy - my) + (cz - mz) * (cz - mz);
+                            const float rad = sqrtf(fmaxf(ra, fmaxf(rb, rc)));
+                            sure = ok && (d + 2.0f * P32.margin < rad * 0.999f + P32.eps);
+                        }
                     }
-                    push(test && face_is_candidate(g1, w, f, s2, q1, x1, q2i, x2, eps), f);
+                    push(sure || (test && face_is_candidate(g1, w, f, s2, q1, x1, q2i, x2, eps)), f);
                 }
             }
         }
@@ -322,6 +347,33 @@ __device__ __noinline__ void block_exclusive_scan(int* buf, int n, int* total) {
 __device__ __noinline__ double bred_sum(double v, double* red) { return block_reduce<RED_SUM>(v, red); }
 __device__ __noinline__ double bred_min(double v, double* red) { return block_reduce<RED_MIN>(v, red); }
 __device__ __noinline__ double bred_max(double v, double* red) { return block_reduce<RED_MAX>(v, red); }
+
+// Up to 8 reductions behind ONE pair of barriers (same shuffle trees as block_reduce, so every result keeps its bits):
+// the hull filter is a chain of tiny block-wide reductions over a few hundred points, dominated by barrier latency.
+// ops[i] in {RED_SUM, RED_MIN, RED_MAX}; red: >= 40 doubles; blockDim.x <= 128 (4 warps x 8 values + 8 results).
+__device__ __noinline__ void bred_multi(double* v, const int* ops, int n, double* red) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    for (int i = 0; i < n; ++i) {
+        double x = v[i];
+        x = ops[i] == RED_SUM ? warp_sum(x) : (ops[i] == RED_MIN ? warp_min(x) : warp_max(x));
+        v[i] = x;
+    }
+    __syncthreads();
+    if (lane == 0) for (int i = 0; i < n; ++i) red[warp * 8 + i] = v[i];
+    __syncthreads();
+    if (warp == 0) {
+        for (int i = 0; i < n; ++i) {
+            const double id = ops[i] == RED_SUM ? 0.0 : (ops[i] == RED_MIN ? INFINITY : -INFINITY);
+            double t = lane < nw ? red[lane * 8 + i] : id;
+            t = ops[i] == RED_SUM ? warp_sum(t) : (ops[i] == RED_MIN ? warp_min(t) : warp_max(t));
+            if (lane == 0) v[i] = t;
+        }
+    }
+    __syncthreads();
+    if (warp == 0 && lane == 0) for (int i = 0; i < n; ++i) red[32 + i] = v[i];
+    __syncthreads();
+    for (int i = 0; i < n; ++i) v[i] = red[32 + i];
+}
 
 // ------------------------------------------------------------------------------------------ refine kernel
 struct RefineSmem {
@@ -586,8 +638,12 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
             s0 += PX[k]; s1 += PY[k]; s2 += PZ[k];
             mx = fmax(mx, fmax(fabs(PX[k]), fmax(fabs(PY[k]), fabs(PZ[k]))));
         }
-        s0 = bred_sum(s0, sm.red); s1 = bred_sum(s1, sm.red);
-        s2 = bred_sum(s2, sm.red); mx = bred_max(mx, sm.red);
+        {
+            double rv[4] = {s0, s1, s2, mx};
+            const int ro[4] = {RED_SUM, RED_SUM, RED_SUM, RED_MAX};
+            bred_multi(rv, ro, 4, sm.red);
+            s0 = rv[0]; s1 = rv[1]; s2 = rv[2]; mx = rv[3];
+        }
         const double m0 = s0 / m, m1 = s1 / m, m2 = s2 / m;
         double v0 = 0, v1 = 0, v2 = 0;
         for (int e = tid; e < m; e += nt) {
@@ -595,9 +651,12 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
             v0 += (PX[k] - m0) * (PX[k] - m0); v1 += (PY[k] - m1) * (PY[k] - m1); v2 += (PZ[k] - m2) * (PZ[k] - m2);
         }
         double var[3];
-        var[0] = bred_sum(v0, sm.red) / (m - 1);
-        var[1] = bred_sum(v1, sm.red) / (m - 1);
-        var[2] = bred_sum(v2, sm.red) / (m - 1);
+        {
+            double rv[3] = {v0, v1, v2};
+            const int ro[3] = {RED_SUM, RED_SUM, RED_SUM};
+            bred_multi(rv, ro, 3, sm.red);
+            var[0] = rv[0] / (m - 1); var[1] = rv[1] / (m - 1); var[2] = rv[2] / (m - 1);
+        }
         // axis order: amin = first argmin (dropped first), then of the remaining two the first argmin is dropped next
         int amin = 0;
         if (var[1] < var[amin]) amin = 1;
@@ -609,7 +668,12 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
         // extremes along the 1-D axis (first min / first max index, like argmin/argmax)
         double lo = INFINITY, hi = -INFINITY;
         for (int e = tid; e < m; e += nt) { const double c = PA[keep1][sm.HI[e]]; lo = fmin(lo, c); hi = fmax(hi, c); }
-        lo = bred_min(lo, sm.red); hi = bred_max(hi, sm.red);
+        {
+            double rv[2] = {lo, hi};
+            const int ro[2] = {RED_MIN, RED_MAX};
+            bred_multi(rv, ro, 2, sm.red);
+            lo = rv[0]; hi = rv[1];
+        }
         __shared__ int s_lo, s_hi;
         if (tid == 0) { s_lo = 0x7fffffff; s_hi = 0x7fffffff; }
         __syncthreads();
@@ -684,8 +748,12 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
                 fd2 = fmax(fd2, l2 > 0 ? fdiv(fabs(cr), l2) : fsqrt((px - ax_) * (px - ax_) + (py - ay_) * (py - ay_)));
                 mx2 = fmax(mx2, fmax(fabs(px), fabs(py)));
             }
-            fd2 = bred_max(fd2, sm.red);
-            mx2 = bred_max(mx2, sm.red);
+            {
+                double rv[2] = {fd2, mx2};
+                const int ro[2] = {RED_MAX, RED_MAX};
+                bred_multi(rv, ro, 2, sm.red);
+                fd2 = rv[0]; mx2 = rv[1];
+            }
             line2 = !(fd2 > 3.0 * distround(2, mx2));
         }
         if (line2) {

@@ -87,6 +87,6 @@ def test_more_than_64_contacts_per_world():
         assert world._stepper.dyn_mode == 1
         assert int(world.contact_set.count.max()) > 64, 'the scene must exceed 64 contacts'
         assert torch.isfinite(vel.grad).all() and float(vel.grad.abs().sum()) > 0
-        outs.append((world.get_p().detach()[0].clone(), vel.grad[0].clone(), world.contact_set.count[0].clone()))
+        outs.append((world.state.p.detach()[0].clone(), vel.grad[0].clone(), world.contact_set.count[0].clone()))
     assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][2], outs[1][2])
     np.testing.assert_allclose(outs[0][1].cpu().numpy(), outs[1][1].cpu().numpy(), rtol=1e-9, atol=1e-12)
