@@ -30,6 +30,7 @@ SIGNATURES = {
     'dsdf_contacts_phase_cycles': (c_i, [c_p, c_i]),
     'dsdf_contact_geometry_backward': (c_i, [c_p, c_p, c_p, c_i, c_i, c_d, c_i, c_i] + [c_p] * 7),
     'dsdf_contact_geometry_backward_rows': (c_i, [c_p, c_p, c_p, c_i, c_i, c_d, c_i, c_i] + [c_p] * 8),
+    'dsdf_contact_geometry_backward_full': (c_i, [c_p, c_p, c_p, c_i, c_i, c_d, c_i, c_i] + [c_p] * 10),
     'dsdf_dynamics_assemble': (c_i, [c_p] * 12 + [c_i] * 4 + [c_p] * 7),
     'dsdf_dynamics_assemble_backward': (c_i, [c_p] * 12 + [c_i] * 6 + [c_p] * 17),
     'dsdf_dynamics_solve_smem_bytes': (c_sz, [c_i] * 4),
@@ -81,7 +82,7 @@ KERNELS_PER_CALL = {
     'dsdf_integrate': 1, 'dsdf_integrate_backward': 1, 'dsdf_contacts_detect': 1,
     'dsdf_contact_geometry_backward': 1, 'dsdf_dynamics_assemble': 1, 'dsdf_dynamics_assemble_backward': 1,
     'dsdf_dynamics_solve': 1, 'dsdf_dynamics_solve_backward': 1, 'dsdf_attempt_commit': 1, 'dsdf_toc_backward': 1, 'dsdf_contactset_move': 1,
-    'dsdf_step_begin': 1, 'dsdf_step_resume': 1, 'dsdf_step_rounds': 0, 'dsdf_dynamics_solve_backward_loop': 1, 'dsdf_dynamics_big_solve': 1, 'dsdf_dynamics_big_solve_backward': 1, 'dsdf_contact_geometry_backward_rows': 1,      # rounds: counted by the stepper (5 per round)
+    'dsdf_step_begin': 1, 'dsdf_step_resume': 1, 'dsdf_step_rounds': 0, 'dsdf_dynamics_solve_backward_loop': 1, 'dsdf_dynamics_big_solve': 1, 'dsdf_dynamics_big_solve_backward': 1, 'dsdf_contact_geometry_backward_rows': 1, 'dsdf_contact_geometry_backward_full': 1,      # rounds: counted by the stepper (5 per round)
 }
 PROFILE = None      # set to {} to record (start, end) CUDA events around every entry-point call
 LAUNCHES = {}       # name -> number of calls since reset_counters()

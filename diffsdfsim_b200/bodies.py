@@ -187,6 +187,11 @@ class SDFBox(SDF3D):
         if mesh is None:
             if self.dims.shape[0] == 1:
                 mesh = meshes.box_mesh(self.dims[0].tolist(), max_tri_length)
+                if self.dims.requires_grad:
+                    # differentiable lattice (the reference builds its custom mesh from `dims` with torch ops,
+                    # bodies.py:799-854): same values (x * (d / d) = x), gradient d vert / d dims = vert / dims
+                    v = torch.as_tensor(np.array(mesh[0]), dtype=F64, device=self.dims.device)
+                    mesh = (v * (self.dims[0] / self.dims[0].detach()), mesh[1])
             else:   # per-world dims: same lattice topology (from the largest box), vertices scaled per world
                 ref = self.dims.max(dim=0)[0]
                 v, f = meshes.box_mesh(ref.tolist(), max_tri_length)

@@ -83,6 +83,8 @@ class GeometryTable:
         self.keep = []
         rows = np.zeros(len(bodies), dtype=_GEOM_DTYPE)
         self.nfaces = []
+        self.faces = []                      # per body: (F,3) or (W,F,3) int32 on the device
+        self.vert_leaf_ids = [i for i, b in enumerate(bodies) if b.verts.requires_grad]
         for i, b in enumerate(bodies):
             verts = b.verts.to(device=device, dtype=F64).contiguous()
             faces = b.faces.to(device=device, dtype=torch.int32).contiguous()
@@ -109,10 +111,12 @@ class GeometryTable:
                 gptr = grid.data_ptr()
                 self.keep.append(grid)
             self.keep += [verts, faces]
+            self.faces.append(faces)
             cell = (np.zeros(3), 0.0, np.zeros(3, dtype=np.int32), 0, 0, 0, 0, 0)
             max_rad = 0.0
             if not per_world:
-                lo, inv, dims, dev_arrays, max_rad = cached_cell_index(verts.cpu().numpy(), faces.cpu().numpy(), device)
+                lo, inv, dims, dev_arrays, max_rad = cached_cell_index(verts.detach().cpu().numpy(), faces.cpu().numpy(),
+                                                                       device)
                 self.keep += dev_arrays
                 cell = (lo, inv, dims, 1) + tuple(a.data_ptr() for a in dev_arrays)
             rows[i] = (b.kind, nverts, faces.shape[-2], res, verts.data_ptr(), faces.data_ptr(), gptr,
@@ -218,40 +222,83 @@ class ContactDetector:
         return out
 
 
+def geometry_vjp(table, p, shape, count, body, face, abc, ggeo, fd_eps, detach_b2, wmap=None, want_shape=False):
+    """VJP of the contact tuples [n, p1, p2, pen] (contacts.py:262-264) for a batch of rows: gp (R,nb,7) and, with
+    ``want_shape``, gshape (R,nb,4) = d/d[a,b,c,scale] and gctri (R,maxc,3) = gradient w.r.t. the body-frame point
+    sum(abc * face vertices) on the mesh body of each contact.  ``wmap`` (R,) int32: world of each row (None: row = world)."""
+    R, nb, maxc = p.shape[0], p.shape[1], body.shape[1]
+    gp = torch.empty_like(p)
+    gshape = torch.empty(R, nb, 4, dtype=F64, device=p.device) if want_shape else None
+    gctri = torch.empty(R, maxc, 3, dtype=F64, device=p.device) if want_shape else None
+    ggeo = ggeo.contiguous()
+    rc = _lib.call('dsdf_contact_geometry_backward_full', table.ptr(), _lib.ptr(p), _lib.ptr(shape), R, nb, fd_eps,
+                   int(detach_b2), maxc, _lib.ptr(count), _lib.ptr(body), _lib.ptr(face), _lib.ptr(abc), _lib.ptr(ggeo),
+                   _lib.ptr(gp), _lib.ptr(wmap), _lib.ptr(gshape), _lib.ptr(gctri), _lib.stream())
+    _lib.check(rc, 'dsdf_contact_geometry_backward')
+    return gp, gshape, gctri
+
+
+def scatter_vertex_grads(grads, leaves, table, gctri, count, body, face, abc, worlds=None):
+    """Accumulate d loss / d vertices from gctri: c_tri = sum_i abc_i * verts[faces[face, i]] on the mesh body (body[...,0])
+    of every contact.  ``leaves`` = [(body index, verts tensor)], ``grads`` the matching accumulators ((V,3) shared or
+    (W,V,3) per world); ``worlds`` (R,) long: world of each row (None: row = world)."""
+    R, maxc = face.shape
+    live = torch.arange(maxc, device=face.device)[None, :] < count[:, None].clamp(max=maxc)
+    for (b, verts), g in zip(leaves, grads):
+        m = live & (body[..., 0] == b)
+        faces_b = table.faces[b]                                        # (F,3) shared or (W,F,3)
+        fidx = face.long().clamp(min=0)
+        if faces_b.dim() == 3:
+            wsel = (worlds if worlds is not None else torch.arange(R, device=face.device))[:, None].expand(R, maxc)
+            vids = faces_b[wsel, fidx.clamp(max=faces_b.shape[1] - 1)].long()     # (R,maxc,3)
+        else:
+            vids = faces_b[fidx.clamp(max=faces_b.shape[0] - 1)].long()
+        contrib = abc[..., :, None] * gctri[..., None, :] * m[..., None, None].to(gctri.dtype)   # (R,maxc,3 verts,3)
+        if verts.dim() == 3:                                            # per-world vertices
+            V = verts.shape[1]
+            wsel = (worlds if worlds is not None else torch.arange(R, device=face.device))[:, None, None]
+            g.view(-1, 3).index_add_(0, (wsel * V + vids).reshape(-1), contrib.reshape(-1, 3))
+        else:
+            g.index_add_(0, vids.reshape(-1), contrib.reshape(-1, 3))
+
+
 class _ContactGeometry(torch.autograd.Function):
-    """Attach the detected contact geometry to the autograd graph of the poses.
+    """Attach the detected contact geometry to the autograd graph of the poses (and, when they carry gradients, of the
+    shape parameters and mesh vertices).
 
     Forward returns the values the detection pass already computed (identical arithmetic to the reference's
-    second, grad-enabled ``_compute_contacts``, contacts.py:262-264); backward is its VJP w.r.t. the poses.
+    second, grad-enabled ``_compute_contacts``, contacts.py:262-264); backward is its VJP.
     """
 
     @staticmethod
-    def forward(ctx, p, shape, geo, count, body, face, abc, table, fd_eps, detach_b2):
+    def forward(ctx, p, shape, geo, count, body, face, abc, table, fd_eps, detach_b2, shape_t, *verts):
         ctx.save_for_backward(p, shape, count, body, face, abc)
         ctx.table, ctx.fd_eps, ctx.detach_b2 = table, fd_eps, detach_b2
+        ctx.want_shape = shape_t is not None
+        ctx.leaves = [(i, v) for i, v in zip(table.vert_leaf_ids, verts)]
         return geo.clone()
 
     @staticmethod
     def backward(ctx, ggeo):
-        L = _lib.lib()
         p, shape, count, body, face, abc = ctx.saved_tensors
-        W, nb = p.shape[0], p.shape[1]
-        gp = torch.empty_like(p)
-        rc = _lib.call('dsdf_contact_geometry_backward', ctx.table.ptr(), _lib.ptr(p), _lib.ptr(shape), W, nb, ctx.fd_eps,
-                                              int(ctx.detach_b2), geo_cap(body), _lib.ptr(count), _lib.ptr(body),
-                                              _lib.ptr(face), _lib.ptr(abc), _lib.ptr(ggeo.contiguous()), _lib.ptr(gp),
-                                              _lib.stream())
-        _lib.check(rc, 'dsdf_contact_geometry_backward')
-        return (gp,) + (None,) * 9
+        gp, gshape, gctri = geometry_vjp(ctx.table, p, shape, count, body, face, abc, ggeo, ctx.fd_eps, ctx.detach_b2,
+                                         None, ctx.want_shape)
+        gverts = []
+        if ctx.leaves:
+            gverts = [torch.zeros_like(v) for _, v in ctx.leaves]
+            scatter_vertex_grads(gverts, ctx.leaves, ctx.table, gctri, count, body, face, abc)
+        return (gp,) + (None,) * 9 + (gshape,) + tuple(gverts)
 
 
 def geo_cap(body):
     return body.shape[1]
 
 
-def differentiable_geometry(p, shape, cs, table, fd_eps=1e-3, detach_b2=False):
-    """(W,maxc,10) contact geometry [n,p1,p2,pen] connected to ``p`` for autograd."""
-    return _ContactGeometry.apply(p, shape, cs.geo, cs.count, cs.body, cs.face, cs.abc, table, fd_eps, detach_b2)
+def differentiable_geometry(p, shape, cs, table, fd_eps=1e-3, detach_b2=False, shape_t=None, verts=()):
+    """(W,maxc,10) contact geometry [n,p1,p2,pen] connected to ``p`` (and to ``shape_t`` (W,nb,4) / the vertex tensors
+    ``verts`` of the bodies listed in table.vert_leaf_ids, when given) for autograd."""
+    return _ContactGeometry.apply(p, shape, cs.geo, cs.count, cs.body, cs.face, cs.abc, table, fd_eps, detach_b2,
+                                  shape_t, *verts)
 
 
 class FWContactHandler:

@@ -74,10 +74,13 @@ __device__ __forceinline__ V3<double> to_b2(V3<double> v, Q4<double> q1, V3<doub
 template <class S> struct ContactGeo { V3<S> n, p1, p2; S pen; };
 
 __device__ __forceinline__ SdfOut<double> sdf_qs(const SdfShape& sh, V3<double> p, bool want_n) { return sdf_q(sh, p, want_n); }
-__device__ __forceinline__ SdfOut<Dual> sdf_qs(const SdfShape& sh, V3<Dual> p, bool want_n) { return sdf_query<Dual>(sh, p, want_n); }
+template <class P> __device__ __forceinline__ SdfOut<Dual> sdf_qs(const SdfShapeT<P>& sh, V3<Dual> p, bool want_n) {
+    return sdf_query<Dual>(sh, p, want_n);
+}
 template <class S> __device__ __forceinline__ V3<S> lift(V3<double> a, S proto) {
     return v3<S>(cst(proto, a.x), cst(proto, a.y), cst(proto, a.z));
 }
+__device__ __forceinline__ V3<Dual> lift(V3<Dual> a, Dual) { return a; }
 __device__ __forceinline__ V3<double> strip(V3<double> a) { return a; }
 __device__ __forceinline__ V3<Dual> strip(V3<Dual> a) { return v3<Dual>(Dual(a.x.v), Dual(a.y.v), Dual(a.z.v)); }
 
@@ -93,12 +96,14 @@ DSDF_GEO_FN double laplacian_fd(SdfShape s, V3<double> c, double d0, double h) {
     return acc;
 }
 
-// contacts.py:161-214 for one contact; c_tri = sum(abc * local verts of the face) is pose-independent.
-template <class S>
-__device__ ContactGeo<S> contact_geometry(const SdfShape& s1, const SdfShape& s2, Q4<S> q1, V3<S> x1, Q4<S> q2, V3<S> x2,
-                                          V3<double> c_tri, double fd_eps, bool detach_b2) {
+// contacts.py:161-214 for one contact; c_tri = sum(abc * local verts of the face) depends on the pose of neither body
+// (but on b1's vertices: V3<Dual> when the derivative w.r.t. the mesh is wanted).  P: double, or Dual to differentiate
+// through the shape parameters as well.
+template <class S, class P, class T>
+__device__ ContactGeo<S> contact_geometry(const SdfShapeT<P>& s1, const SdfShapeT<P>& s2, Q4<S> q1, V3<S> x1, Q4<S> q2,
+                                          V3<S> x2, V3<T> c_tri, double fd_eps, bool detach_b2) {
     S proto = q1.w;
-    V3<S> c1 = lift<S>(c_tri, proto);
+    V3<S> c1 = lift(c_tri, proto);
     SdfOut<S> o1 = sdf_qs(s1, c1, true);
     c1 = c1 - o1.n * o1.d;
     o1 = sdf_qs(s1, c1, true);
@@ -108,8 +113,8 @@ __device__ ContactGeo<S> contact_geometry(const SdfShape& s1, const SdfShape& s2
     SdfOut<S> o2 = sdf_qs(s2, c2, true);
     const V3<double> c1v = v3<double>(val(c1.x), val(c1.y), val(c1.z));
     const V3<double> c2v = v3<double>(val(c2.x), val(c2.y), val(c2.z));
-    const double lap1 = laplacian_fd(s1, c1v, val(o1.d), fd_eps);
-    const double lap2 = laplacian_fd(s2, c2v, val(o2.d), fd_eps);
+    const double lap1 = laplacian_fd(shape_values(s1), c1v, val(o1.d), fd_eps);
+    const double lap2 = laplacian_fd(shape_values(s2), c2v, val(o2.d), fd_eps);
     const bool stable = fabs(lap2) < fabs(lap1);
     ContactGeo<S> g;
     g.n = stable ? qapply(q2, o2.n) : neg(qapply(q1, o1.n));

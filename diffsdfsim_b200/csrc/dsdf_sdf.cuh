@@ -8,21 +8,35 @@
 
 namespace dsdf {
 
-// What a kernel needs to evaluate one body's SDF in that body's frame.
-struct SdfShape {
+// What a kernel needs to evaluate one body's SDF in that body's frame.  P = double, or Dual when the derivative with
+// respect to the shape parameters themselves is wanted (radius / dimension fitting: the reference's grad-enabled
+// _compute_contacts differentiates through params and scale, sdf_physics/physics3d/bodies.py:747-751).
+template <class P> struct SdfShapeT {
     int kind;            // DSDF_SDF_*
-    double a, b, c;      // normalised parameters: box dims/scale; sphere r/scale; cylinder r/scale, h/scale
-    double scale;
+    P a, b, c;           // normalised parameters: box dims/scale; sphere r/scale; cylinder r/scale, h/scale
+    P scale;
     const double* grid;  // (R,R,R) row-major, this world's grid (kind == GRID)
     int res;
 };
+typedef SdfShapeT<double> SdfShape;
+
+// a shape parameter as a scalar of the evaluation type S
+template <class S> __device__ __forceinline__ S par(S proto, double c) { return cst(proto, c); }
+__device__ __forceinline__ Dual par(Dual, Dual c) { return c; }
+__device__ __forceinline__ SdfShape shape_values(const SdfShape& s) { return s; }
+__device__ __forceinline__ SdfShape shape_values(const SdfShapeT<Dual>& s) {
+    SdfShape r;
+    r.kind = s.kind; r.a = s.a.v; r.b = s.b.v; r.c = s.c.v; r.scale = s.scale.v; r.grid = s.grid; r.res = s.res;
+    return r;
+}
 
 template <class S> struct SdfOut { S d; V3<S> n; };
 
 // ---- box (bodies.py:38-72), point u already divided by scale
-template <class S> __device__ __forceinline__ void box_eval(V3<S> u, double dx, double dy, double dz, bool want_n,
-                                                            S& value, V3<S>& dir) {
-    S qx = dabs(u.x) - cst(u.x, dx * 0.5), qy = dabs(u.y) - cst(u.x, dy * 0.5), qz = dabs(u.z) - cst(u.x, dz * 0.5);
+template <class S, class P> __device__ __forceinline__ void box_eval(V3<S> u, P dx, P dy, P dz, bool want_n,
+                                                                     S& value, V3<S>& dir) {
+    const S half = cst(u.x, 0.5);
+    S qx = dabs(u.x) - par(u.x, dx) * half, qy = dabs(u.y) - par(u.x, dy) * half, qz = dabs(u.z) - par(u.x, dz) * half;
     // q.max(dim=1): first maximal index carries the gradient
     S top = qx;
     if (val(qy) > val(top)) top = qy;
@@ -40,16 +54,16 @@ template <class S> __device__ __forceinline__ void box_eval(V3<S> u, double dx, 
 }
 
 // ---- sphere (bodies.py:75-84)
-template <class S> __device__ __forceinline__ void sphere_eval(V3<S> u, double r, bool want_n, S& value, V3<S>& dir) {
-    value = norm3(u) - cst(u.x, r);
+template <class S, class P> __device__ __forceinline__ void sphere_eval(V3<S> u, P r, bool want_n, S& value, V3<S>& dir) {
+    value = norm3(u) - par(u.x, r);
     if (want_n) dir = normalize3(u);
 }
 
 // ---- cylinder along local z (bodies.py:87-125)
-template <class S> __device__ __forceinline__ void cylinder_eval(V3<S> u, double r, double h, bool want_n, S& value,
-                                                                 V3<S>& dir) {
+template <class S, class P> __device__ __forceinline__ void cylinder_eval(V3<S> u, P r, P h, bool want_n, S& value,
+                                                                          V3<S>& dir) {
     S rho = norm2(u.x, u.y);
-    S q0 = dabs(rho) - cst(rho, r), q1 = dabs(u.z) - cst(rho, h * 0.5);
+    S q0 = dabs(rho) - par(rho, r), q1 = dabs(u.z) - par(rho, h) * cst(rho, 0.5);
     S top = q0;
     if (val(q1) > val(top)) top = q1;
     value = norm2(clamp_min0(q0), clamp_min0(q1)) + clamp_max0(top);
@@ -118,22 +132,22 @@ __device__ __forceinline__ bool grid_eval_raw(const double* g, int R, double ux,
 }
 
 // ---- SDF3D.query_sdfs: p in the body frame -> sdf (scaled back) and unit direction. Outside |p|<=scale: (scale, 0).
-template <class S>
-__device__ __forceinline__ SdfOut<S> sdf_query(const SdfShape& sh, V3<S> p, bool want_n = true) {
+template <class S, class P>
+__device__ __forceinline__ SdfOut<S> sdf_query(const SdfShapeT<P>& sh, V3<S> p, bool want_n = true) {
     SdfOut<S> o;
-    const double sc = sh.scale;
+    const double sc = val(sh.scale);
     S zero = cst(p.x, 0.0);
     o.n = v3<S>(zero, zero, zero);
     const bool inside = fabs(val(p.x)) <= sc && fabs(val(p.y)) <= sc && fabs(val(p.z)) <= sc;
-    if (!inside) { o.d = cst(p.x, 1.0 * sc); return o; }
-    S scs = cst(p.x, sc);
+    S scs = par(p.x, sh.scale);
+    if (!inside) { o.d = cst(p.x, 1.0) * scs; return o; }
     V3<S> u = p;
     fdiv3(u.x, u.y, u.z, scs);
     S value;
     V3<S> dir = o.n;
-    if (sh.kind == DSDF_SDF_BOX) box_eval<S>(u, sh.a, sh.b, sh.c, want_n, value, dir);
-    else if (sh.kind == DSDF_SDF_SPHERE) sphere_eval<S>(u, sh.a, want_n, value, dir);
-    else if (sh.kind == DSDF_SDF_CYLINDER) cylinder_eval<S>(u, sh.a, sh.b, want_n, value, dir);
+    if (sh.kind == DSDF_SDF_BOX) box_eval(u, sh.a, sh.b, sh.c, want_n, value, dir);
+    else if (sh.kind == DSDF_SDF_SPHERE) sphere_eval(u, sh.a, want_n, value, dir);
+    else if (sh.kind == DSDF_SDF_CYLINDER) cylinder_eval(u, sh.a, sh.b, want_n, value, dir);
     else {
         double v, n[3];
         // the custom backward (Dual pass) always needs the direction

@@ -55,9 +55,11 @@ def make_bodies(spec, device=None, params=None, W=1):
         pos = params['pos'] if (last and 'pos' in params) else b['pos']
         k = b['kind']
         if k == 'box':
-            ob = B.SDFBox(pos, b['dims'], max_tri_length=b['max_tri_length'], **kw)
+            dims = params['dims'] if (last and 'dims' in params) else b['dims']
+            ob = B.SDFBox(pos, dims, max_tri_length=b['max_tri_length'], **kw)
         elif k == 'sphere':
-            ob = B.SDFSphere(pos, b['rad'], subdivisions=(b['mesh'] or {}).get('subdivisions', 4), **kw)
+            rad = params['rad'] if (last and 'rad' in params) else b['rad']      # (W,) / scalar tensor: radius fitting
+            ob = B.SDFSphere(pos, rad, subdivisions=(b['mesh'] or {}).get('subdivisions', 4), **kw)
         elif k == 'cylinder':
             ob = B.SDFCylinder(pos, b['rad'], b['height'], max_tri_length=b['max_tri_length'], **kw)
         elif k == 'grid':

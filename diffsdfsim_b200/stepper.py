@@ -17,7 +17,7 @@ import time
 import torch
 
 from . import _lib
-from .contacts import ContactSet
+from .contacts import ContactSet, geometry_vjp, scatter_vertex_grads
 
 F64 = torch.float64
 U8 = torch.uint8
@@ -451,16 +451,6 @@ def _toc_bwd(dt, toc_mask, body, p, v, geo, f, mass, gh):
     return g_dt, gp, gv, ggeo, gf, gm
 
 
-def _geometry_bwd(table, p, shape, cs, ggeo, fd_eps, detach_b2, wmap):
-    W, nb = p.shape[0], p.shape[1]
-    gp = torch.empty_like(p)
-    rc = _lib.call('dsdf_contact_geometry_backward_rows', table.ptr(), _ptr(p), _ptr(shape), W, nb, fd_eps, int(detach_b2),
-                   cs.maxc, _ptr(cs.count), _ptr(cs.body), _ptr(cs.face), _ptr(cs.abc), _ptr(ggeo), _ptr(gp), _ptr(wmap),
-                   _lib.stream())
-    _lib.check(rc, 'dsdf_contact_geometry_backward')
-    return gp
-
-
 def _dyn_bwd(cfg, p, v, mass, Ibody, fric, rest, f, dt, active, count, body, geo, x, lam, s, gnv):
     W, nb = p.shape[0], p.shape[1]
     maxc = geo.shape[1]
@@ -514,7 +504,7 @@ class _StepFn(torch.autograd.Function):
     """
 
     @staticmethod
-    def forward(ctx, world, fixed_dt, p, v, geo, last_dt, mass, Ibody, fric, rest, f):
+    def forward(ctx, world, fixed_dt, p, v, geo, last_dt, mass, Ibody, fric, rest, f, shape_t, *verts):
         p, v, mass, Ibody, fric, rest, f = [t.contiguous() for t in (p, v, mass, Ibody, fric, rest, f)]
         tape = world._stepper.run(world, fixed_dt, p, v, last_dt, mass, Ibody, fric, rest, f)
         ctx.tape = tape
@@ -522,7 +512,9 @@ class _StepFn(torch.autograd.Function):
         ctx.geo_in_maxc = geo.shape[1]
         ctx.cfg = dict(eq_rows=world.eq_rows, neq=world.num_constraints, C=tape.C, fric_dirs=world.fric_dirs,
                        stop_contact_grad=world.stop_contact_grad, stop_friction_grad=world.stop_friction_grad,
-                       table=world.table, shape=world.shape, detach_b2=world.detach_contact_b2)
+                       table=world.table, shape=world.shape, detach_b2=world.detach_contact_b2,
+                       want_shape=shape_t is not None,
+                       leaves=[(i, vt) for i, vt in zip(world.table.vert_leaf_ids, verts)])
         world._last_tape = tape
         outs = (tape.p_out, tape.v_out, tape.geo_out, tape.last_dt_out, tape.had)
         # the tape must not keep the outputs: output -> grad_fn (this ctx) -> tape -> output would be a reference cycle
@@ -546,6 +538,9 @@ class _StepFn(torch.autograd.Function):
             ggeo = ggeo.clone()
         gm, gI = torch.zeros_like(mass), torch.zeros_like(Ibody)
         gfr, gre, gf = torch.zeros_like(fric), torch.zeros_like(rest), torch.zeros_like(f)
+        want_shape, leaves = cfg['want_shape'] or bool(cfg['leaves']), cfg['leaves']
+        gshape = torch.zeros(W, mass.shape[1], 4, dtype=F64, device=mass.device) if want_shape else None
+        gverts = [torch.zeros_like(vt) for _, vt in leaves]
         for k in range(tape.maxsub - 1, -1, -1):
             n = tape.slots[k].rows
             if n == 0:
@@ -580,8 +575,17 @@ class _StepFn(torch.autograd.Function):
                 glast_pass = torch.where(tn, zero_n, a_glast)
                 dgf = torch.where(tn3, gf_B, torch.zeros_like(gf_B))
                 dgm = torch.where(tn[:, None], gm_B, torch.zeros_like(gm_B))
-            gptry = gptry + _geometry_bwd(cfg['table'], S.p_try, cfg['shape'], S, ggeo_tot.contiguous(), 1e-3,
-                                          cfg['detach_b2'], wmap)
+            gp_geo, gshape_k, gctri_k = geometry_vjp(cfg['table'], S.p_try, cfg['shape'], S.count, S.body, S.face, S.abc,
+                                                     ggeo_tot, 1e-3, cfg['detach_b2'], wmap, want_shape)
+            gptry = gptry + gp_geo
+            if want_shape:
+                if k == 0:
+                    gshape += gshape_k
+                else:
+                    gshape.index_add_(0, idx, gshape_k)
+                if leaves:
+                    scatter_vertex_grads(gverts, leaves, cfg['table'], gctri_k, S.count, S.body, S.face, S.abc,
+                                         None if k == 0 else idx)
             gp2, gv2, gdt2 = _integrate_bwd(S.p_in, S.new_v, S.dt_used, None, gptry.contiguous())
             gnv = a_gv + gv2 if gnv_acc is None else a_gv + gv2 + gnv_acc
             gp3, gv3, gm3, gI3, gfr3, gre3, gf3, gdt3, ggeo3 = _dyn_bwd(cfg, S.p_in, S.v_in, pm, pI, pfr, pre, pf,
@@ -607,4 +611,4 @@ class _StepFn(torch.autograd.Function):
                 gf.index_add_(0, idx, gf3)
         if ggeo.shape[1] != ctx.geo_in_maxc:
             ggeo = ggeo[:, :ctx.geo_in_maxc]
-        return None, None, gp, gv, ggeo, glast, gm, gI, gfr, gre, gf
+        return (None, None, gp, gv, ggeo, glast, gm, gI, gfr, gre, gf, gshape if cfg['want_shape'] else None) + tuple(gverts)

@@ -150,7 +150,11 @@ class World3D:
         st.Ibody = torch.stack([ex(b.ang_inertia, 3, 3) for b in self.bodies], 1).contiguous()
         st.fric = torch.stack([ex(b.fric_coeff) for b in self.bodies], 1).contiguous()
         st.rest = torch.stack([ex(b.restitution) for b in self.bodies], 1).contiguous()
-        self.shape = torch.stack([ex(b.shape_rows(), 4) for b in self.bodies], 1).contiguous().detach()
+        # [a, b, c, scale] rows of every body: the kernels read the values; shape_t keeps the autograd link to radius /
+        # dimension leaves (radius and size fitting differentiate the contact geometry through them, contacts.py:262-264)
+        shape_t = torch.stack([ex(b.shape_rows(), 4) for b in self.bodies], 1)
+        self.shape = shape_t.detach().contiguous()
+        self.shape_t = shape_t if shape_t.requires_grad else None
         self.body_eps = float(self.bodies[0].eps)
 
         # equality rows: constant 0/1 selections (constraints.py)
@@ -171,6 +175,7 @@ class World3D:
 
         # contact detection set-up (replaces the py3ode HashSpace of world.py:69-72)
         self.table = GeometryTable(self.bodies, W, dev)
+        self.vert_leaves = [self.bodies[i].verts.to(dev) for i in self.table.vert_leaf_ids]   # differentiable meshes
         self._shared_geometry = bool((self.table.rows['vstride'] == 0).all() and (self.table.rows['gstride'] == 0).all())
         self.pairs = [(i, j) for i in range(nb) for j in range(i + 1, nb)
                       if self.bodies[j] not in self.bodies[i].no_contact]
@@ -301,7 +306,7 @@ class World3D:
         self.contact_set = cs
         self.max_nc = int(cs.count.max())
         self.contact_geo = differentiable_geometry(self.state.p, self.shape, cs, self.table, Defaults3D.EPSILON,
-                                                   self.detach_contact_b2)
+                                                   self.detach_contact_b2, self.shape_t, self.vert_leaves)
         return cs
 
     # ------------------------------------------------------------------ stepping
@@ -357,7 +362,8 @@ class World3D:
         if self._stepper is None:
             self._stepper = DeviceStepper(self)
         p, v, geo, last_dt, had = _StepFn.apply(self, fixed_dt, st.p, st.v, self.contact_geo, self.last_dt, st.mass,
-                                                st.Ibody, st.fric, st.rest, self.step_forces())
+                                                st.Ibody, st.fric, st.rest, self.step_forces(), self.shape_t,
+                                                *self.vert_leaves)
         tape = self._last_tape
         st.p, st.v, self.contact_geo, self.last_dt = p, v, geo, last_dt
         self.contact_set = tape.final
@@ -456,7 +462,8 @@ class World3D:
         cs = old.clone()
         self.detector.detect(p_try.detach(), self.shape, cs, active, eps=self.eps, tol=self.tol,
                              fd_eps=Defaults3D.EPSILON, body_eps=self.body_eps, detach_b2=self.detach_contact_b2)
-        geo = differentiable_geometry(p_try, self.shape, cs, self.table, Defaults3D.EPSILON, self.detach_contact_b2)
+        geo = differentiable_geometry(p_try, self.shape, cs, self.table, Defaults3D.EPSILON, self.detach_contact_b2,
+                                      self.shape_t, self.vert_leaves)
         u8 = lambda *shape: torch.empty(*shape, dtype=torch.uint8, device=dev)
         accept, active_next, toc_now, toc_mask = u8(W), u8(W), u8(W), u8(W, self.maxc)
         t_new, dt_next = torch.empty_like(self.t), torch.empty_like(dt_try)
@@ -502,7 +509,8 @@ class World3D:
     def _use_speculation(self, n_active):
         """Speculate when few worlds are still active (their slots are plentiful) and no body has per-world geometry
         (the contact kernels address per-world meshes / grids by slot index)."""
-        return (self.speculate and self.W >= 64 and 0 < n_active <= self.W // 8 and self._shared_geometry)
+        return (self.speculate and self.W >= 64 and 0 < n_active <= self.W // 8 and self._shared_geometry
+                and self.shape_t is None and not self.vert_leaves)
 
     def _attempt_speculative(self, active, dt_try, end_t):
         """One round that tries dt, dt/2 and dt/4 of every still-active world AT ONCE.

@@ -176,6 +176,17 @@ int dsdf_contact_geometry_backward_rows(const dsdf_body_geom* geom, const double
                                         const int32_t* cbody, const int32_t* cface, const double* cabc,
                                         const double* ggeo, double* gp, const int32_t* wmap, void* stream);
 
+/* The same with the gradients w.r.t. the SHAPES as well (radius / dimension fitting: the reference's grad-enabled
+ * _compute_contacts differentiates through the SDF parameters, the scale and the mesh vertices):
+ * gshape (W,nb,4) = d/d[a,b,c,scale] of every body, gctri (W,maxc,3) = gradient w.r.t. the body-frame point
+ * sum(abc * vertices of the face) on the mesh body of each contact (the caller scatters it onto the vertices with the
+ * weights cabc).  gshape == gctri == NULL: pose gradients only. */
+int dsdf_contact_geometry_backward_full(const dsdf_body_geom* geom, const double* p, const double* shape, int W, int nb,
+                                        double fd_eps, int detach_b2, int maxc, const int32_t* count,
+                                        const int32_t* cbody, const int32_t* cface, const double* cabc,
+                                        const double* ggeo, double* gp, const int32_t* wmap, double* gshape,
+                                        double* gctri, void* stream);
+
 /* ------------------------------------------------------------- dynamics ----
  * Replaces the matrix assembly of PdipmEngine.solve_dynamics (lcp_physics/physics/engines.py:31-79) with
  * World3D.M/Jc/Jf (sdf_physics/physics3d/world.py:48-101), orthogonal (physics3d/utils.py:247-256) and

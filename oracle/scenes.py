@@ -21,6 +21,9 @@ def mesh_for(b):
     if k == 'box':
         return meshes.box_mesh(b['dims'], b['max_tri_length'])
     if k == 'sphere':
+        if isinstance(b['rad'], torch.Tensor):       # differentiable radius: unit icosphere scaled by it (bodies.py:1001-1009)
+            v, f = meshes.icosphere(1.0, (b['mesh'] or {}).get('subdivisions', 4))
+            return torch.as_tensor(v, dtype=F64) * b['rad'], f
         return meshes.icosphere(b['rad'], (b['mesh'] or {}).get('subdivisions', 4))
     if k == 'cylinder':
         return meshes.cylinder_mesh(b['rad'], b['height'], 32, b['max_tri_length'])
@@ -58,6 +61,8 @@ def build(spec, params=None, max_iter=10, **world_kw):
     n = len(spec['bodies'])
     for i, b in enumerate(spec['bodies']):
         last = i == n - 1
+        if last and 'rad' in params:
+            b = dict(b, rad=params['rad'])
         mass = params['mass'] if (last and 'mass' in params) else tens(float(b['mass']))
         if 'mass_all' in params:
             mass = params['mass_all'][i]
@@ -68,7 +73,8 @@ def build(spec, params=None, max_iter=10, **world_kw):
         vel = params['vel'] if (last and 'vel' in params) else tens(b['vel'])
         if 'vel_all' in params:
             vel = params['vel_all'][i]
-        ob = Body(kind, sp, scale, torch.as_tensor(verts, dtype=F64), torch.as_tensor(np.asarray(faces)).long(),
+        ob = Body(kind, sp, scale, verts if isinstance(verts, torch.Tensor) else torch.as_tensor(verts, dtype=F64),
+                  torch.as_tensor(np.asarray(faces)).long(),
                   pos, vel, mass, I, b['restitution'], fric)
         if b['gravity']:
             ob.add_gravity()

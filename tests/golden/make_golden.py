@@ -40,7 +40,7 @@ F64 = torch.float64
 
 
 def _inject(cls, verts, faces, inertia=None):
-    v = torch.as_tensor(verts, dtype=F64)
+    v = verts if isinstance(verts, torch.Tensor) else torch.as_tensor(verts, dtype=F64)
     f = torch.as_tensor(np.asarray(faces)).long()
 
     class Injected(cls):
@@ -61,6 +61,8 @@ def build_reference(spec, params=None):
     n = len(spec['bodies'])
     for i, b in enumerate(spec['bodies']):
         last = i == n - 1
+        if last and 'rad' in params:
+            b = dict(b, rad=params['rad'])
         mass = params['mass'] if (last and 'mass' in params) else float(b['mass'])
         if 'mass_all' in params:
             mass = params['mass_all'][i]
@@ -75,6 +77,8 @@ def build_reference(spec, params=None):
         if k == 'box':
             ob = _inject(rb.SDFBox, verts, faces)(pos, b['dims'], custom_mesh=True, custom_inertia=True, **kw)
         elif k == 'sphere':
+            # (a tensor radius keeps the mesh differentiable: mesh_for returns unit icosphere * rad, as the reference's own
+            # custom mesh does, bodies.py:1001-1009)
             ob = _inject(rb.SDFSphere, verts, faces)(pos, b['rad'], custom_mesh=True, custom_inertia=True, **kw)
         elif k == 'cylinder':
             ob = _inject(rb.SDFCylinder, verts, faces)(pos, b['rad'], b['height'], custom_mesh=True,

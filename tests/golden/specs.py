@@ -13,6 +13,10 @@ SCENES = {
     # config-3 shape: several free bodies + pinned floor, every pair searched (pins pair order and multi-pair contact rows)
     'mixed_primitives': (lambda: scenes.mixed_primitives(steps=8),
                          dict(mass=1.2, vel=[0.0, 0.0, 0.0, 0.2, -1.0, 0.1])),
+    # radius fitting (the reference's published experiment, RESULTS.md:22-47): gradient of the rollout w.r.t. the sphere's
+    # RADIUS, which enters through the mesh vertices, the SDF scale, and the inertia (optim_sphere.py:78-111)
+    'sphere_radius': (lambda: scenes.bouncing_sphere(floor=(4.0, 1.0, 4.0), steps=14, floor_tri=0.2, subdivisions=3),
+                      dict(rad=0.5, pos=[0.0, 1.0, 0.0])),
     # ---- BASELINE configurations at their named sizes
     # config 1: sphere dropped from 5 m with 5 m/s sideways on the 20x1x20 floor (176 000 faces), 100 steps
     # (experiments/trajectory_fitting/optim_sphere.py:78-111)

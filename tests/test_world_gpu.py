@@ -25,7 +25,9 @@ TOL = {'box_on_plane': (1e-8, 1e-5), 'bouncing_sphere': (1e-8, 1e-4), 'grid_on_p
        'c1_bouncing_sphere': (5e-6, 5e-3), 'c3_mixed16': (1e-6, 1e-5), 'c4_cow_on_pole': (1e-6, 1e-5),
        # ~75 simultaneous contacts (760 inequality rows): the reference's 10 interior-point iterations leave residuals of
        # ~1e-4 in the velocities, so algebraically equivalent solvers differ by that much (attempt counts stay identical)
-       'c3_mixed16_floor': (2e-5, 1e-2)}
+       'c3_mixed16_floor': (2e-5, 1e-2),
+       # gradient w.r.t. the sphere's radius (mesh vertices + SDF scale + inertia): the reference's radius-fitting experiment
+       'sphere_radius': (1e-8, 1e-5)}
 
 
 def _params(leaves, g, W=1):
