@@ -23,6 +23,8 @@ SIGNATURES = {
     'dsdf_lcp_backward': (c_i, [c_p] * 10 + [c_i] * 5 + [c_p] * 10),
     'dsdf_sdf_query': (c_i, [c_i, c_p, c_p, c_i, c_ll, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
     'dsdf_sdf_query_backward': (c_i, [c_i, c_p, c_p, c_i, c_ll, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
+    'dsdf_sdf_query_ex': (c_i, [c_i, c_p, c_d, c_d, c_p, c_i, c_ll, c_p, c_i, c_i, c_i, c_p, c_p, c_p]),
+    'dsdf_sdf_query_backward_ex': (c_i, [c_i, c_p, c_d, c_d, c_p, c_i, c_ll, c_p, c_i, c_i, c_p, c_p, c_p, c_p]),
     'dsdf_integrate': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p]),
     'dsdf_integrate_backward': (c_i, [c_p, c_p, c_p, c_p, c_i, c_i, c_p, c_p, c_p, c_p, c_p]),
     'dsdf_contacts_detect': (c_i, [c_p, c_p, c_i, c_p, c_p, c_p, c_i, c_i, c_d, c_d, c_d, c_d, c_i, c_i, c_i]
@@ -78,7 +80,7 @@ def lib():
 
 # CUDA kernels launched by one call of each entry point (for bench.py's gpu_launches claim)
 KERNELS_PER_CALL = {
-    'dsdf_lcp_forward': 1, 'dsdf_lcp_backward': 1, 'dsdf_sdf_query': 1, 'dsdf_sdf_query_backward': 1,
+    'dsdf_lcp_forward': 1, 'dsdf_lcp_backward': 1, 'dsdf_sdf_query': 1, 'dsdf_sdf_query_backward': 1, 'dsdf_sdf_query_ex': 1, 'dsdf_sdf_query_backward_ex': 1,
     'dsdf_integrate': 1, 'dsdf_integrate_backward': 1, 'dsdf_contacts_detect': 1,
     'dsdf_contact_geometry_backward': 1, 'dsdf_dynamics_assemble': 1, 'dsdf_dynamics_assemble_backward': 1,
     'dsdf_dynamics_solve': 1, 'dsdf_dynamics_solve_backward': 1, 'dsdf_attempt_commit': 1, 'dsdf_toc_backward': 1, 'dsdf_contactset_move': 1,

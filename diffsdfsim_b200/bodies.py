@@ -15,7 +15,7 @@ from . import meshes, ops
 from .utils import Defaults3D, as_batched
 
 F64 = torch.float64
-BOX, SPHERE, CYLINDER, GRID = 0, 1, 2, 3
+BOX, SPHERE, CYLINDER, GRID, BOX_ROUNDED, BRICK, BOWL = 0, 1, 2, 3, 4, 5, 6
 
 
 def euler_to_quat(e):
@@ -154,7 +154,7 @@ class SDF3D(Body3D):
         grid = self.sdf_grid.to(pts.device) if self.sdf_grid is not None else None
         if grid is not None and grid.dim() == 4 and grid.shape[0] != pts.shape[0]:
             grid = grid[0]
-        out = ops.sdf_query(self.kind, rows, pts, grid, want_dir=return_grads)
+        out = ops.sdf_query(self.kind, rows, pts, grid, want_dir=return_grads, extra=getattr(self, 'sdf_extra', (0.0, 0.0)))
         sd, gr = out if return_grads else (out, None)
         mask = torch.all(pts.abs() <= rows[:, 3].reshape(-1, 1, 1), dim=2)
         if single:
@@ -274,3 +274,73 @@ class SDFGrid3D(SDF3D):
             I = torch.as_tensor(meshes.mesh_inertia(v.cpu().numpy(), self.faces.cpu().numpy()), dtype=F64,
                                 device=mass.device)
         return mass.reshape(-1, 1, 1) * I
+
+
+def _sampled_mesh(kind, shape3, extra, scale, res=96):
+    """Iso-surface mesh of an analytic SDF body sampled on a res^3 lattice over its cube (what the reference extracts with
+    128^3 marching cubes when custom_mesh=False, bodies.py:652-712): meshes.surface_nets of meshes.sample_sdf."""
+    g = meshes.sample_sdf(kind, [float(x) for x in shape3], [float(x) for x in extra], res)
+    v, f = meshes.surface_nets(g)
+    return v * float(scale), f
+
+
+class SDFBoxRounded(SDF3D):
+    """bodies.py:856-870: box_sdf(dims - 2 r) - r.  The mesh is the iso-surface of the sampled SDF unless given."""
+    kind = BOX_ROUNDED
+
+    def __init__(self, pos, dims, r, vel=(0, 0, 0, 0, 0, 0), mass=1, restitution=Defaults3D.RESTITUTION,
+                 fric_coeff=Defaults3D.FRIC_COEFF, eps=Defaults3D.EPSILON, mesh=None, inertia=None, device=None, **_ignored):
+        self.dims = as_batched(dims, 1, device)
+        assert self.dims.shape[0] == 1, 'per-world dims are not supported for rounded boxes'
+        self.r = float(r)
+        scale = self.dims.max(dim=1)[0] * 1.5 / 2
+        shape = (self.dims - 2 * self.r) / scale.unsqueeze(1)
+        self.sdf_extra = (self.r / float(scale[0]), 0.0)
+        if mesh is None:
+            mesh = _sampled_mesh('box_rounded', shape[0].tolist(), self.sdf_extra, scale[0])
+        self._unit_inertia = inertia
+        super().__init__(pos, scale, shape, mesh, vel=vel, mass=mass, restitution=restitution, fric_coeff=fric_coeff,
+                         eps=eps, device=device)
+
+    def _get_ang_inertia(self, mass):
+        I = self._unit_inertia
+        if I is None:
+            I = meshes.mesh_inertia(self.verts.detach().cpu().numpy(), self.faces.cpu().numpy())
+        return mass.reshape(-1, 1, 1) * torch.as_tensor(I, dtype=F64, device=mass.device)
+
+
+class SDFBrick(SDFBoxRounded):
+    """bodies.py:873-886: box whose first two dimensions are rounded in-plane (brick_sdf); the reference pairs it with the
+    direction function of a cube of side r (its rounded_sdf_grad wrapper drops the first parameter), reproduced here."""
+    kind = BRICK
+
+    def __init__(self, pos, dims, r, vel=(0, 0, 0, 0, 0, 0), mass=1, restitution=Defaults3D.RESTITUTION,
+                 fric_coeff=Defaults3D.FRIC_COEFF, eps=Defaults3D.EPSILON, mesh=None, inertia=None, device=None, **_ignored):
+        self.dims = as_batched(dims, 1, device)
+        assert self.dims.shape[0] == 1, 'per-world dims are not supported for bricks'
+        self.r = float(r)
+        scale = self.dims.max(dim=1)[0] * 1.5 / 2
+        shape = self.dims / scale.unsqueeze(1)
+        self.sdf_extra = (self.r / float(scale[0]), 0.0)
+        if mesh is None:
+            mesh = _sampled_mesh('brick', shape[0].tolist(), self.sdf_extra, scale[0])
+        self._unit_inertia = inertia
+        SDF3D.__init__(self, pos, scale, shape, mesh, vel=vel, mass=mass, restitution=restitution, fric_coeff=fric_coeff,
+                       eps=eps, device=device)
+
+
+class SDFBowl(SDFBoxRounded):
+    """bodies.py:1012-1026: half shell of radius r and half thickness d (bowl_sdf / bowl_sdf_grad), scale (r + d) * 1.3333."""
+    kind = BOWL
+
+    def __init__(self, pos, r, d, vel=(0, 0, 0), mass=1, restitution=Defaults3D.RESTITUTION,
+                 fric_coeff=Defaults3D.FRIC_COEFF, eps=Defaults3D.EPSILON, mesh=None, inertia=None, device=None, **_ignored):
+        self.r, self.d = float(r), float(d)
+        scale = as_batched((self.r + self.d) * 1.3333, 0, device)
+        shape = torch.tensor([[self.r, self.d, 0.0]], dtype=F64, device=scale.device) / scale.unsqueeze(1)
+        self.sdf_extra = (0.0, 0.0)
+        if mesh is None:
+            mesh = _sampled_mesh('bowl', shape[0].tolist(), self.sdf_extra, scale[0])
+        self._unit_inertia = inertia
+        SDF3D.__init__(self, pos, scale, shape, mesh, vel=vel, mass=mass, restitution=restitution, fric_coeff=fric_coeff,
+                       eps=eps, device=device)

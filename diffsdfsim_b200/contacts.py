@@ -15,9 +15,10 @@ _GEOM_DTYPE = np.dtype([('kind', 'i4'), ('nverts', 'i4'), ('nfaces', 'i4'), ('re
                         ('faces', 'u8'), ('grid', 'u8'), ('vstride', 'i8'), ('gstride', 'i8'),
                         ('cell_lo', 'f8', (3,)), ('cell_inv', 'f8'), ('cell_dims', 'i4', (3,)), ('has_cells', 'i4'),
                         ('fcell_start', 'u8'), ('fcell_items', 'u8'), ('vcell_start', 'u8'), ('vcell_items', 'u8'),
-                        ('max_face_rad', 'f8'), ('fstride', 'i8'), ('nfaces_w', 'u8'), ('nverts_w', 'u8')],
+                        ('max_face_rad', 'f8'), ('fstride', 'i8'), ('nfaces_w', 'u8'), ('nverts_w', 'u8'),
+                        ('extra', 'f8', (2,))],
                        align=True)
-assert _GEOM_DTYPE.itemsize == 168
+assert _GEOM_DTYPE.itemsize == 184
 
 
 _CELL_CACHE = {}
@@ -120,7 +121,8 @@ class GeometryTable:
                 self.keep += dev_arrays
                 cell = (lo, inv, dims, 1) + tuple(a.data_ptr() for a in dev_arrays)
             rows[i] = (b.kind, nverts, faces.shape[-2], res, verts.data_ptr(), faces.data_ptr(), gptr,
-                       nverts * 3 if per_world else 0, gstride) + cell + (max_rad, fstride, nf_ptr, nv_ptr)
+                       nverts * 3 if per_world else 0, gstride) + cell + (max_rad, fstride, nf_ptr, nv_ptr,
+                                                                         tuple(getattr(b, 'sdf_extra', (0.0, 0.0))))
             self.nfaces.append(int(faces.shape[-2]))
         self.rows = rows
         self.dev = torch.from_numpy(rows.view(np.uint8).copy()).to(device)

@@ -23,6 +23,7 @@ struct BodyGeom {                 // mirrors dsdf_body_geom in include/dsdf_b200
     // world w uses faces + w*fstride, nfaces_w[w] faces and nverts_w[w] vertices; NULL / 0 = shared topology
     long long fstride;
     const int *nfaces_w, *nverts_w;
+    double extra[2];              // further SDF parameters of the kind (rounding radius / scale)
 };
 
 // the geometry of body g as world w sees it (topology pointers / counts resolved; vertices stay strided, see load_vert)
@@ -59,6 +60,7 @@ __device__ __forceinline__ SdfShape body_shape(const BodyGeom& g, const double* 
     sh.kind = g.kind; sh.a = s[0]; sh.b = s[1]; sh.c = s[2]; sh.scale = s[3];
     sh.grid = g.grid ? g.grid + (size_t)w * g.gstride : nullptr;
     sh.res = g.res;
+    sh.e0 = g.extra[0]; sh.e1 = g.extra[1];
     return sh;
 }
 __device__ __forceinline__ V3<double> load_vert(const BodyGeom& g, int w, int vi) {

@@ -145,7 +145,7 @@ struct Pre32 { float R[9], t[3]; float a, b, c, scale, thresh, margin, eps; int 
 __device__ __forceinline__ Pre32 make_pre32(const BodyGeom& g1, const SdfShape& s2, Q4<double> q1, V3<double> x1,
                                             Q4<double> q2, V3<double> x2, double eps) {
     Pre32 P;
-    P.on = g1.max_face_rad > 0.0 && s2.kind != DSDF_SDF_GRID;
+    P.on = g1.max_face_rad > 0.0 && s2.kind <= DSDF_SDF_CYLINDER;    // (exact distance fields with a cheap fp32 form)
     const M3<double> R1 = q2mat(q1), R2 = q2mat(q2);
     const V3<double> t = mat_applyT(R2, x1 - x2);
     double amax = fabs(t.x) + fabs(t.y) + fabs(t.z);

@@ -54,7 +54,7 @@ contact_geometry_bwd_kernel(const BodyGeom* __restrict__ geom, const double* __r
         } else {
             auto shp = [](const SdfShape& s, int seed) {
                 SdfShapeT<Dual> r;
-                r.kind = s.kind; r.grid = s.grid; r.res = s.res;
+                r.kind = s.kind; r.grid = s.grid; r.res = s.res; r.e0 = s.e0; r.e1 = s.e1;
                 r.a = Dual(s.a, seed == 0); r.b = Dual(s.b, seed == 1); r.c = Dual(s.c, seed == 2);
                 r.scale = Dual(s.scale, seed == 3);
                 return r;

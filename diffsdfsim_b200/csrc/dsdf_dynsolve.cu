@@ -60,10 +60,17 @@ struct DynCtx {
     __device__ int gidx(int c, int k) const { return 6 * cb[2 * c + (k >= 6)] + (k % 6); }
 };
 
+// DSDF_DYN_OUTLINE: keep ONE out-of-line copy of the building blocks (the kernel is 17 k SASS instructions = 280 KB when
+// everything is inlined, far beyond the instruction cache; ncu: 13-34 % of stall samples "no_instructions")
+#ifdef DSDF_DYN_OUTLINE
+#define DYN_FN __device__ __noinline__
+#else
+#define DYN_FN __device__ __forceinline__
+#endif
 __device__ __forceinline__ double wsum(double v) { return warp_sum(v); }
 
 // ---- warp-level pivoted LU / solve on a small matrix in shared memory ---------------------------------------
-__device__ inline int warp_lu(double* A, int ld, int n, int* perm) {
+DYN_FN int warp_lu(double* A, int ld, int n, int* perm) {
     const int lane = threadIdx.x & 31;
     int fail = 0;
     for (int i = lane; i < n; i += 32) perm[i] = i;
@@ -93,7 +100,7 @@ __device__ inline int warp_lu(double* A, int ld, int n, int* perm) {
     return fail;
 }
 // x <- (PLU)^-1 b ; b, x distinct shared vectors
-__device__ inline void warp_lu_solve(const double* LU, int ld, int n, const int* perm, const double* b, double* x) {
+DYN_FN void warp_lu_solve(const double* LU, int ld, int n, const int* perm, const double* b, double* x) {
     const int lane = threadIdx.x & 31;
     for (int i = lane; i < n; i += 32) x[i] = b[perm[i]];
     __syncwarp();
@@ -103,7 +110,7 @@ __device__ inline void warp_lu_solve(const double* LU, int ld, int n, const int*
 }
 
 // ---- load one world's problem into shared memory ---------------------------------------------------------------
-__device__ void dyn_load(DynCtx& c, int w, const double* p, const double* v, const double* mass, const double* Ibody,
+DYN_FN void dyn_load(DynCtx& c, int w, const double* p, const double* v, const double* mass, const double* Ibody,
                          const double* fric, const double* rest, const double* f, double dtw, const int* count,
                          const int* cbody, const double* cgeo, const int* eq_rows, int maxc, int fd, double* mu_out,
                          double* e_out, double* h_out) {
@@ -177,7 +184,7 @@ __device__ __forceinline__ double Fz_row(const DynCtx& c, const double* z, const
     return acc;
 }
 // out = G x for all rows (contact-major): friction row q + half is the negative of row q, the cone row is zero
-__device__ __forceinline__ void Gx_all(const DynCtx& c, const double* x, double* out) {
+DYN_FN void Gx_all(const DynCtx& c, const double* x, double* out) {
     const int lane = threadIdx.x & 31, per = c.L.per, half = c.L.half, rows = 1 + half;
     for (int e = lane; e < c.nc * rows; e += 32) {
         const int cc = e / rows, j = e % rows;
@@ -192,7 +199,7 @@ __device__ __forceinline__ void Gx_all(const DynCtx& c, const double* x, double*
     __syncwarp();
 }
 // (G' w)[I]
-__device__ __forceinline__ double Gtw_row(const DynCtx& c, const double* w, int I, int fd) {
+DYN_FN double Gtw_row(const DynCtx& c, const double* w, int I, int fd) {
     const int per = c.L.per, half = c.L.half, b = I / 6, k6 = I % 6;
     double acc = 0.0;
     for (int cc = 0; cc < c.nc; ++cc) {
@@ -207,7 +214,7 @@ __device__ __forceinline__ double Gtw_row(const DynCtx& c, const double* w, int 
     return acc;
 }
 // solve B_c u = t for every contact in place on t (contact-major), thread per contact
-__device__ __forceinline__ void block_solve(const DynCtx& c, const double* mu, double* t, int fd) {
+DYN_FN void block_solve(const DynCtx& c, const double* mu, double* t, int fd) {
     const int lane = threadIdx.x & 31, per = c.L.per;
     for (int cc = lane; cc < c.nc; cc += 32) {
         double* tc = t + cc * per;
@@ -224,7 +231,7 @@ __device__ __forceinline__ void block_solve(const DynCtx& c, const double* mu, d
 }
 
 // factor: a = 1/d, den, YG, K = [[Q + sum G' B^-1 G, A'],[A,0]] -> LU.  Returns 1 on a singular K.
-__device__ int dyn_factor(DynCtx& c, const double* d, const double* mu, int fd) {
+DYN_FN int dyn_factor(DynCtx& c, const double* d, const double* mu, int fd) {
     const int lane = threadIdx.x & 31;
     const DynSmem& L = c.L;
     const int per = L.per, nz = L.nz, nF = L.nF, ld = L.ldF;
@@ -295,7 +302,7 @@ __device__ inline void kkt_solve(DynCtx& c, const double* rhs, double* dxy) {
 
 // KKT solve (batch.py:380-410 semantics).  rxy = [rx; ry] (NULL = 0), rs (NULL = 0), rz (NULL = 0).
 // Outputs dxy = [dx; dy], ds, dz.  Scratch: vec(DV_T), sv(DS_RHS).
-__device__ void dyn_solve(DynCtx& c, const double* d, const double* mu, int fd, const double* rxy, const double* rs,
+DYN_FN void dyn_solve(DynCtx& c, const double* d, const double* mu, int fd, const double* rxy, const double* rs,
                           const double* rz, double* dxy, double* ds, double* dz) {
     const int lane = threadIdx.x & 31;
     const DynSmem& L = c.L;
@@ -330,7 +337,7 @@ __device__ void dyn_solve(DynCtx& c, const double* d, const double* mu, int fd, 
     __syncwarp();
 }
 
-__device__ double dyn_ratio_step(const DynCtx& c, const double* v, const double* dv) {
+DYN_FN double dyn_ratio_step(const DynCtx& c, const double* v, const double* dv) {
     const int lane = threadIdx.x & 31;
     double mx = -INFINITY;
     for (int r = lane; r < c.ni; r += 32) mx = fmax(mx, -v[r] / dv[r]);

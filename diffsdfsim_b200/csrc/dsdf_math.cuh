@@ -89,6 +89,9 @@ HD Dual clamp_max0(Dual a) { return a.v > 0.0 ? Dual(0.0, 0.0) : a; }
 // torch.max(x, 0) (binary maximum): tie splits the gradient in half
 HD double maximum0(double a) { return a > 0.0 ? a : 0.0; }
 HD Dual maximum0(Dual a) { return a.v > 0.0 ? a : (a.v == 0.0 ? Dual(0.0, 0.5 * a.d) : Dual(0.0, 0.0)); }
+// torch.min(0, x) (binary minimum): tie splits the gradient in half
+HD double minimum0(double a) { return a < 0.0 ? a : 0.0; }
+HD Dual minimum0(Dual a) { return a.v < 0.0 ? a : (a.v == 0.0 ? Dual(0.0, 0.5 * a.d) : Dual(0.0, 0.0)); }
 // clamp(x, lo) general lower clamp (so3_exponential_map): passes where x >= lo
 HD double clamp_lo(double a, double lo) { return a < lo ? lo : a; }
 HD Dual clamp_lo(Dual a, double lo) { return a.v < lo ? Dual(lo, 0.0) : a; }

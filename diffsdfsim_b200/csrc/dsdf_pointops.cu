@@ -7,19 +7,20 @@
 
 namespace dsdf {
 
-__device__ __forceinline__ SdfShape load_shape(int kind, const double* shape4, const double* grid, int res) {
+__device__ __forceinline__ SdfShape load_shape(int kind, const double* shape4, const double* grid, int res, double e0,
+                                               double e1) {
     SdfShape s;
     s.kind = kind; s.a = shape4[0]; s.b = shape4[1]; s.c = shape4[2]; s.scale = shape4[3];
-    s.grid = grid; s.res = res;
+    s.grid = grid; s.res = res; s.e0 = e0; s.e1 = e1;
     return s;
 }
 
 __global__ void __launch_bounds__(256)
 sdf_query_kernel(int kind, const double* __restrict__ shape, const double* __restrict__ grid, int res,
                  long long grid_stride, const double* __restrict__ pts, int N, int want_dir,
-                 double* __restrict__ sdf, double* __restrict__ dir) {
+                 double* __restrict__ sdf, double* __restrict__ dir, double e0, double e1) {
     const int w = blockIdx.y;
-    const SdfShape sh = load_shape(kind, shape + 4 * (size_t)w, grid ? grid + (size_t)w * grid_stride : nullptr, res);
+    const SdfShape sh = load_shape(kind, shape + 4 * (size_t)w, grid ? grid + (size_t)w * grid_stride : nullptr, res, e0, e1);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const size_t o = (size_t)w * N + i;
         V3<double> p = v3<double>(pts[3 * o], pts[3 * o + 1], pts[3 * o + 2]);
@@ -161,9 +162,10 @@ sdf_query_grid_kernel(const double* __restrict__ shape, const double* __restrict
 __global__ void __launch_bounds__(256)
 sdf_query_bwd_kernel(int kind, const double* __restrict__ shape, const double* __restrict__ grid, int res,
                      long long grid_stride, const double* __restrict__ pts, int N,
-                     const double* __restrict__ gsdf, const double* __restrict__ gdir, double* __restrict__ gpts) {
+                     const double* __restrict__ gsdf, const double* __restrict__ gdir, double* __restrict__ gpts,
+                     double e0, double e1) {
     const int w = blockIdx.y;
-    const SdfShape sh = load_shape(kind, shape + 4 * (size_t)w, grid ? grid + (size_t)w * grid_stride : nullptr, res);
+    const SdfShape sh = load_shape(kind, shape + 4 * (size_t)w, grid ? grid + (size_t)w * grid_stride : nullptr, res, e0, e1);
     for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < N; i += gridDim.x * blockDim.x) {
         const size_t o = (size_t)w * N + i;
         const double gs = gsdf ? gsdf[o] : 0.0;
@@ -239,9 +241,10 @@ using namespace dsdf;
 
 extern "C" {
 
-int dsdf_sdf_query(int kind, const double* shape, const double* grid, int res, long long grid_world_stride,
-                   const double* pts, int W, int N, int want_dir, double* sdf, double* dir, void* stream) {
-    if (W <= 0 || N < 0 || kind < 0 || kind > 3 || (kind == DSDF_SDF_GRID && (!grid || res < 2))) return -1;
+int dsdf_sdf_query_ex(int kind, const double* shape, double extra0, double extra1, const double* grid, int res,
+                      long long grid_world_stride, const double* pts, int W, int N, int want_dir, double* sdf, double* dir,
+                      void* stream) {
+    if (W <= 0 || N < 0 || kind < 0 || kind > DSDF_SDF_BOWL || (kind == DSDF_SDF_GRID && (!grid || res < 2))) return -1;
     if (N == 0) return 0;
     int bx = (N + 255) / 256;
     if (bx > 148 * 8) bx = 148 * 8;
@@ -254,20 +257,32 @@ int dsdf_sdf_query(int kind, const double* shape, const double* grid, int res, l
                                                                              want_dir, sdf, dir);
     } else
         sdf_query_kernel<<<dim3(bx, W), 256, 0, (cudaStream_t)stream>>>(kind, shape, grid, res, grid_world_stride, pts,
-                                                                        N, want_dir, sdf, dir);
+                                                                        N, want_dir, sdf, dir, extra0, extra1);
+    return (int)cudaGetLastError();
+}
+
+int dsdf_sdf_query(int kind, const double* shape, const double* grid, int res, long long grid_world_stride,
+                   const double* pts, int W, int N, int want_dir, double* sdf, double* dir, void* stream) {
+    return dsdf_sdf_query_ex(kind, shape, 0.0, 0.0, grid, res, grid_world_stride, pts, W, N, want_dir, sdf, dir, stream);
+}
+
+int dsdf_sdf_query_backward_ex(int kind, const double* shape, double extra0, double extra1, const double* grid, int res,
+                               long long grid_world_stride, const double* pts, int W, int N, const double* gsdf,
+                               const double* gdir, double* gpts, void* stream) {
+    if (W <= 0 || N < 0 || kind < 0 || kind > DSDF_SDF_BOWL || (kind == DSDF_SDF_GRID && (!grid || res < 2))) return -1;
+    if (N == 0) return 0;
+    int bx = (N + 255) / 256;
+    if (bx > 148 * 8) bx = 148 * 8;
+    sdf_query_bwd_kernel<<<dim3(bx, W), 256, 0, (cudaStream_t)stream>>>(kind, shape, grid, res, grid_world_stride, pts,
+                                                                        N, gsdf, gdir, gpts, extra0, extra1);
     return (int)cudaGetLastError();
 }
 
 int dsdf_sdf_query_backward(int kind, const double* shape, const double* grid, int res, long long grid_world_stride,
                             const double* pts, int W, int N, const double* gsdf, const double* gdir, double* gpts,
                             void* stream) {
-    if (W <= 0 || N < 0 || kind < 0 || kind > 3 || (kind == DSDF_SDF_GRID && (!grid || res < 2))) return -1;
-    if (N == 0) return 0;
-    int bx = (N + 255) / 256;
-    if (bx > 148 * 8) bx = 148 * 8;
-    sdf_query_bwd_kernel<<<dim3(bx, W), 256, 0, (cudaStream_t)stream>>>(kind, shape, grid, res, grid_world_stride, pts,
-                                                                        N, gsdf, gdir, gpts);
-    return (int)cudaGetLastError();
+    return dsdf_sdf_query_backward_ex(kind, shape, 0.0, 0.0, grid, res, grid_world_stride, pts, W, N, gsdf, gdir, gpts,
+                                      stream);
 }
 
 int dsdf_integrate(const double* p, const double* v, const double* dt, const unsigned char* active, int W, int nb,

@@ -17,6 +17,7 @@ template <class P> struct SdfShapeT {
     P scale;
     const double* grid;  // (R,R,R) row-major, this world's grid (kind == GRID)
     int res;
+    double e0, e1;       // further parameters of the kind (rounded box / brick: r/scale), not differentiated
 };
 typedef SdfShapeT<double> SdfShape;
 
@@ -27,6 +28,7 @@ __device__ __forceinline__ SdfShape shape_values(const SdfShape& s) { return s; 
 __device__ __forceinline__ SdfShape shape_values(const SdfShapeT<Dual>& s) {
     SdfShape r;
     r.kind = s.kind; r.a = s.a.v; r.b = s.b.v; r.c = s.c.v; r.scale = s.scale.v; r.grid = s.grid; r.res = s.res;
+    r.e0 = s.e0; r.e1 = s.e1;
     return r;
 }
 
@@ -78,6 +80,51 @@ template <class S, class P> __device__ __forceinline__ void cylinder_eval(V3<S> 
     S ex = u.x, ey = u.y;
     normalize2(ex, ey);
     dir = normalize3(v3<S>(g0 * ex, g0 * ey, g1 * cst(m0, sz)));
+}
+
+// ---- brick (bodies.py:184-200): box whose first two dimensions are rounded in-plane with radius r.  Value only: the
+// reference pairs it with the direction of a CUBE of side r (rounded_sdf_grad(box_sdf_grad) receives (dims, r) and passes
+// r on as the box size, bodies.py:175-181,882-884) -- reproduced as it is.
+template <class S, class P> __device__ __forceinline__ S brick_value(V3<S> u, P dx, P dy, P dz, double r) {
+    const S half = cst(u.x, 0.5), rr = cst(u.x, r);
+    S q0 = dabs(u.x) - (par(u.x, dx) * half - rr), q1 = dabs(u.y) - (par(u.x, dy) * half - rr);
+    S q2 = dabs(u.z) - par(u.x, dz) * half;
+    S top01 = q0;
+    if (val(q1) > val(top01)) top01 = q1;
+    S s01 = norm2(clamp_min0(q0), clamp_min0(q1)) + clamp_max0(top01) - rr;
+    S top = s01;
+    if (val(q2) > val(top)) top = q2;
+    return norm2(clamp_min0(s01), clamp_min0(q2)) + clamp_max0(top);
+}
+
+// ---- bowl (bodies.py:128-163): half shell of radius r and half thickness d, opening towards +z.  The reference's
+// value and direction functions shift the z coordinate IN PLACE (pts[:, 2] -= r/2) on the same tensor, so the direction is
+// evaluated at z - r (shifted twice); `u` here is the point as the respective function sees it.
+template <class S, class P> __device__ __forceinline__ void bowl_ps(V3<S> u, P r, P d, S& ps0, S& ps1, S& psn) {
+    S rho = norm2(u.x, u.y);
+    psn = norm2(rho, u.z);
+    ps1 = u.z;
+    S first = val(u.z) < 0.0 ? psn : rho;
+    ps0 = dabs(first - par(u.x, r)) - par(u.x, d);
+}
+template <class S, class P> __device__ __forceinline__ S bowl_value(V3<S> u, P r, P d) {
+    S ps0, ps1, psn;
+    bowl_ps(u, r, d, ps0, ps1, psn);
+    S top = ps0;
+    if (val(ps1) > val(top)) top = ps1;
+    return norm2(maximum0(ps0), maximum0(ps1)) + minimum0(top);
+}
+template <class S, class P> __device__ __forceinline__ V3<S> bowl_dir(V3<S> u, P r, P d) {
+    S ps0, ps1, psn;
+    bowl_ps(u, r, d, ps0, ps1, psn);
+    const double diff = val(psn) - val(par(u.x, r));
+    const double sg = diff > 0.0 ? 1.0 : (diff < 0.0 ? -1.0 : 0.0);
+    V3<S> g = v3<S>(u.x * cst(u.x, sg), u.y * cst(u.x, sg), u.z * cst(u.x, sg));
+    if (val(ps1) >= 0.0) {
+        if (val(ps0) < 0.0) { g.x = cst(u.x, 0.0); g.y = cst(u.x, 0.0); }
+        g.z = dabs(g.z);
+    }
+    return normalize3(g);
 }
 
 // ---- grid (bodies.py:203-257 + ev_sdf_utils.grid_interp semantics)
@@ -148,7 +195,18 @@ __device__ __forceinline__ SdfOut<S> sdf_query(const SdfShapeT<P>& sh, V3<S> p, 
     if (sh.kind == DSDF_SDF_BOX) box_eval(u, sh.a, sh.b, sh.c, want_n, value, dir);
     else if (sh.kind == DSDF_SDF_SPHERE) sphere_eval(u, sh.a, want_n, value, dir);
     else if (sh.kind == DSDF_SDF_CYLINDER) cylinder_eval(u, sh.a, sh.b, want_n, value, dir);
-    else {
+    else if (sh.kind == DSDF_SDF_BOX_ROUNDED) {                 // box(dims - 2r) - r, direction of that box
+        box_eval(u, sh.a, sh.b, sh.c, want_n, value, dir);
+        value = value - cst(u.x, sh.e0);
+    } else if (sh.kind == DSDF_SDF_BRICK) {
+        value = brick_value(u, sh.a, sh.b, sh.c, sh.e0);
+        if (want_n) { S dummy; box_eval(u, sh.e0, sh.e0, sh.e0, true, dummy, dir); }
+    } else if (sh.kind == DSDF_SDF_BOWL) {
+        const S half = cst(u.x, 0.5);
+        V3<S> u1 = v3<S>(u.x, u.y, u.z - par(u.x, sh.a) * half);
+        value = bowl_value(u1, sh.a, sh.b);
+        if (want_n) dir = bowl_dir(v3<S>(u1.x, u1.y, u1.z - par(u.x, sh.a) * half), sh.a, sh.b);
+    } else {
         double v, n[3];
         // the custom backward (Dual pass) always needs the direction
         grid_eval_raw(sh.grid, sh.res, val(u.x), val(u.y), val(u.z), want_n || needs_tan(p.x), v, n);

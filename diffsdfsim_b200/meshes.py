@@ -201,3 +201,28 @@ def surface_nets(grid, iso=0.0):
     faces = np.concatenate(faces).astype(np.int32) if faces else np.zeros((0, 3), np.int32)
     assert faces.min(initial=0) >= 0, 'surface touches the grid boundary'
     return verts, faces
+
+
+def sample_sdf(kind, shape3, extra, res):
+    """(res,res,res) samples on [-1,1]^3 of the NORMALISED analytic SDFs that have no closed-form mesh generator here
+    (rounded box, brick, bowl: sdf_physics/physics3d/bodies.py:128-200), for iso-surface meshing at construction time.
+    shape3 / extra are the kernels' normalised parameters (dims / scale ..., r / scale)."""
+    t = np.linspace(-1.0, 1.0, res)
+    X, Y, Z = np.meshgrid(t, t, t, indexing='ij')
+    a, b, c = shape3
+    if kind == 'box_rounded':
+        q = np.stack([np.abs(X) - a / 2, np.abs(Y) - b / 2, np.abs(Z) - c / 2], -1)
+        return np.linalg.norm(np.maximum(q, 0), axis=-1) + np.minimum(q.max(-1), 0) - extra[0]
+    if kind == 'brick':
+        r = extra[0]
+        q0, q1, q2 = np.abs(X) - (a / 2 - r), np.abs(Y) - (b / 2 - r), np.abs(Z) - c / 2
+        s01 = np.hypot(np.maximum(q0, 0), np.maximum(q1, 0)) + np.minimum(np.maximum(q0, q1), 0) - r
+        return np.hypot(np.maximum(s01, 0), np.maximum(q2, 0)) + np.minimum(np.maximum(s01, q2), 0)
+    if kind == 'bowl':
+        r, d = a, b
+        z = Z - r / 2
+        rho = np.hypot(X, Y)
+        nrm = np.hypot(rho, z)
+        p0 = np.abs(np.where(z < 0, nrm, rho) - r) - d
+        return np.hypot(np.maximum(p0, 0), np.maximum(z, 0)) + np.minimum(np.maximum(p0, z), 0)
+    raise ValueError(kind)

@@ -4,7 +4,7 @@ import torch
 from . import _lib
 
 F64 = torch.float64
-KIND = {'box': 0, 'sphere': 1, 'cylinder': 2, 'grid': 3}
+KIND = {'box': 0, 'sphere': 1, 'cylinder': 2, 'grid': 3, 'box_rounded': 4, 'brick': 5, 'bowl': 6}
 
 
 def _c(t):
@@ -15,7 +15,7 @@ class _SdfQuery(torch.autograd.Function):
     """SDF3D.query_sdfs (bodies.py:721-760): pts (W,N,3) -> sdf (W,N), dir (W,N,3)."""
 
     @staticmethod
-    def forward(ctx, pts, shape, grid, kind, want_dir):
+    def forward(ctx, pts, shape, grid, kind, want_dir, extra=(0.0, 0.0)):
         L = _lib.lib()
         _lib.require_cuda(pts, shape)
         pts, shape = _c(pts), _c(shape)
@@ -28,11 +28,12 @@ class _SdfQuery(torch.autograd.Function):
             stride = res ** 3 if grid.dim() == 4 else 0
         sdf = torch.empty(W, N, dtype=F64, device=pts.device)
         d = torch.empty(W, N, 3, dtype=F64, device=pts.device) if want_dir else None
-        rc = _lib.call('dsdf_sdf_query', kind, _lib.ptr(shape), _lib.ptr(grid) if kind == 3 else None, res, stride,
-                              _lib.ptr(pts), W, N, int(want_dir), _lib.ptr(sdf), _lib.ptr(d), _lib.stream())
+        rc = _lib.call('dsdf_sdf_query_ex', kind, _lib.ptr(shape), float(extra[0]), float(extra[1]),
+                       _lib.ptr(grid) if kind == 3 else None, res, stride, _lib.ptr(pts), W, N, int(want_dir), _lib.ptr(sdf),
+                       _lib.ptr(d), _lib.stream())
         _lib.check(rc, 'dsdf_sdf_query')
         ctx.save_for_backward(pts, shape, grid if kind == 3 else pts.new_empty(0))
-        ctx.meta = (kind, res, stride, want_dir)
+        ctx.meta = (kind, res, stride, want_dir, extra)
         if want_dir:
             return sdf, d
         ctx.mark_non_differentiable()
@@ -42,22 +43,23 @@ class _SdfQuery(torch.autograd.Function):
     def backward(ctx, gsdf, gdir):
         L = _lib.lib()
         pts, shape, grid = ctx.saved_tensors
-        kind, res, stride, want_dir = ctx.meta
+        kind, res, stride, want_dir, extra = ctx.meta
         W, N = pts.shape[0], pts.shape[1]
         gpts = torch.empty_like(pts)
         gdir = _c(gdir) if (want_dir and gdir is not None and gdir.numel()) else None
         gsdf = _c(gsdf)                  # contiguous copies stay bound to locals until the launch has been enqueued
-        rc = _lib.call('dsdf_sdf_query_backward', kind, _lib.ptr(shape), _lib.ptr(grid) if kind == 3 else None, res, stride,
-                                       _lib.ptr(pts), W, N, _lib.ptr(gsdf), _lib.ptr(gdir), _lib.ptr(gpts),
-                                       _lib.stream())
+        rc = _lib.call('dsdf_sdf_query_backward_ex', kind, _lib.ptr(shape), float(extra[0]), float(extra[1]),
+                       _lib.ptr(grid) if kind == 3 else None, res, stride, _lib.ptr(pts), W, N, _lib.ptr(gsdf), _lib.ptr(gdir),
+                       _lib.ptr(gpts), _lib.stream())
         _lib.check(rc, 'dsdf_sdf_query_backward')
-        return gpts, None, None, None, None
+        return gpts, None, None, None, None, None
 
 
-def sdf_query(kind, shape, pts, grid=None, want_dir=True):
-    """kind: 'box'|'sphere'|'cylinder'|'grid' (or int); shape (W,4); pts (W,N,3); grid (W,R,R,R) or (R,R,R)."""
+def sdf_query(kind, shape, pts, grid=None, want_dir=True, extra=(0.0, 0.0)):
+    """kind: 'box'|'sphere'|'cylinder'|'grid'|'box_rounded'|'brick'|'bowl' (or int); shape (W,4); pts (W,N,3);
+    grid (W,R,R,R) or (R,R,R); extra: the kind's further parameters (rounded box / brick: r / scale)."""
     k = KIND[kind] if isinstance(kind, str) else int(kind)
-    sdf, d = _SdfQuery.apply(pts, shape, grid, k, want_dir)
+    sdf, d = _SdfQuery.apply(pts, shape, grid, k, want_dir, tuple(extra))
     return (sdf, d) if want_dir else sdf
 
 

@@ -62,6 +62,10 @@ def make_bodies(spec, device=None, params=None, W=1):
             ob = B.SDFSphere(pos, rad, subdivisions=(b['mesh'] or {}).get('subdivisions', 4), **kw)
         elif k == 'cylinder':
             ob = B.SDFCylinder(pos, b['rad'], b['height'], max_tri_length=b['max_tri_length'], **kw)
+        elif k in ('box_rounded', 'brick'):
+            ob = (B.SDFBoxRounded if k == 'box_rounded' else B.SDFBrick)(pos, b['dims'], b['rad'], mesh=extra_kind_mesh(b), **kw)
+        elif k == 'bowl':
+            ob = B.SDFBowl(pos, b['rad'], b['height'], mesh=extra_kind_mesh(b), **kw)
         elif k == 'grid':
             grid, mesh = grid_array(b), grid_mesh(b)
             if last and 'grid' in params:          # per-world grids (W,R,R,R) and, optionally, per-world vertices
@@ -161,6 +165,24 @@ def inertia_fitting(dims=(1.0, 0.5, 0.25), torque=(1.0, 0.5, 0.25), until=0.3, m
 
 
 _GRID_CACHE = {}
+
+
+def extra_kind_mesh(b, res=64):
+    """(verts, faces) of a rounded box / brick / bowl body spec: iso-surface of its sampled SDF (memoised)."""
+    from . import bodies as B
+    key = ('xmesh', b['kind'], tuple(b['dims'] or ()), b['rad'], b['height'], res)
+    if key not in _GRID_CACHE:
+        if b['kind'] == 'bowl':
+            r, d = float(b['rad']), float(b['height'])
+            sc = (r + d) * 1.3333
+            shape, extra = [r / sc, d / sc, 0.0], (0.0, 0.0)
+        else:
+            dims, r = np.asarray(b['dims'], dtype=np.float64), float(b['rad'])
+            sc = dims.max() * 1.5 / 2
+            shape = ((dims - 2 * r) / sc if b['kind'] == 'box_rounded' else dims / sc).tolist()
+            extra = (r / sc, 0.0)
+        _GRID_CACHE[key] = B._sampled_mesh(b['kind'], shape, extra, sc, res)
+    return _GRID_CACHE[key]
 
 
 def grid_array(b):
@@ -339,3 +361,15 @@ def mixed16_floor(seed=0, steps=6, spacing=1.5, floor=(8.0, 1.0, 8.0), floor_tri
             r, h = float(0.2 + 0.2 * rng.rand()), float(0.4 + 0.4 * rng.rand())
             bodies.append(body('cylinder', [x, r + gap, z], rad=r, height=h, max_tri_length=tri, **kw))   # axis = z: lying
     return scene(bodies, steps=steps)
+
+
+def rounded_box_on_plane(kind='box_rounded', dims=(0.8, 0.5, 0.6), r=0.1, floor=(4.0, 1.0, 4.0), push=(3.0, 2.0), fric=0.2,
+                         gap=2 * EPS, steps=6, floor_tri=0.2):
+    """A rounded box (or brick) -- sdf_physics/physics3d/bodies.py:856-886 -- resting ``gap`` above a pinned floor, pushed
+    along x, z; its mesh is the iso-surface of its own sampled SDF."""
+    return scene([
+        body('box', [0, -floor[1] / 2, 0], dims=list(floor), pinned=True, fric_coeff=fric, restitution=0.5,
+             max_tri_length=floor_tri),
+        body(kind, [0.0, dims[1] / 2 + gap, 0.0], dims=list(dims), rad=r, fric_coeff=fric, restitution=0.5, gravity=True,
+             ext_force=[0, 0, 0, push[0], 0, push[1]]),
+    ], strict_no_penetration=False, steps=steps)

@@ -38,6 +38,9 @@ extern "C" {
 #define DSDF_SDF_SPHERE   1
 #define DSDF_SDF_CYLINDER 2
 #define DSDF_SDF_GRID     3
+#define DSDF_SDF_BOX_ROUNDED 4   /* bodies.py:166-181,856-870: box(dims - 2r) - r; shape = (dims-2r)/scale, extra[0] = r/scale   */
+#define DSDF_SDF_BRICK    5      /* bodies.py:184-200,873-886: in-plane rounded box; shape = dims/scale, extra[0] = r/scale        */
+#define DSDF_SDF_BOWL     6      /* bodies.py:128-163,1012-1026: half shell; shape = [r/scale, d/scale]                            */
 
 int dsdf_version(void);
 
@@ -94,6 +97,13 @@ int dsdf_sdf_query(int kind, const double* shape, const double* grid, int res, l
 int dsdf_sdf_query_backward(int kind, const double* shape, const double* grid, int res, long long grid_world_stride,
                             const double* pts, int W, int N, const double* gsdf, const double* gdir, double* gpts,
                             void* stream);
+/* The same with the extra parameters of the kinds that need more than three (DSDF_SDF_BOX_ROUNDED / BRICK: extra0 = r/scale). */
+int dsdf_sdf_query_ex(int kind, const double* shape, double extra0, double extra1, const double* grid, int res,
+                      long long grid_world_stride, const double* pts, int W, int N, int want_dir, double* sdf, double* dir,
+                      void* stream);
+int dsdf_sdf_query_backward_ex(int kind, const double* shape, double extra0, double extra1, const double* grid, int res,
+                               long long grid_world_stride, const double* pts, int W, int N, const double* gsdf,
+                               const double* gdir, double* gpts, void* stream);
 
 /* ----------------------------------------------------------- integrator ----
  * Replaces Body3D.move (sdf_physics/physics3d/bodies.py:488-496): q <- standardize(quat(expmap(w dt)) * q),
@@ -133,6 +143,7 @@ typedef struct dsdf_body_geom {
      * the allocated maxima).  0 / NULL = one topology shared by all worlds. */
     long long face_world_stride;
     const int32_t *nfaces_w, *nverts_w;
+    double extra[2];              /* further SDF parameters of the body kind (rounding radius / scale), shared by all worlds */
 } dsdf_body_geom;
 
 /* per-world contact status bits (int32) */

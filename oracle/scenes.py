@@ -29,6 +29,8 @@ def mesh_for(b):
         return meshes.cylinder_mesh(b['rad'], b['height'], 32, b['max_tri_length'])
     if k == 'grid':
         return scenes.grid_mesh(b)
+    if k in ('box_rounded', 'brick', 'bowl'):
+        return scenes.extra_kind_mesh(b)
     raise ValueError(k)
 
 
@@ -49,6 +51,17 @@ def shape_for(b, mass):
         sc = torch.max(r, h / 2) * 1.5
         I = mass * torch.diag(torch.stack([(3 * r ** 2 + h ** 2) / 12, (3 * r ** 2 + h ** 2) / 12, r ** 2 / 2]))
         return S.CYLINDER, [r / sc, h / sc], sc, I
+    if k in ('box_rounded', 'brick'):
+        d, r = tens(b['dims']), tens(float(b['rad']))
+        sc = d.max() * 1.5 / 2
+        v, f = scenes.extra_kind_mesh(b)
+        I = mass * tens(meshes.mesh_inertia(v, f))
+        return (S.BOX_ROUNDED, [(d - 2 * r) / sc, r / sc], sc, I) if k == 'box_rounded' else (S.BRICK, [d / sc, r / sc], sc, I)
+    if k == 'bowl':
+        r, d = tens(float(b['rad'])), tens(float(b['height']))
+        sc = (r + d) * 1.3333
+        v, f = scenes.extra_kind_mesh(b)
+        return S.BOWL, [r / sc, d / sc], sc, mass * tens(meshes.mesh_inertia(v, f))
     if k == 'grid':
         grid = tens(scenes.grid_array(b))
         return S.GRID, [grid], tens(b['scale']), mass * tens(scenes.grid_unit_inertia(b))

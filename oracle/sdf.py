@@ -17,7 +17,7 @@ reference (clamp vs. maximum sub-gradients, sign(0) handling):
 import torch
 from torch.nn.functional import normalize
 
-BOX, SPHERE, CYLINDER, GRID = 0, 1, 2, 3
+BOX, SPHERE, CYLINDER, GRID, BOX_ROUNDED, BRICK, BOWL = 0, 1, 2, 3, 4, 5, 6
 
 
 # ----------------------------------------------------------------- analytic
@@ -66,6 +66,54 @@ def cylinder_direction(x, rad, height):
     g2 = normalize(q.clamp(min=0.), dim=1) + (top <= 0).to(x.dtype).unsqueeze(1) * tie
     g = torch.cat([g2[:, 0:1] * normalize(x[:, :2], dim=1), (g2[:, 1] * sgn).unsqueeze(1)], dim=1)
     return normalize(g, dim=1)
+
+
+# ------------------------------------------------- rounded box / brick / bowl (bodies.py:128-200)
+def rounded_box_value(x, dims, r):
+    """rounded_sdf(box_sdf) with params [r, dims] (bodies.py:166-172, 866-867)."""
+    return box_value(x, dims) - r
+
+
+def rounded_box_direction(x, dims, r):
+    return box_direction(x, dims)
+
+
+def brick_value(x, dims, r):
+    """bodies.py:184-200."""
+    half = torch.cat([dims[:2] / 2 - r, dims[2:3] / 2])
+    q = x.abs() - half
+    top01 = q[:, :2].max(dim=1)[0]
+    s01 = q[:, :2].clamp(min=0.).norm(dim=1) + top01.clamp(max=0.) - r
+    q2 = torch.stack([s01, q[:, 2]], dim=1)
+    return q2.clamp(min=0.).norm(dim=1) + q2.max(dim=1)[0].clamp(max=0.)
+
+
+def brick_direction(x, dims, r):
+    """The reference's wrapper hands the SECOND parameter (r) to box_sdf_grad as the box size (bodies.py:175-181, 882-884)."""
+    return box_direction(x, r)
+
+
+def _bowl_ps(x, r, d):
+    ps = torch.stack([x[:, :2].norm(dim=1), x[:, 2]], dim=1)
+    nrm = ps.norm(dim=1)
+    first = torch.where(ps[:, 1] < 0, nrm, ps[:, 0])
+    return torch.stack([(first - r).abs() - d, ps[:, 1]], dim=1), nrm
+
+
+def bowl_value(x, r, d):
+    """bodies.py:128-142; the in-place shift of the caller's tensor is made explicit by ``query``."""
+    ps, _ = _bowl_ps(x, r, d)
+    return torch.max(ps, ps.new_zeros(1)).norm(dim=1) + torch.min(ps.new_zeros(1), ps.max(dim=1)[0])
+
+
+def bowl_direction(x, r, d):
+    """bodies.py:145-163."""
+    ps, nrm = _bowl_ps(x, r, d)
+    g = x * (nrm - r).sign().unsqueeze(1)
+    up = ps[:, 1] >= 0
+    gxy = torch.where((up & (ps[:, 0] < 0)).unsqueeze(1), torch.zeros_like(g[:, :2]), g[:, :2])
+    gz = torch.where(up, g[:, 2].abs(), g[:, 2])
+    return normalize(torch.cat([gxy, gz.unsqueeze(1)], dim=1), dim=1)
 
 
 # --------------------------------------------------------------------- grid
@@ -142,8 +190,10 @@ def grid_value(x, grid):
     return _GridValue.apply(x, grid)
 
 
-_VALUE = {BOX: box_value, SPHERE: sphere_value, CYLINDER: cylinder_value, GRID: grid_value}
-_DIRECTION = {BOX: box_direction, SPHERE: sphere_direction, CYLINDER: cylinder_direction, GRID: grid_direction}
+_VALUE = {BOX: box_value, SPHERE: sphere_value, CYLINDER: cylinder_value, GRID: grid_value,
+          BOX_ROUNDED: rounded_box_value, BRICK: brick_value, BOWL: bowl_value}
+_DIRECTION = {BOX: box_direction, SPHERE: sphere_direction, CYLINDER: cylinder_direction, GRID: grid_direction,
+              BOX_ROUNDED: rounded_box_direction, BRICK: brick_direction, BOWL: bowl_direction}
 
 
 def query(kind, params, scale, pts, want_dir=True):
@@ -157,8 +207,17 @@ def query(kind, params, scale, pts, want_dir=True):
     direction = pts.new_zeros(pts.shape)
     if torch.any(inside):
         u = pts[inside] / scale
-        val[inside] = _VALUE[kind](u, *params)
-        if want_dir:
-            direction[inside] = normalize(_DIRECTION[kind](u, *params), dim=1)
+        if kind == BOWL:
+            # bowl_sdf and bowl_sdf_grad both shift the z coordinate of the SAME tensor in place (bodies.py:129,146):
+            # the value sees z - r/2, the direction z - r
+            shift = torch.stack([torch.zeros_like(params[0]), torch.zeros_like(params[0]), params[0] / 2])
+            u = u - shift
+            val[inside] = _VALUE[kind](u, *params)
+            if want_dir:
+                direction[inside] = normalize(_DIRECTION[kind](u - shift, *params), dim=1)
+        else:
+            val[inside] = _VALUE[kind](u, *params)
+            if want_dir:
+                direction[inside] = normalize(_DIRECTION[kind](u, *params), dim=1)
     val = val * scale
     return (val, direction) if want_dir else val

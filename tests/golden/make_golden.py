@@ -240,6 +240,19 @@ def golden_sdf():
         pts[:64] = torch.round(pts[:64] / s * 4) / 4 * s
         sd, gr = b.query_sdfs(pts)
         d[nm + '_pts'], d[nm + '_sdf'], d[nm + '_dir'] = pts.numpy(), sd.numpy(), gr.numpy()
+    # rounded box / brick / bowl (bodies.py:128-200, 856-886, 1012-1026): the reference classes with an injected mesh
+    from diffsdfsim_b200 import bodies as pb
+    shapes = {'box_rounded': (rb.SDFBoxRounded, pb.SDFBoxRounded, ([0.8, 0.5, 0.6], 0.1)),
+              'brick': (rb.SDFBrick, pb.SDFBrick, ([1.0, 0.6, 0.5], 0.1)),
+              'bowl': (rb.SDFBowl, pb.SDFBowl, (0.6, 0.15))}
+    for nm, (ref_cls, our_cls, args) in shapes.items():
+        ours = our_cls([0.0, 0.0, 0.0], *args)                       # (mesh generator only)
+        b = _inject(ref_cls, ours.verts.numpy(), ours.faces.numpy())(torch.zeros(3, dtype=F64), *args)
+        s = float(b.scale)
+        pts = (torch.rand(4096, 3, generator=g, dtype=F64) * 2 - 1) * s * 1.1
+        pts[:64] = torch.round(pts[:64] / s * 4) / 4 * s
+        sd, gr = b.query_sdfs(pts.clone())
+        d[nm + '_pts'], d[nm + '_sdf'], d[nm + '_dir'] = pts.numpy(), sd.numpy(), gr.numpy()
     np.savez_compressed(os.path.join(HERE, 'sdf_query.npz'), **d)
     print('sdf_query', {k: v.shape for k, v in d.items()})
 

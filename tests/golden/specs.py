@@ -53,3 +53,25 @@ def make_spec(name, g=None):
     else:
         spec = mk()
     return spec, default_leaves(spec, leaves)
+
+
+def extra_sdf_kinds():
+    """The analytic SDFs beyond box / sphere / cylinder (bodies.py:128-200): name -> (oracle kind id, normalised parameter
+    tensors in the oracle's order, scale, kernel shape row [a,b,c,scale], kernel extra parameters).  Same bodies as the
+    reference instances behind tests/golden/sdf_query.npz."""
+    import torch
+    from oracle import sdf as S
+    F64 = torch.float64
+    out = {}
+    dims, r = torch.tensor([0.8, 0.5, 0.6], dtype=F64), 0.1
+    sc = dims.max() * 1.5 / 2
+    out['box_rounded'] = (S.BOX_ROUNDED, [(dims - 2 * r) / sc, torch.tensor(r, dtype=F64) / sc], sc,
+                          torch.cat([(dims - 2 * r) / sc, sc.reshape(1)]), (float(r / sc), 0.0))
+    dims = torch.tensor([1.0, 0.6, 0.5], dtype=F64)
+    sc = dims.max() * 1.5 / 2
+    out['brick'] = (S.BRICK, [dims / sc, torch.tensor(r, dtype=F64) / sc], sc, torch.cat([dims / sc, sc.reshape(1)]),
+                    (float(r / sc), 0.0))
+    rr, d = torch.tensor(0.6, dtype=F64), torch.tensor(0.15, dtype=F64)
+    sc = (rr + d) * 1.3333
+    out['bowl'] = (S.BOWL, [rr / sc, d / sc], sc, torch.stack([rr / sc, d / sc, torch.zeros((), dtype=F64), sc]), (0.0, 0.0))
+    return out

@@ -106,3 +106,29 @@ def test_integrator_forward_backward_vs_oracle():
     act[::2] = 0
     res2 = integrate(pg.detach(), vg.detach(), dtg.detach(), act)
     assert torch.equal(res2[::2], pg.detach()[::2]) and torch.equal(res2[1::2], res.detach()[1::2])
+
+
+@pytest.mark.parametrize('kind', ['box_rounded', 'brick', 'bowl'])
+def test_extra_sdf_kinds_match_reference_golden_and_oracle_autograd(kind):
+    """Rounded box / brick / bowl (bodies.py:128-200): values and directions vs the reference instances, point gradients
+    vs the oracle's autograd."""
+    from diffsdfsim_b200.ops import sdf_query
+    from specs import extra_sdf_kinds
+    g = np.load(os.path.join(GOLD, 'sdf_query.npz'))
+    k, params, scale, row, extra = extra_sdf_kinds()[kind]
+    pts = torch.tensor(g[kind + '_pts'], device='cuda')[None]
+    sd, d = sdf_query(kind, row.cuda()[None], pts, extra=extra)
+    np.testing.assert_allclose(sd[0].cpu().numpy(), g[kind + '_sdf'], rtol=0, atol=1e-14)
+    np.testing.assert_allclose(d[0].cpu().numpy(), g[kind + '_dir'], rtol=0, atol=1e-13)
+    gen = torch.Generator().manual_seed(1)
+    N = 2000
+    p0 = (torch.rand(N, 3, generator=gen, dtype=F64) * 2 - 1) * float(scale) * 1.05
+    ws, wd = torch.randn(N, generator=gen, dtype=F64), torch.randn(N, 3, generator=gen, dtype=F64)
+    po = p0.clone().requires_grad_(True)
+    so, do = S.query(k, params, scale, po)
+    ((so * ws).sum() + (do * wd).sum()).backward()
+    pg = p0.cuda()[None].requires_grad_(True)
+    sg, dg = sdf_query(kind, row.cuda()[None], pg, extra=extra)
+    ((sg[0] * ws.cuda()).sum() + (dg[0] * wd.cuda()).sum()).backward()
+    ref = po.grad.numpy()
+    np.testing.assert_allclose(pg.grad[0].cpu().numpy(), ref, rtol=1e-9, atol=1e-9 * max(1.0, np.abs(ref).max()))

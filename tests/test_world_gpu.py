@@ -470,3 +470,38 @@ def test_per_world_topologies_match_oracle_per_world():
         ref = leaf.grad.numpy()
         np.testing.assert_allclose(params['pos'].grad[w].cpu().numpy(), ref, rtol=1e-4,
                                    atol=1e-4 * max(1e-9, np.abs(ref).max()), err_msg=f'world {w} grad pos')
+
+
+@pytest.mark.parametrize('kind', ['box_rounded'])
+def test_rounded_box_world_matches_oracle_per_world(kind):
+    """Bodies with the reference's remaining analytic SDFs (bodies.py:166-200, 856-886) stepping on a floor: poses,
+    velocities, contact counts and mass / friction gradients vs the oracle, world by world."""
+    W, steps = 2, 6
+    mass = torch.tensor([0.9, 1.2], dtype=F64)
+    fric = torch.tensor([0.1, 0.25], dtype=F64)
+    spec = scenes.rounded_box_on_plane(kind=kind, steps=steps)
+    params = dict(mass=mass.cuda().requires_grad_(True), fric_coeff=fric.cuda().requires_grad_(True))
+    world = scenes.build_world(spec, device='cuda', params=params, capK=768)
+    loss, traj = 0., []
+    for k in range(steps):
+        world.step(fixed_dt=True)
+        traj.append((world.get_p().detach().cpu(), world.v.detach().cpu(), world.contact_set.count.cpu()))
+        loss = loss + (world.bodies[-1].pos ** 2).sum()
+    loss.backward()
+    assert int(traj[-1][2].min()) >= 1, 'the body must be in contact with the floor'
+    for w in range(W):
+        leaves = dict(mass=mass[w].clone().requires_grad_(True), fric_coeff=fric[w].clone().requires_grad_(True))
+        ow = build_oracle(spec, leaves)
+        lo = 0.
+        for k in range(steps):
+            ow.step()
+            np.testing.assert_allclose(traj[k][0][w].numpy(), ow.get_p().detach().numpy(), atol=1e-7, rtol=0)
+            np.testing.assert_allclose(traj[k][1][w].numpy(), ow.v.detach().numpy(), atol=1e-5, rtol=0)
+            assert int(traj[k][2][w]) == len(ow.contacts), f'world {w} step {k}: contact count'
+            lo = lo + (ow.bodies[-1].pos ** 2).sum()
+        lo.backward()
+        for k in leaves:
+            ref = leaves[k].grad.numpy()
+            got = params[k].grad[w].cpu().numpy()
+            np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4 * max(1e-9, np.abs(ref).max()),
+                                       err_msg=f'{kind}: world {w} grad {k}')
