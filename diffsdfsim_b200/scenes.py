@@ -168,8 +168,10 @@ _GRID_CACHE = {}
 
 
 def extra_kind_mesh(b, res=64):
-    """(verts, faces) of a rounded box / brick / bowl body spec: iso-surface of its sampled SDF (memoised)."""
+    """(verts, faces) of a rounded box / brick / bowl body spec: iso-surface of its sampled SDF (memoised); the sampling
+    resolution comes from the spec's mesh=dict(res=...)."""
     from . import bodies as B
+    res = (b.get('mesh') or {}).get('res', res)
     key = ('xmesh', b['kind'], tuple(b['dims'] or ()), b['rad'], b['height'], res)
     if key not in _GRID_CACHE:
         if b['kind'] == 'bowl':
@@ -364,12 +366,12 @@ def mixed16_floor(seed=0, steps=6, spacing=1.5, floor=(8.0, 1.0, 8.0), floor_tri
 
 
 def rounded_box_on_plane(kind='box_rounded', dims=(0.8, 0.5, 0.6), r=0.1, floor=(4.0, 1.0, 4.0), push=(3.0, 2.0), fric=0.2,
-                         gap=2 * EPS, steps=6, floor_tri=0.2):
+                         gap=2 * EPS, steps=6, floor_tri=0.2, mesh_res=28):
     """A rounded box (or brick) -- sdf_physics/physics3d/bodies.py:856-886 -- resting ``gap`` above a pinned floor, pushed
     along x, z; its mesh is the iso-surface of its own sampled SDF."""
     return scene([
         body('box', [0, -floor[1] / 2, 0], dims=list(floor), pinned=True, fric_coeff=fric, restitution=0.5,
              max_tri_length=floor_tri),
         body(kind, [0.0, dims[1] / 2 + gap, 0.0], dims=list(dims), rad=r, fric_coeff=fric, restitution=0.5, gravity=True,
-             ext_force=[0, 0, 0, push[0], 0, push[1]]),
+             ext_force=[0, 0, 0, push[0], 0, push[1]], mesh=dict(res=mesh_res)),
     ], strict_no_penetration=False, steps=steps)
