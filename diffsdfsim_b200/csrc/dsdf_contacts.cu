@@ -375,6 +375,161 @@ __device__ __noinline__ void bred_multi(double* v, const int* ops, int n, double
     for (int i = 0; i < n; ++i) v[i] = red[32 + i];
 }
 
+// ------------------------------------------------------------------------------------------ 3-D convex hull
+// Vertices of the convex hull of a genuinely three-dimensional cluster of contact points (contacts.py:126-133: scipy's
+// Qhull on the host in the reference): gift wrapping with all threads of the CTA scanning the points of every wrap step.
+// Around a directed hull edge s -> t whose known face has outward normal n0 and in-plane direction m0 (from the edge
+// towards that face), the neighbouring face is spanned by the point with the smallest rotation angle phi from the
+// continuation of the known plane; among points on that same plane (planar facets with more than three vertices) the next
+// boundary vertex of the facet polygon wins (most clockwise about t, farthest on ties), so points inside a facet or inside
+// an edge are never selected -- Qhull's merged-facet vertex set.  Faces are triangles (t, s, c); an m x m bit matrix
+// remembers which directed edges already belong to a face.
+struct HullPick { int idx; double x, y, al, rho; };
+
+__device__ __forceinline__ bool hull_better(const HullPick& p, const HullPick& q, double L) {
+    // true when p beats q (q may be empty)
+    if (q.idx < 0) return p.idx >= 0;
+    if (p.idx < 0) return false;
+    const double det = p.x * q.y - q.x * p.y;                          // > 0: phi_p < phi_q
+    const double tol = 1e-13 * p.rho * q.rho;
+    if (det > tol) return true;
+    if (det < -tol) return false;
+    // same plane: next boundary vertex of the facet polygon after t (coordinates (al, rho), rho >= 0, t at (L, 0))
+    // (the facet lies in the wedge at t between the direction towards s, angle pi, and its other neighbour of t: the
+    // candidate with the SMALLEST angle about t is that neighbour -- a vertex of the facet, never an interior point)
+    const double cr = (q.al - L) * p.rho - q.rho * (p.al - L);        // cross(q - t, p - t) > 0: angle_p > angle_q
+    const double dp2 = (p.al - L) * (p.al - L) + p.rho * p.rho, dq2 = (q.al - L) * (q.al - L) + q.rho * q.rho;
+    const double tol2 = 1e-13 * sqrt(dp2 * dq2);
+    if (cr < -tol2) return true;
+    if (cr > tol2) return false;
+    if (dp2 != dq2) return dp2 > dq2;
+    return p.idx < q.idx;
+}
+
+// one wrap step; all threads call it; returns the chosen point (index into the cluster's member list) or -1
+__device__ int hull_wrap(const double* PX, const double* PY, const double* PZ, const int* HI, int m, V3<double> S,
+                         V3<double> T, V3<double> n0, V3<double> m0, int skip_s, int skip_t, double* red) {
+    const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
+    const V3<double> E = T - S;
+    const double L = norm3(E);
+    const V3<double> e = v3<double>(E.x / L, E.y / L, E.z / L);
+    HullPick best; best.idx = -1; best.x = best.y = best.al = best.rho = 0.0;
+    for (int i = tid; i < m; i += nt) {
+        if (i == skip_s || i == skip_t) continue;
+        const int k = HI[i];
+        const V3<double> d = v3<double>(PX[k], PY[k], PZ[k]) - S;
+        HullPick c;
+        c.idx = i;
+        c.al = dot(d, e);
+        const V3<double> r = d - e * c.al;
+        c.rho = norm3(r);
+        if (!(c.rho > 1e-14 * (L + fabs(c.al)))) continue;              // on the edge's line: not a candidate
+        c.x = -dot(r, m0);
+        c.y = -dot(r, n0);
+        if (hull_better(c, best, L)) best = c;
+    }
+#pragma unroll 1
+    for (int o = 16; o > 0; o >>= 1) {
+        HullPick q;
+        q.idx = __shfl_xor_sync(DSDF_FULL, best.idx, o);
+        q.x = __shfl_xor_sync(DSDF_FULL, best.x, o); q.y = __shfl_xor_sync(DSDF_FULL, best.y, o);
+        q.al = __shfl_xor_sync(DSDF_FULL, best.al, o); q.rho = __shfl_xor_sync(DSDF_FULL, best.rho, o);
+        if (hull_better(q, best, L)) best = q;
+    }
+    __syncthreads();
+    if (lane == 0) {
+        red[warp * 5] = (double)best.idx; red[warp * 5 + 1] = best.x; red[warp * 5 + 2] = best.y;
+        red[warp * 5 + 3] = best.al; red[warp * 5 + 4] = best.rho;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        HullPick b; b.idx = -1; b.x = b.y = b.al = b.rho = 0.0;
+        for (int ww = 0; ww < nw; ++ww) {
+            HullPick q;
+            q.idx = (int)red[ww * 5]; q.x = red[ww * 5 + 1]; q.y = red[ww * 5 + 2]; q.al = red[ww * 5 + 3]; q.rho = red[ww * 5 + 4];
+            if (hull_better(q, b, L)) b = q;
+        }
+        red[39] = (double)b.idx;
+    }
+    __syncthreads();
+    return (int)red[39];
+}
+
+// marks KEEP[HI[i]] = 1 for the hull vertices of the cluster's m points; returns false when the work buffers are too
+// small for m (the caller keeps the whole cluster and flags it).  bits: >= m*m/32 + 1 ints; stk0 / stk1: cap ints each.
+__device__ bool hull3d_vertices(const double* PX, const double* PY, const double* PZ, const int* HI, int m, int* KEEP,
+                                unsigned* bits, size_t nbits_ints, int* stk0, int* stk1, int cap, double* red,
+                                double maxabs) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    if ((size_t)m * m / 32 + 1 > nbits_ints || 3 * m > 2 * cap || m > 1023) return false;
+    for (size_t i = tid; i < (size_t)m * m / 32 + 1; i += nt) bits[i] = 0u;
+    __shared__ int s_top, s_a;
+    // lexicographically smallest point: a hull vertex
+    if (tid == 0) {
+        int a = 0;
+        for (int i = 1; i < m; ++i) {
+            const int k = HI[i], ka = HI[a];
+            if (PX[k] < PX[ka] || (PX[k] == PX[ka] && (PY[k] < PY[ka] || (PY[k] == PY[ka] && PZ[k] < PZ[ka])))) a = i;
+        }
+        s_a = a; s_top = 0;
+    }
+    __syncthreads();
+    const int a = s_a;
+    auto P = [&](int i) { const int k = HI[i]; return v3<double>(PX[k], PY[k], PZ[k]); };
+    auto unit = [](V3<double> v) { const double n = norm3(v); return v3<double>(v.x / n, v.y / n, v.z / n); };
+    auto edge_done = [&](int u, int v) { const size_t b = (size_t)u * m + v; return (bits[b >> 5] >> (b & 31)) & 1u; };
+    auto mark_edge = [&](int u, int v) { const size_t b = (size_t)u * m + v; bits[b >> 5] |= 1u << (b & 31); };
+    auto push = [&](int s_, int t_, int w_) {
+        const int top = s_top++;
+        (top < cap ? stk0[top] : stk1[top - cap]) = s_ | (t_ << 10) | (w_ << 20);
+    };
+    // first edge: wrap around the vertical line through a (virtual end point far above every point), starting from the
+    // supporting plane x = a.x: "known face" (a, virtual, a + e_y), outward normal -e_x = e_z x e_y
+    const V3<double> A = P(a);
+    const V3<double> Vt = A + v3<double>(0.0, 0.0, 8.0 * maxabs + 1.0);
+    const int b = hull_wrap(PX, PY, PZ, HI, m, A, Vt, v3<double>(-1.0, 0.0, 0.0), v3<double>(0.0, 1.0, 0.0), a, -1, red);
+    if (b < 0) return true;                                             // (cannot happen for a non-degenerate cluster)
+    // first face: wrap around a -> b; the known face is the vertical supporting plane (a, b, virtual) just found
+    const V3<double> Bp = P(b);
+    {
+        const V3<double> eab = unit(Bp - A);
+        V3<double> rw = (Vt - A) - eab * dot(Vt - A, eab);
+        const int c = hull_wrap(PX, PY, PZ, HI, m, A, Bp, unit(cross(Bp - A, Vt - A)), unit(rw), a, b, red);
+        if (c < 0) return true;
+        if (tid == 0) {
+            KEEP[HI[a]] = 1; KEEP[HI[b]] = 1; KEEP[HI[c]] = 1;
+            // face (b, a, c): counter-clockwise seen from outside
+            mark_edge(b, a); mark_edge(a, c); mark_edge(c, b);
+            push(b, a, c); push(a, c, b); push(c, b, a);
+        }
+    }
+    __syncthreads();
+    for (int guard = 0; guard < 8 * m + 64; ++guard) {
+        __syncthreads();
+        if (s_top == 0) break;
+        const int top = s_top - 1;
+        const int ent = top < cap ? stk0[top] : stk1[top - cap];
+        const int s_ = ent & 1023, t_ = (ent >> 10) & 1023, w_ = ent >> 20;
+        const bool need = !edge_done(t_, s_);                            // the face across s -> t (it contains t -> s)
+        __syncthreads();
+        if (tid == 0) s_top = top;
+        if (!need) continue;
+        const V3<double> Sp = P(s_), Tp = P(t_), Wp = P(w_);
+        const V3<double> e = unit(Tp - Sp);
+        const V3<double> rw = (Wp - Sp) - e * dot(Wp - Sp, e);
+        const int c = hull_wrap(PX, PY, PZ, HI, m, Sp, Tp, unit(cross(Tp - Sp, Wp - Sp)), unit(rw), s_, t_, red);
+        if (c < 0) continue;
+        if (tid == 0) {
+            KEEP[HI[c]] = 1;
+            // new face (t, s, c)
+            mark_edge(t_, s_); mark_edge(s_, c); mark_edge(c, t_);
+            if (s_top + 2 <= 2 * cap) { push(s_, c, t_); push(c, t_, s_); }
+        }
+    }
+    __syncthreads();
+    return true;
+}
+
 // ------------------------------------------------------------------------------------------ refine kernel
 struct RefineSmem {
     double* P;      // [9][capK] candidate triangle in b2 frame, later GEO rows 0..8
@@ -726,9 +881,16 @@ __device__ int filter_contacts(const RefineSmem& sm, int capK, int n, double eps
             flat3 = true;
         }
         if (!flat3) {
-            // genuine 3-D point set: every point of a tetrahedron is a hull vertex; larger sets are kept whole (flagged)
-            if (m > 4) status |= 4;
-            for (int e = tid; e < m; e += nt) sm.KEEP[sm.HI[e]] = 1;
+            // genuine 3-D point set (contacts.py:126-133 succeeds with the 3-D Qhull): every point of a tetrahedron is a
+            // hull vertex; larger sets go through the gift-wrapping hull (work buffers: HK as edge bit matrix, SC / TMP as
+            // stack); a cluster too large for the buffers is kept whole and flagged
+            bool done = false;
+            if (m > 4) {
+                done = hull3d_vertices(PX, PY, PZ, sm.HI, m, sm.KEEP, reinterpret_cast<unsigned*>(sm.HK),
+                                       (size_t)4 * capK, sm.SC, sm.TMP, capK, sm.red, mx);
+                if (!done) status |= 4;
+            }
+            if (!done) for (int e = tid; e < m; e += nt) sm.KEEP[sm.HI[e]] = 1;
             __syncthreads();
             continue;
         }
