@@ -382,59 +382,46 @@ __device__ __noinline__ void bred_multi(double* v, const int* ops, int n, double
 // towards that face), the neighbouring face is spanned by the point with the smallest rotation angle phi from the
 // continuation of the known plane; among points on that same plane (planar facets with more than three vertices) the next
 // boundary vertex of the facet polygon wins (most clockwise about t, farthest on ties), so points inside a facet or inside
-// an edge are never selected -- Qhull's merged-facet vertex set.  Faces are triangles (t, s, c); an m x m bit matrix
-// remembers which directed edges already belong to a face.
+// an edge are never selected -- Qhull's merged-facet vertex set.  Faces are triangles (t, s, c); a hash set (open
+// addressing, filled by thread 0) remembers which directed edges already belong to a face.
 struct HullPick { int idx; double x, y, al, rho; };
 
-__device__ __forceinline__ bool hull_better(const HullPick& p, const HullPick& q, double L) {
-    // true when p beats q (q may be empty)
+// primary order: smaller rotation angle phi in [0, pi] (y is clamped at 0, so the 2x2 determinant orders the angles; phi = 0
+// against phi = pi has det == 0 and is decided by x).  Strict -- a total order, exact ties by index.
+__device__ __forceinline__ bool hull_phi_less(const HullPick& p, const HullPick& q) {
     if (q.idx < 0) return p.idx >= 0;
     if (p.idx < 0) return false;
     const double det = p.x * q.y - q.x * p.y;                          // > 0: phi_p < phi_q
-    const double tol = 1e-13 * p.rho * q.rho;
-    if (det > tol) return true;
-    if (det < -tol) return false;
-    // same plane: next boundary vertex of the facet polygon after t (coordinates (al, rho), rho >= 0, t at (L, 0))
-    // (the facet lies in the wedge at t between the direction towards s, angle pi, and its other neighbour of t: the
-    // candidate with the SMALLEST angle about t is that neighbour -- a vertex of the facet, never an interior point)
+    if (det != 0.0) return det > 0.0;
+    if (p.x * q.x + p.y * q.y < 0.0) return p.x > 0.0;
+    return p.idx < q.idx;
+}
+// secondary order among the points on the winning plane: the facet lies in the wedge at t between the direction towards s
+// (angle pi) and its other neighbour of t, so the candidate with the SMALLEST angle about t is that neighbour -- a vertex
+// of the facet, never an interior point; collinear with t: the farthest; exact duplicates: the lowest index.
+// tol = coordinate round-off bound (Qhull's distance tolerance scale) -- both points may be off by it.
+__device__ __forceinline__ bool hull_turn_less(const HullPick& p, const HullPick& q, double L, double tol) {
+    if (q.idx < 0) return p.idx >= 0;
+    if (p.idx < 0) return false;
     const double cr = (q.al - L) * p.rho - q.rho * (p.al - L);        // cross(q - t, p - t) > 0: angle_p > angle_q
     const double dp2 = (p.al - L) * (p.al - L) + p.rho * p.rho, dq2 = (q.al - L) * (q.al - L) + q.rho * q.rho;
-    const double tol2 = 1e-13 * sqrt(dp2 * dq2);
+    const double tol2 = tol * (sqrt(dp2) + sqrt(dq2));
     if (cr < -tol2) return true;
     if (cr > tol2) return false;
     if (dp2 != dq2) return dp2 > dq2;
     return p.idx < q.idx;
 }
 
-// one wrap step; all threads call it; returns the chosen point (index into the cluster's member list) or -1
-__device__ int hull_wrap(const double* PX, const double* PY, const double* PZ, const int* HI, int m, V3<double> S,
-                         V3<double> T, V3<double> n0, V3<double> m0, int skip_s, int skip_t, double* red) {
+template <bool SECOND>
+__device__ HullPick hull_reduce(HullPick best, double L, double tol, double* red) {
     const int tid = threadIdx.x, nt = blockDim.x, lane = tid & 31, warp = tid >> 5, nw = nt >> 5;
-    const V3<double> E = T - S;
-    const double L = norm3(E);
-    const V3<double> e = v3<double>(E.x / L, E.y / L, E.z / L);
-    HullPick best; best.idx = -1; best.x = best.y = best.al = best.rho = 0.0;
-    for (int i = tid; i < m; i += nt) {
-        if (i == skip_s || i == skip_t) continue;
-        const int k = HI[i];
-        const V3<double> d = v3<double>(PX[k], PY[k], PZ[k]) - S;
-        HullPick c;
-        c.idx = i;
-        c.al = dot(d, e);
-        const V3<double> r = d - e * c.al;
-        c.rho = norm3(r);
-        if (!(c.rho > 1e-14 * (L + fabs(c.al)))) continue;              // on the edge's line: not a candidate
-        c.x = -dot(r, m0);
-        c.y = -dot(r, n0);
-        if (hull_better(c, best, L)) best = c;
-    }
 #pragma unroll 1
     for (int o = 16; o > 0; o >>= 1) {
         HullPick q;
         q.idx = __shfl_xor_sync(DSDF_FULL, best.idx, o);
         q.x = __shfl_xor_sync(DSDF_FULL, best.x, o); q.y = __shfl_xor_sync(DSDF_FULL, best.y, o);
         q.al = __shfl_xor_sync(DSDF_FULL, best.al, o); q.rho = __shfl_xor_sync(DSDF_FULL, best.rho, o);
-        if (hull_better(q, best, L)) best = q;
+        if (SECOND ? hull_turn_less(q, best, L, tol) : hull_phi_less(q, best)) best = q;
     }
     __syncthreads();
     if (lane == 0) {
@@ -442,34 +429,91 @@ __device__ int hull_wrap(const double* PX, const double* PY, const double* PZ, c
         red[warp * 5 + 3] = best.al; red[warp * 5 + 4] = best.rho;
     }
     __syncthreads();
-    if (tid == 0) {
-        HullPick b; b.idx = -1; b.x = b.y = b.al = b.rho = 0.0;
-        for (int ww = 0; ww < nw; ++ww) {
-            HullPick q;
-            q.idx = (int)red[ww * 5]; q.x = red[ww * 5 + 1]; q.y = red[ww * 5 + 2]; q.al = red[ww * 5 + 3]; q.rho = red[ww * 5 + 4];
-            if (hull_better(q, b, L)) b = q;
-        }
-        red[39] = (double)b.idx;
+    HullPick b; b.idx = -1; b.x = b.y = b.al = b.rho = 0.0;
+    for (int ww = 0; ww < nw; ++ww) {                                   // every thread: same order, same result
+        HullPick q;
+        q.idx = (int)red[ww * 5]; q.x = red[ww * 5 + 1]; q.y = red[ww * 5 + 2]; q.al = red[ww * 5 + 3]; q.rho = red[ww * 5 + 4];
+        if (SECOND ? hull_turn_less(q, b, L, tol) : hull_phi_less(q, b)) b = q;
     }
     __syncthreads();
-    return (int)red[39];
+    return b;
+}
+
+// one wrap step; all threads call it; returns the chosen point (index into the cluster's member list) or -1.
+// Pass 1: the point of smallest rotation angle.  Pass 2: among the points on that plane (within the round-off bound of
+// the angle comparison, Qhull's coplanarity notion) the facet vertex next to t.  Defining the tie set against the single
+// best point keeps the choice well defined (a pairwise tolerant comparison is not transitive).
+__device__ int hull_wrap(const double* PX, const double* PY, const double* PZ, const int* HI, int m, V3<double> S,
+                         V3<double> T, V3<double> n0, V3<double> m0, int skip_s, int skip_t, double tol, double* red) {
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const V3<double> E = T - S;
+    const double L = norm3(E);
+    const V3<double> e = v3<double>(E.x / L, E.y / L, E.z / L);
+    auto pick = [&](int i) {
+        HullPick c; c.idx = -1; c.x = c.y = c.al = c.rho = 0.0;
+        if (i == skip_s || i == skip_t) return c;
+        const int k = HI[i];
+        const V3<double> d = v3<double>(PX[k], PY[k], PZ[k]) - S;
+        c.al = dot(d, e);
+        const V3<double> r = d - e * c.al;
+        c.rho = norm3(r);
+        if (!(c.rho > 1e-14 * (L + fabs(c.al)))) return c;              // on the edge's line: not a candidate
+        c.x = -dot(r, m0);
+        c.y = fmax(-dot(r, n0), 0.0);
+        c.idx = i;
+        return c;
+    };
+    HullPick best; best.idx = -1; best.x = best.y = best.al = best.rho = 0.0;
+    for (int i = tid; i < m; i += nt) {
+        const HullPick c = pick(i);
+        if (hull_phi_less(c, best)) best = c;
+    }
+    HullPick star = hull_reduce<false>(best, L, tol, red);
+    if (star.idx < 0) return -1;
+    // the tie set is re-centred on the chosen point until it stops moving: a run of collinear / coplanar points that
+    // leaves the tolerance band of the first winner is still walked to its end (its extreme point is the vertex)
+#pragma unroll 1
+    for (int it = 0; it < 8; ++it) {
+        best.idx = -1;
+        for (int i = tid; i < m; i += nt) {
+            const HullPick c = pick(i);
+            if (c.idx < 0) continue;
+            const double det = star.x * c.y - c.x * star.y;
+            if (fabs(det) > tol * (star.rho + c.rho)) continue;            // not on the winning plane
+            if (star.x * c.x + star.y * c.y < 0.0) continue;                // (opposite half-plane: angle pi apart)
+            if (hull_turn_less(c, best, L, tol)) best = c;
+        }
+        const HullPick nxt = hull_reduce<true>(best, L, tol, red);
+        if (nxt.idx == star.idx) break;
+        star = nxt;
+    }
+    return star.idx;
 }
 
 // marks KEEP[HI[i]] = 1 for the hull vertices of the cluster's m points; returns false when the work buffers are too
-// small for m (the caller keeps the whole cluster and flags it).  bits: >= m*m/32 + 1 ints; stk0 / stk1: cap ints each.
+// small for m (the caller keeps the whole cluster and flags it).  tab: hash table of ntab ints (<= 6 m directed edges);
+// stk0 / stk1: cap ints each.
 __device__ bool hull3d_vertices(const double* PX, const double* PY, const double* PZ, const int* HI, int m, int* KEEP,
-                                unsigned* bits, size_t nbits_ints, int* stk0, int* stk1, int cap, double* red,
+                                unsigned* tab, size_t ntab, int* stk0, int* stk1, int cap, double* red,
                                 double maxabs) {
     const int tid = threadIdx.x, nt = blockDim.x;
-    if ((size_t)m * m / 32 + 1 > nbits_ints || 3 * m > 2 * cap || m > 1023) return false;
-    for (size_t i = tid; i < (size_t)m * m / 32 + 1; i += nt) bits[i] = 0u;
+    const double tol = 2e-15 * maxabs;                                  // round-off bound of the coordinates (tuned on Qhull)
+    if ((size_t)8 * m > ntab || 3 * m > 2 * cap || m > 1023) return false;          // load factor <= 0.75
+    for (size_t i = tid; i < ntab; i += nt) tab[i] = 0u;
     __shared__ int s_top, s_a;
-    // lexicographically smallest point: a hull vertex
+    // lexicographically smallest point (x, then y, the coordinate ties up to round-off, then z): a hull vertex -- with
+    // exact ties only, round-off would pick an interior point of a hull edge parallel to the z (or y) axis
     if (tid == 0) {
-        int a = 0;
-        for (int i = 1; i < m; ++i) {
-            const int k = HI[i], ka = HI[a];
-            if (PX[k] < PX[ka] || (PX[k] == PX[ka] && (PY[k] < PY[ka] || (PY[k] == PY[ka] && PZ[k] < PZ[ka])))) a = i;
+        double lo = PX[HI[0]];
+        for (int i = 1; i < m; ++i) lo = fmin(lo, PX[HI[i]]);
+        const double xcut = lo + tol;
+        lo = 1e300;
+        for (int i = 0; i < m; ++i) if (PX[HI[i]] <= xcut) lo = fmin(lo, PY[HI[i]]);
+        const double ycut = lo + tol;
+        int a = -1;
+        for (int i = 0; i < m; ++i) {
+            const int k = HI[i];
+            if (PX[k] <= xcut && PY[k] <= ycut && (a < 0 || PZ[k] < PZ[HI[a]])) a = i;
         }
         s_a = a; s_top = 0;
     }
@@ -477,8 +521,19 @@ __device__ bool hull3d_vertices(const double* PX, const double* PY, const double
     const int a = s_a;
     auto P = [&](int i) { const int k = HI[i]; return v3<double>(PX[k], PY[k], PZ[k]); };
     auto unit = [](V3<double> v) { const double n = norm3(v); return v3<double>(v.x / n, v.y / n, v.z / n); };
-    auto edge_done = [&](int u, int v) { const size_t b = (size_t)u * m + v; return (bits[b >> 5] >> (b & 31)) & 1u; };
-    auto mark_edge = [&](int u, int v) { const size_t b = (size_t)u * m + v; bits[b >> 5] |= 1u << (b & 31); };
+    auto edge_done = [&](int u, int v) {
+        const unsigned key = ((unsigned)u << 10 | (unsigned)v) + 1u;
+        for (size_t h = (key * 2654435761u) % ntab;; h = h + 1 == ntab ? 0 : h + 1) {
+            if (tab[h] == key) return true;
+            if (tab[h] == 0u) return false;
+        }
+    };
+    auto mark_edge = [&](int u, int v) {                               // thread 0 only
+        const unsigned key = ((unsigned)u << 10 | (unsigned)v) + 1u;
+        size_t h = (key * 2654435761u) % ntab;
+        while (tab[h] != 0u && tab[h] != key) h = h + 1 == ntab ? 0 : h + 1;
+        tab[h] = key;
+    };
     auto push = [&](int s_, int t_, int w_) {
         const int top = s_top++;
         (top < cap ? stk0[top] : stk1[top - cap]) = s_ | (t_ << 10) | (w_ << 20);
@@ -487,14 +542,14 @@ __device__ bool hull3d_vertices(const double* PX, const double* PY, const double
     // supporting plane x = a.x: "known face" (a, virtual, a + e_y), outward normal -e_x = e_z x e_y
     const V3<double> A = P(a);
     const V3<double> Vt = A + v3<double>(0.0, 0.0, 8.0 * maxabs + 1.0);
-    const int b = hull_wrap(PX, PY, PZ, HI, m, A, Vt, v3<double>(-1.0, 0.0, 0.0), v3<double>(0.0, 1.0, 0.0), a, -1, red);
+    const int b = hull_wrap(PX, PY, PZ, HI, m, A, Vt, v3<double>(-1.0, 0.0, 0.0), v3<double>(0.0, 1.0, 0.0), a, -1, tol, red);
     if (b < 0) return true;                                             // (cannot happen for a non-degenerate cluster)
     // first face: wrap around a -> b; the known face is the vertical supporting plane (a, b, virtual) just found
     const V3<double> Bp = P(b);
     {
         const V3<double> eab = unit(Bp - A);
         V3<double> rw = (Vt - A) - eab * dot(Vt - A, eab);
-        const int c = hull_wrap(PX, PY, PZ, HI, m, A, Bp, unit(cross(Bp - A, Vt - A)), unit(rw), a, b, red);
+        const int c = hull_wrap(PX, PY, PZ, HI, m, A, Bp, unit(cross(Bp - A, Vt - A)), unit(rw), a, b, tol, red);
         if (c < 0) return true;
         if (tid == 0) {
             KEEP[HI[a]] = 1; KEEP[HI[b]] = 1; KEEP[HI[c]] = 1;
@@ -517,7 +572,7 @@ __device__ bool hull3d_vertices(const double* PX, const double* PY, const double
         const V3<double> Sp = P(s_), Tp = P(t_), Wp = P(w_);
         const V3<double> e = unit(Tp - Sp);
         const V3<double> rw = (Wp - Sp) - e * dot(Wp - Sp, e);
-        const int c = hull_wrap(PX, PY, PZ, HI, m, Sp, Tp, unit(cross(Tp - Sp, Wp - Sp)), unit(rw), s_, t_, red);
+        const int c = hull_wrap(PX, PY, PZ, HI, m, Sp, Tp, unit(cross(Tp - Sp, Wp - Sp)), unit(rw), s_, t_, tol, red);
         if (c < 0) continue;
         if (tid == 0) {
             KEEP[HI[c]] = 1;
