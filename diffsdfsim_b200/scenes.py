@@ -302,7 +302,7 @@ def mixed16(seed=0, steps=12, spacing=1.3, speed=1.0, gravity=False, subdivision
     return scene(bodies, steps=steps)
 
 
-def per_world_grid_bodies(W, res=64, seed0=0, scale=2.0, device=None):
+def per_world_grid_bodies(W, res=64, seed0=0, scale=2.0, device=None, latent_scale=0.15):
     """Per-world geometry of ``W`` config-4 bodies: W seeded random-init IGR-style decoders baked to (W,res,res,res) grids,
     the iso-surface mesh of each grid (vertex / face arrays padded to the largest, true counts alongside) and the
     unit-mass inertia of each mesh.  Returns the ``params`` entries make_bodies understands for the LAST body:
@@ -312,10 +312,14 @@ def per_world_grid_bodies(W, res=64, seed0=0, scale=2.0, device=None):
     grids, vs, fs, Is = [], [], [], []
     for w in range(W):
         seed = seed0 + w
-        while True:                      # a fresh decoder occasionally has no (or a clipped) zero level set: draw again
-            g = igr.random_shape_grid(seed, res, latent_scale=0.15, device=device or 'cpu')
+        while True:                      # a fresh decoder occasionally has no zero level set, or one that leaves the grid
+            g = igr.random_shape_grid(seed, res, latent_scale=latent_scale, device=device or 'cpu')
+            ga = np.asarray(g)
+            # closed surface strictly inside the grid: the field is positive on all six boundary faces (a level set clipped
+            # by the grid gives an open mesh around a body whose SDF says "inside" at the cube wall -- not a valid body)
+            wall = min(ga[0].min(), ga[-1].min(), ga[:, 0].min(), ga[:, -1].min(), ga[:, :, 0].min(), ga[:, :, -1].min())
             try:
-                v, f = meshes.surface_nets(g)
+                v, f = meshes.surface_nets(g) if wall > 0.02 else (None, [])
             except AssertionError:
                 f = []
             if len(f) >= 200:

@@ -365,12 +365,13 @@ class DeviceStepper:
         if c[CT_CONSTAT] & CON_STALLED:
             world.stats['stalled'] = world.stats.get('stalled', 0) + 1
         if c[CT_CONSTAT] & CON_HULL3D:
-            # contacts.py:126-152 runs a 3-D Qhull on such clusters; the device filter keeps all their points instead
+            # contacts.py:126-152 runs a 3-D Qhull on such clusters; so does the device filter (hull3d_vertices) unless the
+            # cluster is larger than its work buffers (8 m <= 4 capK), in which case every point of the cluster is kept
             world.stats['hull3d_steps'] = world.stats.get('hull3d_steps', 0) + 1
             if world.stats['hull3d_steps'] == 1:
                 import warnings
-                warnings.warn('a normal cluster of more than 4 non-coplanar contact points was kept unfiltered '
-                              '(DSDF_CON_HULL3D): the reference would reduce it to its 3-D convex hull vertices')
+                warnings.warn('a non-planar contact cluster was too large for the device 3-D hull and was kept unfiltered '
+                              '(DSDF_CON_HULL3D); raise capK to at least twice the cluster size')
         if ls & LCP_INACCURATE and getattr(world.engine, 'verbose', -1) >= 0:
             print('qpth warning: Returning an inaccurate and potentially incorrect solution.')       # batch.py:165,229
         tape.maxsub, tape.any_toc = c[CT_MAXNSUB], bool(c[CT_ANYTOC])

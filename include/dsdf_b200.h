@@ -149,7 +149,7 @@ typedef struct dsdf_body_geom {
 /* per-world contact status bits (int32) */
 #define DSDF_CON_CAND_OVERFLOW  1   /* more centroid candidates than capK in some direction */
 #define DSDF_CON_OVERFLOW       2   /* more contacts than maxc */
-#define DSDF_CON_HULL3D         4   /* a non-planar normal cluster of > 4 points was kept unfiltered */
+#define DSDF_CON_HULL3D         4   /* a non-planar cluster too large for the device 3-D hull (8 m > 4 capK) was kept whole */
 #define DSDF_CON_PENETRATION    8   /* some pen > tol: the step attempt will be rejected (world.py:270) */
 #define DSDF_CON_STALLED       16   /* (step loop, ctrl[14] only) a world exhausted the tape slots of one step and left it early */
 
