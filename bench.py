@@ -33,7 +33,7 @@ UNIT = 'world-steps/s'
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
-    ap.add_argument('--steps', type=int, default=3)
+    ap.add_argument('--steps', type=int, default=5)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--worlds', type=int, default=4096, help='worlds per GPU')
@@ -62,6 +62,7 @@ class ClockSampler(threading.Thread):
     def __init__(self, index=0):
         super().__init__(daemon=True)
         self.index, self.rows, self.stop_flag, self.t_keep = index, [], False, None
+        self.period = float(os.environ.get('BENCH_SMI_PERIOD', 0.5))   # every nvidia-smi call can stall launches for ms: sample sparsely
 
     def run(self):
         q = ('clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,'
@@ -74,7 +75,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append([c.strip() for c in out.strip().split(',')])
             except Exception:
                 pass
-            time.sleep(0.2)
+            time.sleep(self.period)
 
     def summary(self):
         sm = sorted(int(r[0]) for r in self.rows if r and r[0].isdigit())
