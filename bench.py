@@ -453,8 +453,10 @@ def sdf_query_roofline(device, W=256, R=64, N=1 << 17, reps=5):
             'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
             'peak_source': which, 'avg_launch_ms': ms, 'algorithmic_bytes_per_launch': alg,
             'l2_policy': 'inputs (%.2f GB) larger than L2' % (alg / 1e9), 'traffic': ncu_traffic('sdf_query_grid_kernel'),
-            'note': 'DRAM traffic equals the algorithmic bytes; the remaining gap is on-chip: 35 eight-byte loads per point '
-                    '(L1/TEX 74 % of peak in ncu) and ~200 FP64 instr/point (FP64 pipe 38 %), see DESIGN.md s5',
+            'note': 'value + direction: DRAM traffic equals the algorithmic bytes; the remaining gap is on-chip: 35 eight-byte '
+                    'gathers per point (L1/TEX 74 % of peak in ncu) and ~200 FP64 instr/point (FP64 pipe 38 %); occupancy '
+                    'does not move it.  value_only = the same query without the direction (its own kernel instantiation: '
+                    '8 gathers per point, HBM-bound), see DESIGN.md s5',
             'value_only': {'achieved': ach_v, 'frac': ach_v / peaks['hbm_gbs'], 'avg_launch_ms': ms_v,
                            'algorithmic_bytes_per_launch': alg_v}}
 

@@ -50,23 +50,34 @@ __device__ __forceinline__ V3<double> normalize3_rcp(V3<double> a) {
     return v3<double>(q(a.x), q(a.y), q(a.z));
 }
 
-#ifndef SDFQ_MINB
-#define SDFQ_MINB 2
+#ifndef SDFQ_MINB_DIR
+#define SDFQ_MINB_DIR 2
+#endif
+#ifndef SDFQ_MINB_VAL
+#define SDFQ_MINB_VAL 4
 #endif
 #ifndef SDFQ_WAVES
 #define SDFQ_WAVES 8
 #endif
-__global__ void __launch_bounds__(256, SDFQ_MINB)
+// Grid SDF (bodies.py:203-257): trilinear value and, with DIR, the normalised trilinear interpolation of the central
+// difference field -- a 32-voxel register stencil per point.  ncu (profiles/r1_ncu_summary.md): DRAM traffic = the
+// algorithmic bytes; the limits are on chip, the L1 wavefronts of the 32 gathers and ~200 FP64 instructions per point,
+// which only overlap across warps.  Value-only queries get their own instantiation (8 gathers, 56 registers, 4 CTAs per
+// SM: 0.84 of the measured HBM peak instead of 0.58 when it shared the direction kernel's registers).  The direction is
+// accumulated in three passes over the stencil (z, x, y neighbours; each accumulator keeps the summation order of a
+// single loop, so the bits are unchanged); measured: 2, 3 or 4 CTAs per SM make no difference for it (0.47-0.49, 4 CTAs
+// spill) -- it sits on the L1 wavefront limit of its 32 scattered 8-byte gathers per point.
+template <bool DIR>
+__global__ void __launch_bounds__(256, DIR ? SDFQ_MINB_DIR : SDFQ_MINB_VAL)
 sdf_query_grid_kernel(const double* __restrict__ shape, const double* __restrict__ grid, int R, long long grid_stride,
-                      const double* __restrict__ pts, int N, int want_dir, double* __restrict__ sdf,
-                      double* __restrict__ dir) {
+                      const double* __restrict__ pts, int N, double* __restrict__ sdf, double* __restrict__ dir) {
     const int w = blockIdx.y;
     const double sc = shape[4 * (size_t)w + 3];
     const double* __restrict__ g = grid + (size_t)w * grid_stride;
     const double ext = (double)(R - 1);
     const size_t sx = (size_t)R * R, sy = (size_t)R;
     // persistent-style loop with the NEXT point's coordinates prefetched: the DRAM latency of the point stream overlaps
-    // the ~400 FP64 instructions of the current point
+    // the FP64 instructions of the current point
     const int step = gridDim.x * blockDim.x;
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     double qx = 0.0, qy = 0.0, qz = 0.0;
@@ -97,43 +108,65 @@ sdf_query_grid_kernel(const double* __restrict__ shape, const double* __restrict
 #pragma unroll
                         for (int dz = 0; dz < 2; ++dz) C[dx][dy][dz] = c[dx * sx + dy * sy + dz];
                 double acc = 0.0;
-                if (want_dir) {
+                auto wgt = [&](int dx, int dy, int dz) { return (dx ? tx : 1 - tx) * (dy ? ty : 1 - ty) * (dz ? tz : 1 - tz); };
+                if (DIR) {
                     // axis neighbours one step outside the cell.  On a boundary plane the reference's central difference
                     // is zero (bodies.py:225-234): there the neighbour is redirected to the voxel it is subtracted from,
-                    // so hi - lo = 0 exactly and no per-corner select is needed.
-                    double XM[2][2], XP[2][2], YM[2][2], YP[2][2], ZM[2][2], ZP[2][2];
-                    const long long oxm = bx > 0 ? -(long long)sx : (long long)sx, oxp = bx + 2 < R ? 2 * (long long)sx : 0;
-                    const long long oym = by > 0 ? -(long long)sy : (long long)sy, oyp = by + 2 < R ? 2 * (long long)sy : 0;
-                    const long long ozm = bz > 0 ? -1 : 1, ozp = bz + 2 < R ? 2 : 0;
+                    // so hi - lo = 0 exactly and no per-corner select is needed.  Twice the central differences are
+                    // summed; the exact factor 1/2 is applied once at the end (scaling by a power of two commutes with
+                    // every rounding involved).
+                    {
+                        const long long ozm = bz > 0 ? -1 : 1, ozp = bz + 2 < R ? 2 : 0;
+                        double ZM[2][2], ZP[2][2];
 #pragma unroll
-                    for (int a = 0; a < 2; ++a)
+                        for (int a = 0; a < 2; ++a)
 #pragma unroll
-                        for (int b = 0; b < 2; ++b) {
-                            XM[a][b] = c[oxm + a * sy + b];  XP[a][b] = c[oxp + a * sy + b];
-                            YM[a][b] = c[a * sx + oym + b];  YP[a][b] = c[a * sx + oyp + b];
-                            ZM[a][b] = c[a * sx + b * sy + ozm];  ZP[a][b] = c[a * sx + b * sy + ozp];
-                        }
+                            for (int b = 0; b < 2; ++b) { ZM[a][b] = c[a * sx + b * sy + ozm]; ZP[a][b] = c[a * sx + b * sy + ozp]; }
 #pragma unroll
-                    for (int dx = 0; dx < 2; ++dx) {
-                        const double wx = dx ? tx : 1 - tx;
+                        for (int dx = 0; dx < 2; ++dx)
 #pragma unroll
-                        for (int dy = 0; dy < 2; ++dy) {
-                            const double wy = dy ? ty : 1 - ty;
+                            for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                            for (int dz = 0; dz < 2; ++dz) {
-                                const double wz = dz ? tz : 1 - tz;
-                                const double wgt = wx * wy * wz;
-                                acc = acc + C[dx][dy][dz] * wgt;
-                                // twice the central differences; the exact factor 1/2 is applied once after the sums
-                                // (scaling by a power of two commutes with every rounding involved)
-                                const double hi_x = dx ? XP[dy][dz] : C[1][dy][dz], lo_x = dx ? C[0][dy][dz] : XM[dy][dz];
-                                const double hi_y = dy ? YP[dx][dz] : C[dx][1][dz], lo_y = dy ? C[dx][0][dz] : YM[dx][dz];
-                                const double hi_z = dz ? ZP[dx][dy] : C[dx][dy][1], lo_z = dz ? C[dx][dy][0] : ZM[dx][dy];
-                                a0 = a0 + (hi_x - lo_x) * wgt;
-                                a1 = a1 + (hi_y - lo_y) * wgt;
-                                a2 = a2 + (hi_z - lo_z) * wgt;
-                            }
-                        }
+                                for (int dz = 0; dz < 2; ++dz) {
+                                    const double wg = wgt(dx, dy, dz);
+                                    acc = acc + C[dx][dy][dz] * wg;
+                                    const double hi = dz ? ZP[dx][dy] : C[dx][dy][1], lo = dz ? C[dx][dy][0] : ZM[dx][dy];
+                                    a2 = a2 + (hi - lo) * wg;
+                                }
+                    }
+                    {
+                        const long long oxm = bx > 0 ? -(long long)sx : (long long)sx, oxp = bx + 2 < R ? 2 * (long long)sx : 0;
+                        double XM[2][2], XP[2][2];
+#pragma unroll
+                        for (int a = 0; a < 2; ++a)
+#pragma unroll
+                            for (int b = 0; b < 2; ++b) { XM[a][b] = c[oxm + a * sy + b]; XP[a][b] = c[oxp + a * sy + b]; }
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+                            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                                for (int dz = 0; dz < 2; ++dz) {
+                                    const double hi = dx ? XP[dy][dz] : C[1][dy][dz], lo = dx ? C[0][dy][dz] : XM[dy][dz];
+                                    a0 = a0 + (hi - lo) * wgt(dx, dy, dz);
+                                }
+                    }
+                    {
+                        const long long oym = by > 0 ? -(long long)sy : (long long)sy, oyp = by + 2 < R ? 2 * (long long)sy : 0;
+                        double YM[2][2], YP[2][2];
+#pragma unroll
+                        for (int a = 0; a < 2; ++a)
+#pragma unroll
+                            for (int b = 0; b < 2; ++b) { YM[a][b] = c[a * sx + oym + b]; YP[a][b] = c[a * sx + oyp + b]; }
+#pragma unroll
+                        for (int dx = 0; dx < 2; ++dx)
+#pragma unroll
+                            for (int dy = 0; dy < 2; ++dy)
+#pragma unroll
+                                for (int dz = 0; dz < 2; ++dz) {
+                                    const double hi = dy ? YP[dx][dz] : C[dx][1][dz], lo = dy ? C[dx][0][dz] : YM[dx][dz];
+                                    a1 = a1 + (hi - lo) * wgt(dx, dy, dz);
+                                }
                     }
                     a0 *= 0.5; a1 *= 0.5; a2 *= 0.5;
                 } else {
@@ -142,20 +175,19 @@ sdf_query_grid_kernel(const double* __restrict__ shape, const double* __restrict
 #pragma unroll
                         for (int dy = 0; dy < 2; ++dy)
 #pragma unroll
-                            for (int dz = 0; dz < 2; ++dz)
-                                acc = acc + C[dx][dy][dz] * ((dx ? tx : 1 - tx) * (dy ? ty : 1 - ty) * (dz ? tz : 1 - tz));
+                            for (int dz = 0; dz < 2; ++dz) acc = acc + C[dx][dy][dz] * wgt(dx, dy, dz);
                 }
                 v = acc;
             }
             val_ = v * sc;
-            if (want_dir) {
+            if (DIR) {
                 const V3<double> d1 = ok ? normalize3_rcp(v3<double>(a0, a1, a2)) : v3<double>(0.0, 0.0, 0.0);
                 const V3<double> d2 = normalize3_rcp(d1);
                 n0 = d2.x; n1 = d2.y; n2 = d2.z;
             }
         }
         sdf[o] = val_;
-        if (want_dir) { dir[3 * o] = n0; dir[3 * o + 1] = n1; dir[3 * o + 2] = n2; }
+        if (DIR) { dir[3 * o] = n0; dir[3 * o + 1] = n1; dir[3 * o + 2] = n2; }
     }
 }
 
@@ -250,11 +282,15 @@ int dsdf_sdf_query_ex(int kind, const double* shape, double extra0, double extra
     if (bx > 148 * 8) bx = 148 * 8;
     if (kind == DSDF_SDF_GRID) {
         // ~4 resident waves of CTAs over the whole launch (148 SMs x 3 CTAs); each thread streams several points
-        int per_world = (148 * SDFQ_MINB * SDFQ_WAVES + W - 1) / W;
+        int per_world = (148 * (want_dir ? SDFQ_MINB_DIR : SDFQ_MINB_VAL) * SDFQ_WAVES + W - 1) / W;
         if (per_world < 1) per_world = 1;
         if (bx > per_world) bx = per_world;
-        sdf_query_grid_kernel<<<dim3(bx, W), 256, 0, (cudaStream_t)stream>>>(shape, grid, res, grid_world_stride, pts, N,
-                                                                             want_dir, sdf, dir);
+        if (want_dir)
+            sdf_query_grid_kernel<true><<<dim3(bx, W), 256, 0, (cudaStream_t)stream>>>(shape, grid, res, grid_world_stride,
+                                                                                       pts, N, sdf, dir);
+        else
+            sdf_query_grid_kernel<false><<<dim3(bx, W), 256, 0, (cudaStream_t)stream>>>(shape, grid, res, grid_world_stride,
+                                                                                        pts, N, sdf, dir);
     } else
         sdf_query_kernel<<<dim3(bx, W), 256, 0, (cudaStream_t)stream>>>(kind, shape, grid, res, grid_world_stride, pts,
                                                                         N, want_dir, sdf, dir, extra0, extra1);
