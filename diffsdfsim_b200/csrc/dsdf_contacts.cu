@@ -751,13 +751,47 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
     // vector); the geometry is a pure function of that point, so it is evaluated once per DISTINCT point and copied.
     int* REP = sm.TMP;                 // representative (smallest index with identical coordinates)
     int* UL = sm.HI;                   // compact list of representatives
-    for (int k = tid; k < total; k += nt) {
-        const double a0 = sm.X[k], a1 = sm.X[capK + k], a2 = sm.X[2 * capK + k];
-        int rep = k;
-        for (int j = 0; j < k; ++j)
-            if (sm.X[j] == a0 && sm.X[capK + j] == a1 && sm.X[2 * capK + j] == a2) { rep = j; break; }
-        REP[k] = rep;
-        sm.SC[k] = rep == k;
+    {
+        // open-addressing hash set over the coordinates (capK slots in CL, free until the filter): a slot holds the smallest
+        // index seen so far of its key.  Replaces an O(total^2) scan (9 % of the kernel's instructions, ncu round 2).
+        int* TAB = sm.CL;
+        for (int k = tid; k < capK; k += nt) TAB[k] = 0x7fffffff;
+        __syncthreads();
+        auto slot0 = [&](double a0, double a1, double a2) {
+            const unsigned long long u0 = __double_as_longlong(a0 + 0.0), u1 = __double_as_longlong(a1 + 0.0),
+                                     u2 = __double_as_longlong(a2 + 0.0);               // (+ 0.0: -0 and +0 compare equal)
+            unsigned long long h = u0 * 0x9E3779B97F4A7C15ull;
+            h = (h ^ (h >> 29)) + u1 * 0xBF58476D1CE4E5B9ull;
+            h = (h ^ (h >> 31)) + u2 * 0x94D049BB133111EBull;
+            h ^= h >> 32;
+            return (int)((unsigned)h % (unsigned)capK);
+        };
+        for (int k = tid; k < total; k += nt) {
+            const double a0 = sm.X[k], a1 = sm.X[capK + k], a2 = sm.X[2 * capK + k];
+            int s_ = slot0(a0, a1, a2);
+            for (int probes = 0; probes < capK; ++probes, s_ = s_ + 1 == capK ? 0 : s_ + 1) {
+                int j = TAB[s_];
+                if (j == 0x7fffffff) {
+                    j = atomicCAS(&TAB[s_], 0x7fffffff, k);
+                    if (j == 0x7fffffff) break;                                        // new key
+                }
+                // j indexes a contact with this slot's key (atomicMin only ever swaps in an equal-key index)
+                if (sm.X[j] == a0 && sm.X[capK + j] == a1 && sm.X[2 * capK + j] == a2) { atomicMin(&TAB[s_], k); break; }
+            }
+        }
+        __syncthreads();
+        for (int k = tid; k < total; k += nt) {
+            const double a0 = sm.X[k], a1 = sm.X[capK + k], a2 = sm.X[2 * capK + k];
+            int rep = k;
+            int s_ = slot0(a0, a1, a2);
+            for (int probes = 0; probes < capK; ++probes, s_ = s_ + 1 == capK ? 0 : s_ + 1) {
+                const int j = TAB[s_];
+                if (j == 0x7fffffff) break;                                            // (NaN coordinates: own representative)
+                if (sm.X[j] == a0 && sm.X[capK + j] == a1 && sm.X[2 * capK + j] == a2) { rep = j; break; }
+            }
+            REP[k] = rep;
+            sm.SC[k] = rep == k;
+        }
     }
     int nuniq = 0;
     block_exclusive_scan(sm.SC, total, &nuniq);
