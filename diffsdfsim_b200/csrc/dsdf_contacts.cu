@@ -654,7 +654,7 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
         const int cur = it & 1, nxt = cur ^ 1;
         const int nact = s_nact[cur];
         const int* act_list = lists[cur];
-        int any_active = 0, any_pen = 0;
+        int any_pen = 0;
         // phase 1: evaluate (no state change until the exit test is known)
         for (int a = tid; a < nact; a += nt) {
             const int k = act_list[a];
@@ -671,16 +671,16 @@ __device__ DirResult search_direction(const RefineSmem& sm, int capK, const Body
                                             sm.P[(3 * pick + 2) * capK + k]);
             const double gain = (x.x - s.x) * o.n.x + (x.y - s.y) * o.n.y + (x.z - s.z) * o.n.z;
             const int act = fabs(gain) > tol;
-            any_active |= act;
             any_pen |= (o.d < -tol);
             sm.SC[k] = act ? pick : -1;
             // a candidate whose step is zero keeps its x, so re-evaluating it would reproduce the same decision: it leaves
             // the list for good (the reference recomputes it every iteration with identical results)
             if (act) lists[nxt][atomicAdd(&s_nact[nxt], 1)] = k;
         }
-        // __syncthreads_or returns a predicate, not a bitwise OR: one barrier per flag
-        const int blk_active = __syncthreads_or(any_active);
+        // one barrier: the penetration flag through the barrier's predicate, "anything still moving" from the length of
+        // the next list (every active candidate was appended to it before the barrier)
         const int blk_pen = __syncthreads_or(any_pen);
+        const int blk_active = s_nact[nxt] > 0;
         PH_ADD(PH_FW_ITERS, 1);
         if (!blk_active || blk_pen) break;
         const double gamma = 2.0 / (it + 2.0);
