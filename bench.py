@@ -378,6 +378,14 @@ def secondary_workloads(device, reps=2):
                                       'iso-surface meshes (%d..%d faces), scale 2, pinned pole + 50x1x50 floor (1 040 000 faces), '
                                       '33 steps, fwd+bwd' % (int(pw['nfaces'].min()), int(pw['nfaces'].max())),
                           'stalled_steps': stalled[0],
+                          'contacts_kernel_ncu': {
+                              'dram_bytes_per_launch': ncu_traffic('contacts_kernel@config4'),
+                              'upper_bound_bytes': int(W * (R ** 3 * 8 + (int(pw['nverts'].max()) * 24 + int(pw['nfaces'].max()) * 12))),
+                              'source': 'committed ncu capture of the heaviest contacts_kernel launch of scratch/c4prof.py (256 '
+                                        'worlds, same per-world grids and meshes; profiles/r2_ncu_summary.md), not measured in this '
+                                        'run; upper_bound = every voxel of every 64^3 f64 grid + every vertex and face of every '
+                                        'per-world mesh -- the kernel reads a fraction of it (dram_bytes / upper_bound): only the cells of the body mesh near the '
+                                        'pole / floor and the voxels under the pole and floor faces it tests'},
                           'note': 'strict_no_penetration=False; stalled_steps = steps in which some world exhausted the 64 '
                                   'sub-step tape (it keeps giving up at dt/2^10, the reference would sub-step ~1000 times)'}
     # ---- config 3: 1024 worlds x 16 mixed primitives (120 body pairs), 200 steps, gradients w.r.t. every body's initial
@@ -452,13 +460,14 @@ def sdf_query_roofline(device, W=256, R=64, N=1 << 17, reps=5):
     return {'kernel': 'dsdf_sdf_query (grid, per-world %d^3 f64 grids, W=%d, N=%d pts/world, value+direction)' % (R, W, N),
             'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm_gbs'], 'unit': 'GB/s', 'frac': ach / peaks['hbm_gbs'],
             'peak_source': which, 'avg_launch_ms': ms, 'algorithmic_bytes_per_launch': alg,
-            'l2_policy': 'inputs (%.2f GB) larger than L2' % (alg / 1e9), 'traffic': ncu_traffic('sdf_query_grid_kernel'),
+            'l2_policy': 'inputs (%.2f GB) larger than L2' % (alg / 1e9), 'traffic': ncu_traffic('sdf_query_grid_kernel<1>'),
+            'traffic_source': 'committed ncu capture (profiles/ncu_traffic.json), not measured in this run',
             'note': 'value + direction: DRAM traffic equals the algorithmic bytes; the remaining gap is on-chip: 35 eight-byte '
                     'gathers per point (L1/TEX 74 % of peak in ncu) and ~200 FP64 instr/point (FP64 pipe 38 %); occupancy '
                     'does not move it.  value_only = the same query without the direction (its own kernel instantiation: '
                     '8 gathers per point, HBM-bound), see DESIGN.md s5',
             'value_only': {'achieved': ach_v, 'frac': ach_v / peaks['hbm_gbs'], 'avg_launch_ms': ms_v,
-                           'algorithmic_bytes_per_launch': alg_v}}
+                           'algorithmic_bytes_per_launch': alg_v, 'traffic': ncu_traffic('sdf_query_grid_kernel<0>')}}
 
 
 def ncu_counters(kernel):
@@ -476,7 +485,8 @@ def ncu_traffic(kernel):
     """dram bytes (read + write) per launch of `kernel` from the committed ncu capture (profiles/ncu_traffic.json)."""
     try:
         with open(os.path.join(ROOT, 'profiles', 'ncu_traffic.json')) as fh:
-            return json.load(fh).get(kernel)
+            d = json.load(fh)
+        return d.get(kernel, d.get('void ' + kernel))
     except Exception:
         return None
 

@@ -81,6 +81,8 @@ def main(rnd):
             if name in seen:
                 continue
             seen.add(name)
+            if '_c4' in os.path.basename(rep):          # the same kernel captured on the config-4 workload
+                name += '@config4'
             md += ['## %s  (`%s`)' % (name, os.path.basename(rep)), '', '| counter | value |', '|---|---|']
             byt = 0.0
             for k, label in KEYS:
