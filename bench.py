@@ -381,7 +381,7 @@ def secondary_workloads(device, reps=2):
                           'contacts_kernel_ncu': {
                               'dram_bytes_per_launch': ncu_traffic('contacts_kernel@config4'),
                               'upper_bound_bytes': int(W * (R ** 3 * 8 + (int(pw['nverts'].max()) * 24 + int(pw['nfaces'].max()) * 12))),
-                              'source': 'committed ncu capture of the heaviest contacts_kernel launch of scratch/c4prof.py (256 '
+                              'source': 'committed ncu capture of the heaviest contacts_kernel launch of profiles/tools/c4prof.py (256 '
                                         'worlds, same per-world grids and meshes; profiles/r2_ncu_summary.md), not measured in this '
                                         'run; upper_bound = every voxel of every 64^3 f64 grid + every vertex and face of every '
                                         'per-world mesh -- the kernel reads a fraction of it (dram_bytes / upper_bound): only the cells of the body mesh near the '
