@@ -1,8 +1,8 @@
 """numpy model of the device gift wrapping (dsdf_contacts.cu hull3d_vertices) to tune against Qhull."""
 import pickle, sys, numpy as np
 from scipy.spatial import ConvexHull
-TOL1 = float(sys.argv[1]) if len(sys.argv) > 1 else 5e-15
-TOL2 = float(sys.argv[2]) if len(sys.argv) > 2 else 5e-15
+TOL1 = float(sys.argv[1]) if len(sys.argv) > 1 else 2e-15
+TOL2 = float(sys.argv[2]) if len(sys.argv) > 2 else 2e-15
 CLOSE = int(sys.argv[3]) if len(sys.argv) > 3 else 8
 
 def unit(v): return v / np.linalg.norm(v)
@@ -69,23 +69,38 @@ def hull(P):
     return keep
 
 if __name__ == '__main__':
-    rec = pickle.load(open('gpurun_out/hull_cases.pkl', 'rb'))
+    # usage: python profiles/tools/hull_wrap_np.py [tol1] [tol2] [closure iterations]
+    # clusters: a lattice box surface (coplanar faces, collinear edges) under rotations of 0 ... 2 rad, random clouds, points
+    # on a sphere; plus, when present, the contact clusters recorded from the oracle (gpurun_out/hull_cases.pkl)
+    import os
     rng = np.random.default_rng(0)
-    cases = [(p, set(v.tolist())) for p, v in rec]
-    # more cases: the same clusters under small random rigid motions (what successive states look like)
-    for p, _ in rec:
-        for mag in (1e-10, 1e-7, 1e-4, 1e-2):
-            w = rng.normal(size=3) * mag
-            K = np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
-            R = np.eye(3) + K + K @ K / 2
-            q = p @ R.T + rng.normal(size=3) * 0.1
-            cases.append((q, set(ConvexHull(q).vertices.tolist())))
+
+    def rot(mag):
+        w = rng.normal(size=3) * mag
+        th = np.linalg.norm(w); k = w / th
+        K = np.array([[0, -k[2], k[1]], [k[2], 0, -k[0]], [-k[1], k[0], 0]])
+        return np.eye(3) + np.sin(th) * K + (1 - np.cos(th)) * K @ K
+
+    g = np.linspace(-0.5, 0.5, 6)
+    X, Y, Z = np.meshgrid(g, g * 0.4, g * 0.7, indexing='ij')
+    box = np.stack([X.ravel(), Y.ravel(), Z.ravel()], 1)
+    surf = box[(np.abs(box[:, 0]) == 0.5) | (np.abs(box[:, 1]) == 0.2) | (np.abs(box[:, 2]) == 0.35)]
+    base = [surf]
+    if os.path.exists('gpurun_out/hull_cases.pkl'):
+        base += [p for p, _ in pickle.load(open('gpurun_out/hull_cases.pkl', 'rb'))]
+    cases = []
+    for p in base:
+        cases.append(p)
+        for mag in (1e-15, 1e-12, 1e-9, 1e-6, 1e-3, 1.0, 2.0):
+            cases.append(p @ rot(mag).T + rng.normal(size=3) * 0.2)
+    for n in (5, 8, 20, 100):
+        cases.append(rng.normal(size=(n, 3)))
+    s_ = rng.normal(size=(200, 3)); cases.append(s_ / np.linalg.norm(s_, axis=1)[:, None])
     bad = 0
-    for k, (p, ref) in enumerate(cases):
-        got = hull(p)
-        gc = {tuple(p[i]) for i in got}; rc = {tuple(p[i]) for i in ref}
-        if gc != rc:
-            got = {i for i in got if tuple(p[i]) not in rc}; ref = {i for i in ref if tuple(p[i]) not in gc}
+    for k, p in enumerate(cases):
+        ref = {tuple(p[i]) for i in ConvexHull(p).vertices}
+        got = {tuple(p[i]) for i in hull(p)}
+        if got != ref:
             bad += 1
-            print(k, 'extra', sorted(got - ref), 'missing', sorted(ref - got), 'nref', len(ref))
-    print('cases', len(cases), 'bad', bad)
+            print(k, len(p), 'extra', len(got - ref), 'missing', len(ref - got))
+    print('cases', len(cases), 'different from Qhull', bad)
