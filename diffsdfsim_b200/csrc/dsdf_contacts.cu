@@ -1249,13 +1249,37 @@ contacts_kernel(const BodyGeom* __restrict__ geom, const int* __restrict__ pairs
     if (tid == 0) { count[w] = nout; wstatus[w] = status; }
 }
 
+// _filter_contacts (contacts.py:97-158) as a stand-alone operator: one CTA per contact list.
+__global__ void __launch_bounds__(CONTACT_THREADS)
+filter_kernel(const double* __restrict__ normals, const double* __restrict__ p1, const int* __restrict__ n, int capK, double eps,
+              int* __restrict__ keep, int* __restrict__ status) {
+    extern __shared__ double smraw[];
+    const int w = blockIdx.x, tid = threadIdx.x, nt = blockDim.x;
+    RefineSmem sm;
+    sm.P = smraw; sm.X = sm.P + 9 * (size_t)capK; sm.ABC = sm.X + 3 * (size_t)capK; sm.HK = sm.X + (size_t)capK;
+    sm.red = sm.ABC + 3 * (size_t)capK;
+    sm.ID = reinterpret_cast<int*>(sm.red + 40);
+    sm.SC = sm.ID + capK; sm.CL = sm.SC + capK; sm.HI = sm.CL + capK; sm.KEEP = sm.HI + capK; sm.TMP = sm.KEEP + capK;
+    const int m = min(n[w], capK);
+    for (int k = tid; k < m; k += nt) {
+        const size_t o = ((size_t)w * capK + k) * 3;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) { sm.P[(size_t)c * capK + k] = normals[o + c]; sm.P[(size_t)(3 + c) * capK + k] = p1[o + c]; }
+    }
+    __syncthreads();
+    const int st = filter_contacts(sm, capK, m, eps);
+    __syncthreads();
+    for (int k = tid; k < m; k += nt) keep[(size_t)w * capK + k] = sm.KEEP[k];
+    if (tid == 0) status[w] = st | (n[w] > capK ? 1 : 0);
+}
+
 }  // namespace dsdf
 
 using namespace dsdf;
 
 extern "C" {
 
-static size_t g_contacts_smem = 0;
+static size_t g_contacts_smem = 0, g_filter_smem = 0;
 
 int dsdf_contacts_detect_loop(const dsdf_body_geom* geom, const int32_t* pairs, int npairs, const double* p,
                               const double* shape, const unsigned char* active,
@@ -1284,6 +1308,17 @@ int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, int n
     return dsdf_contacts_detect_loop(geom, pairs, npairs, p, shape, active, W, nb, eps, tol, fd_eps, body_eps, detach_b2,
                                      capK, maxc, count, cbody, cface, cabc, cgeo, wstatus, pre_ids, pre_cnt, nullptr,
                                      nullptr, stream);
+}
+
+int dsdf_filter_contacts(const double* normals, const double* p1, const int32_t* n, int W, int capK, double eps,
+                         int32_t* keep, int32_t* status, void* stream) {
+    if (W <= 0 || capK < 32 || capK > 1024 || (capK & 3)) return -1;
+    const size_t smem = refine_smem_bytes(capK);
+    if (smem > 227 * 1024) return -2;
+    cudaError_t e = ensure_smem(filter_kernel, smem, &g_filter_smem);
+    if (e != cudaSuccess) return (int)e;
+    filter_kernel<<<W, CONTACT_THREADS, smem, (cudaStream_t)stream>>>(normals, p1, n, capK, eps, keep, status);
+    return (int)cudaGetLastError();
 }
 
 int dsdf_contacts_phase_cycles(unsigned long long* out8, int reset) {   /* out: PH_COUNT = 16 counters */

@@ -97,3 +97,28 @@ class _Integrate(torch.autograd.Function):
 def integrate(p, v, dt, active=None):
     """active: optional uint8 (W) mask; inactive worlds pass their pose through."""
     return _Integrate.apply(p, v, dt, active)
+
+
+def filter_contacts(normals, p1, eps=1e-3, count=None):
+    """``_filter_contacts`` (sdf_physics/physics3d/contacts.py:97-158) on the device, batched: normals, p1 (W,K,3) (or (K,3)),
+    ``count`` (W) valid rows per list (default: all K).  Returns the boolean keep mask (W,K) (the reference returns the
+    kept indices cluster by cluster; the SET is the same) and the per-list status bits."""
+    _lib.require_cuda(normals, p1)
+    single = normals.dim() == 2
+    if single:
+        normals, p1 = normals[None], p1[None]
+    W, K = normals.shape[0], normals.shape[1]
+    # work-buffer capacity: the device 3-D hull needs capK >= 2 x the largest cluster (dsdf_contacts.cu hull3d_vertices)
+    capK = min(1024, max(32, (2 * K + 3) // 4 * 4))
+    if K > capK:
+        raise ValueError('filter_contacts: at most 1024 contacts per list')
+    pad = lambda t: torch.cat([t, t.new_zeros(W, capK - K, 3)], 1).contiguous() if capK != K else t.contiguous()
+    nrm, pts = pad(normals.detach().double()), pad(p1.detach().double())
+    n = (torch.full((W,), K, dtype=torch.int32, device=nrm.device) if count is None else count.to(torch.int32).contiguous())
+    keep = torch.zeros(W, capK, dtype=torch.int32, device=nrm.device)
+    status = torch.zeros(W, dtype=torch.int32, device=nrm.device)
+    rc = _lib.call('dsdf_filter_contacts', _lib.ptr(nrm), _lib.ptr(pts), _lib.ptr(n), W, capK, float(eps), _lib.ptr(keep),
+                   _lib.ptr(status), _lib.stream())
+    _lib.check(rc, 'dsdf_filter_contacts')
+    mask = keep[:, :K].bool()
+    return (mask[0], status[0]) if single else (mask, status)

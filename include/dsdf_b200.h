@@ -170,6 +170,13 @@ int dsdf_contacts_detect(const dsdf_body_geom* geom, const int32_t* pairs, int n
                          int W, int nb, double eps, double tol, double fd_eps, double body_eps, int detach_b2,
                          int capK, int maxc, int32_t* count, int32_t* cbody, int32_t* cface, double* cabc, double* cgeo,
                          int32_t* wstatus, int32_t* pre_ids, int32_t* pre_cnt, void* stream);
+/* Replaces _filter_contacts (sdf_physics/physics3d/contacts.py:97-158) as a stand-alone operator: W independent contact
+ * lists, list w = the first n[w] rows of normals / p1 (W,capK,3).  keep (W,capK) <- 1 for the contacts the reference keeps:
+ * zero normals dropped, greedy clustering by angle < 1e-2 rad to the first remaining normal, per cluster the vertices of the
+ * convex hull of p1 (3-D; min-variance axis dropped when flat -> 2-D; -> 1-D min / max, one point if the extent <= eps),
+ * with Qhull's degeneracy decisions (scipy.spatial.ConvexHull in the reference).  status (W): DSDF_CON_* bits. */
+int dsdf_filter_contacts(const double* normals, const double* p1, const int32_t* n, int W, int capK, double eps,
+                         int32_t* keep, int32_t* status, void* stream);
 /* Profiling aid: cumulative SM cycles (thread 0 of every CTA) per phase of the contact kernel
  * [overlap, gather, sort+init, frank-wolfe, push+compact, geometry, filter, append]; returns -1 unless the library
  * was built with -DDSDF_PHASE_PROFILE (DSDF_PHASE_PROFILE=1 python -m diffsdfsim_b200.build). Host pointer out8. */
