@@ -307,6 +307,25 @@ def golden_detach_2nd_bounce():
     np.savez_compressed(os.path.join(HERE, 'detach_2nd_bounce.npz'), **d)
 
 
+def golden_filter_contacts():
+    """The reference's own _filter_contacts (sdf_physics/physics3d/contacts.py:97-158, scipy's Qhull) on synthetic contact
+    lists (specs.filter_cases): kept indices per list."""
+    from specs import filter_cases
+    cases = filter_cases()
+    K = max(len(p) for _, p, _ in cases)
+    P, N = np.zeros((len(cases), K, 3)), np.zeros((len(cases), K, 3))
+    kept, off = [], [0]
+    for w, (name, p, n) in enumerate(cases):
+        P[w, :len(p)], N[w, :len(p)] = p, n
+        idx = rc._filter_contacts(torch.as_tensor(n, dtype=F64), torch.as_tensor(p, dtype=F64), eps=1e-3)
+        kept += idx.tolist()
+        off.append(len(kept))
+        print('filter_contacts', name, len(p), '->', len(idx))
+    np.savez_compressed(os.path.join(HERE, 'filter_contacts.npz'), names=np.array([c[0] for c in cases]), p1=P, normals=N,
+                        count=np.array([len(p) for _, p, _ in cases]), kept=np.array(kept, dtype=np.int64),
+                        off=np.array(off, dtype=np.int64))
+
+
 if __name__ == '__main__':
     torch.manual_seed(0)
     names = sys.argv[1:] or (list(SCENES) + ['sdf_query'])
@@ -315,6 +334,8 @@ if __name__ == '__main__':
             golden_sdf()
         elif n == 'detach_2nd_bounce':
             golden_detach_2nd_bounce()
+        elif n == 'filter_contacts':
+            golden_filter_contacts()
         else:
             mk, leaves = SCENES[n]
             spec = mk()
