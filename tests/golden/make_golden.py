@@ -307,6 +307,34 @@ def golden_detach_2nd_bounce():
     np.savez_compressed(os.path.join(HERE, 'detach_2nd_bounce.npz'), **d)
 
 
+def golden_trajectory_loss():
+    """The reference's own trajectory_loss (experiments/trajectory_fitting/optim_sphere.py:114-160) on synthetic recorded
+    trajectories: 4 worlds, 14 model states vs 19 target states each, irregular and partly coinciding time stamps (the
+    tie rule of the nearest-time scan matters), random poses / velocities of two bodies."""
+    from types import SimpleNamespace
+    fn = reference_function('experiments/trajectory_fitting/optim_sphere.py', 'trajectory_loss', {})
+    rng = np.random.RandomState(3)
+    W, S, St = 4, 14, 19
+    t = np.sort(rng.uniform(0, 1, (W, S)), 1)
+    tt = np.sort(rng.uniform(0, 1, (W, St)), 1)
+    tt[1, 5] = 0.5 * (t[1, 3] + t[1, 4]); tt[1] = np.sort(tt[1])     # a target state exactly between two model states
+    t[2] = np.arange(S) / 30.0; tt[2] = np.arange(St) / 60.0 + 1.0 / 120.0   # ties at equal distance
+    p, pt = rng.normal(size=(W, S, 14)), rng.normal(size=(W, St, 14))
+    v, vt = rng.normal(size=(W, S, 12)), rng.normal(size=(W, St, 12))
+    loss, grad = np.zeros(W), np.zeros((W, S, 14))
+    for w in range(W):
+        ps = [torch.tensor(p[w, k], dtype=F64, requires_grad=True) for k in range(S)]
+        a = SimpleNamespace(trajectory=[(float(t[w, k]), ps[k], torch.tensor(v[w, k]), [], None) for k in range(S)])
+        b = SimpleNamespace(trajectory=[(float(tt[w, k]), torch.tensor(pt[w, k]), torch.tensor(vt[w, k]), [], None)
+                                        for k in range(St)])
+        l = fn(a, b)
+        l.backward()
+        loss[w] = float(l)
+        grad[w] = np.stack([x.grad.numpy() for x in ps])
+        print('trajectory_loss world', w, float(l))
+    np.savez_compressed(os.path.join(HERE, 'trajectory_loss.npz'), t=t, tt=tt, p=p, pt=pt, v=v, vt=vt, loss=loss, grad=grad)
+
+
 def golden_filter_contacts():
     """The reference's own _filter_contacts (sdf_physics/physics3d/contacts.py:97-158, scipy's Qhull) on synthetic contact
     lists (specs.filter_cases): kept indices per list."""
@@ -336,6 +364,8 @@ if __name__ == '__main__':
             golden_detach_2nd_bounce()
         elif n == 'filter_contacts':
             golden_filter_contacts()
+        elif n == 'trajectory_loss':
+            golden_trajectory_loss()
         else:
             mk, leaves = SCENES[n]
             spec = mk()

@@ -65,3 +65,28 @@ def test_analytic_meshes_have_the_surveyed_sizes():
     v, f = meshes.icosphere(0.5, 4)
     assert v.shape == (2562, 3) and f.shape == (5120, 3)
     np.testing.assert_allclose(np.linalg.norm(v, axis=1), 0.5, rtol=1e-12)
+
+
+def test_batched_trajectory_loss_matches_the_reference_function():
+    """losses.trajectory_loss (batched, every world matched on its own) against the outputs of the reference's own
+    trajectory_loss (experiments/trajectory_fitting/optim_sphere.py:114-160, executed by tests/golden/make_golden.py):
+    irregular time stamps, exact ties in the nearest-time scan, gradients w.r.t. every recorded pose."""
+    import os
+    from types import SimpleNamespace
+    import numpy as np
+    import torch
+    from diffsdfsim_b200.losses import trajectory_loss
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'trajectory_loss.npz'))
+    W, S, St = g['t'].shape[0], g['t'].shape[1], g['tt'].shape[1]
+    T = lambda a: torch.tensor(a, dtype=torch.float64)
+    ps = [T(g['p'][:, k]).reshape(W, 2, 7).requires_grad_(True) for k in range(S)]
+    a = SimpleNamespace(W=W, device=torch.device('cpu'), batched=True,
+                        trajectory=[(T(g['t'][:, k]), ps[k], T(g['v'][:, k]).reshape(W, 2, 6), None, None) for k in range(S)])
+    b = SimpleNamespace(W=W, device=torch.device('cpu'), batched=True,
+                        trajectory=[(T(g['tt'][:, k]), T(g['pt'][:, k]).reshape(W, 2, 7), T(g['vt'][:, k]).reshape(W, 2, 6),
+                                     None, None) for k in range(St)])
+    loss = trajectory_loss(a, b)
+    np.testing.assert_allclose(loss.detach().numpy(), g['loss'], rtol=1e-13)
+    loss.sum().backward()
+    grad = np.stack([x.grad.reshape(W, 14).numpy() for x in ps], 1)
+    np.testing.assert_allclose(grad, g['grad'], rtol=1e-12, atol=1e-15)
