@@ -205,8 +205,76 @@ class PdipmEngine(Engine):
         return new_v
 
     def post_stabilization(self, world):
-        raise NotImplementedError('post-stabilisation (engines.py:85-121) is off by default in the reference '
-                                  '(utils.py:64) and listed under "next" in SURVEY.md s8f')
+        """engines.py:85-121 for all worlds at once: dp = -argmin 1/2 z'Mz  s.t.  Jc z <= Jc v (1 - e),  Je z = Je v, with the
+        contacts, velocities and mass matrix the world has after its accepted sub-step.  The reference builds a fresh
+        ``LCPFunction()`` for it (20 iterations, not the engine's ``max_iter``); so does this.  Runs on the general dense LCP
+        operator (``dsdf_lcp_forward / backward`` with per-world inequality counts) and is differentiable like the
+        reference's.  Returns (W, nb, 6) -- ``(nz,)`` for a single world through ``World3D``'s own call."""
+        from .transforms import quaternion_to_matrix
+        st, cs = world.state, world.contact_set
+        W, nb, maxc, dev = world.W, world.nb, world.maxc, world.device
+        nz = 6 * nb
+        v = st.v.reshape(W, nz)
+        R = quaternion_to_matrix(st.p[..., :4])                                        # (W,nb,3,3)
+        Iw = R @ st.Ibody.reshape(W, nb, 3, 3) @ R.transpose(-1, -2)
+        M = torch.zeros(W, nb, 6, nb, 6, dtype=F64, device=dev)
+        eye3 = torch.eye(3, dtype=F64, device=dev)
+        for b in range(nb):
+            M[:, b, :3, b, :3] = Iw[:, b]
+            M[:, b, 3:, b, 3:] = st.mass[:, b, None, None] * eye3
+        M = M.reshape(W, nz, nz)
+        neq = world.A.shape[1] if world.A is not None else 0
+        geo = world.contact_geo.detach() if world.stop_contact_grad else world.contact_geo
+        n, p1, p2 = geo[..., 0:3], geo[..., 3:6], geo[..., 6:9]
+        valid = (torch.arange(maxc, device=dev)[None, :] < cs.count[:, None])
+        i1, i2 = cs.body[..., 0].long().clamp(0, nb - 1), cs.body[..., 1].long().clamp(0, nb - 1)
+        r1 = torch.cat([torch.linalg.cross(p1, n), n], -1) * valid[..., None]           # world.py:56-71 (physics3d)
+        r2 = -torch.cat([torch.linalg.cross(p2, n), n], -1) * valid[..., None]
+        Jc = torch.zeros(W, maxc, nb, 6, dtype=F64, device=dev)
+        Jc = Jc.scatter_add(2, i1[:, :, None, None].expand(-1, -1, 1, 6), r1[:, :, None, :])
+        Jc = Jc.scatter_add(2, i2[:, :, None, None].expand(-1, -1, 1, 6), r2[:, :, None, :]).reshape(W, maxc, nz)
+        e = 0.5 * (torch.gather(st.rest, 1, i1) + torch.gather(st.rest, 1, i2))
+        jv = (Jc @ v[..., None])[..., 0]
+        gc = jv + jv * -e
+        # a world without contacts gets one inert row (0 z <= 1): the solution is then the equality-constrained one the
+        # reference computes by a direct solve (engines.py:99-110)
+        none = (cs.count == 0)
+        gc = torch.where(none[:, None] & (torch.arange(maxc, device=dev)[None, :] == 0), torch.ones_like(gc), gc)
+        nin = torch.clamp(cs.count, min=1).to(torch.int32).contiguous()
+        A = world.A if neq else None
+        ge = (world.A @ v[..., None])[..., 0] if neq else None
+        x = _LcpRagged.apply(M, torch.zeros(W, nz, dtype=F64, device=dev), Jc, gc, A, ge,
+                             torch.zeros(W, maxc, maxc, dtype=F64, device=dev), nin)
+        return (-x).reshape(W, nb, 6)
+
+
+class _LcpRagged(torch.autograd.Function):
+    """LCPFunction (lcp.py:48-213) with a per-world number of inequality rows (the first nin[w] rows of G, h, F count)."""
+
+    @staticmethod
+    def forward(ctx, Q, p, G, h, A, b, F, nin):
+        c = lambda t: t.contiguous()
+        Q, p, G, h, F = c(Q), c(p), c(G), c(h), c(F)
+        A, b = (c(A), c(b)) if A is not None else (None, None)
+        x, nu, lam, s, status, _ = lcp_solve_raw(Q, p, G, h, A, b, F, nin, max_iter=20, check_spd=False)
+        ctx.save_for_backward(x, nu, lam, s, Q, G, A if A is not None else Q.new_empty(0), F, nin)
+        ctx.has_eq = A is not None
+        return x
+
+    @staticmethod
+    def backward(ctx, gz):
+        x, nu, lam, s, Q, G, A, F, nin = ctx.saved_tensors
+        A = A if ctx.has_eq else None
+        need = list(ctx.needs_input_grad[:7])
+        dQ, dp, dG, dh, dA, db, dF = lcp_backward_raw(Q, G, A, F, x, nu, lam, s, gz, nin, need)
+        rows = (torch.arange(G.shape[1], device=G.device)[None, :] < nin[:, None])
+        if dG is not None:
+            dG = dG * rows[..., None]
+        if dh is not None:
+            dh = dh * rows
+        if dF is not None:
+            dF = dF * rows[..., None] * rows[:, None, :]
+        return dQ, dp, dG, dh, dA, db, dF, None
 
 
 class DensePdipmEngine(PdipmEngine):

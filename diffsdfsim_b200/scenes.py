@@ -26,8 +26,8 @@ def body(kind, pos, *, dims=None, rad=None, height=None, grid=None, scale=None, 
 
 
 def scene(bodies, *, no_contact=(), axis_locks=(), dt=1.0 / 30, eps=EPS, tol=1e-8, fric_dirs=8,
-          strict_no_penetration=True, time_of_contact_diff=True, steps=10):
-    return dict(bodies=bodies, no_contact=list(no_contact), axis_locks=list(axis_locks), dt=dt, eps=eps,
+          strict_no_penetration=True, time_of_contact_diff=True, steps=10, post_stab=False):
+    return dict(post_stab=post_stab, bodies=bodies, no_contact=list(no_contact), axis_locks=list(axis_locks), dt=dt, eps=eps,
                 tol=tol, fric_dirs=fric_dirs, strict_no_penetration=strict_no_penetration,
                 time_of_contact_diff=time_of_contact_diff, steps=steps)
 
@@ -104,7 +104,7 @@ def build_world(spec, device=None, params=None, **world_kw):
     bodies, cons = make_bodies(spec, device, params)
     kw = dict(dt=spec['dt'], eps=spec['eps'], tol=spec['tol'], fric_dirs=spec['fric_dirs'],
               strict_no_penetration=spec['strict_no_penetration'],
-              time_of_contact_diff=spec['time_of_contact_diff'])
+              time_of_contact_diff=spec['time_of_contact_diff'], post_stab=spec.get('post_stab', False))
     kw.update(world_kw)
     kw.setdefault('device', device)
     return World3D(bodies, cons, **kw)

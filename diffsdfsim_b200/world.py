@@ -114,8 +114,7 @@ class World3D:
                  strict_no_penetration=True, time_of_contact_diff=True, stop_contact_grad=False,
                  stop_friction_grad=False, detach_contact_b2=False, device=None, capK=384, maxc=32,
                  record_prefilter=False):
-        if post_stab:
-            raise NotImplementedError('post_stab (off by default in the reference) is not built yet')
+        self.post_stab = bool(post_stab)          # world.py:358-370; runs on the host-driven loop + the dense LCP operator
         self.engine = get_instance(engines_module, engine)
         self.contact_callback = get_instance(contacts_module, contact_callback)
         self.bodies = list(bodies)
@@ -330,7 +329,8 @@ class World3D:
         """The device-resident loop covers the default configuration; plug-in engines, the dense LCP path, the torch
         restatement of World.H, per-sub-step (vectorised) forces and pre-filter recording use the host-driven loop."""
         return (self.device_loop and self.device.type == 'cuda' and type(self.engine) is engines_module.PdipmEngine
-                and self.toc_native and not self._f_vectorized and not self.detector.record_prefilter)
+                and self.toc_native and not self._f_vectorized and not self.detector.record_prefilter
+                and not self.post_stab)
 
     def _snapshot(self):
         st = self.state
@@ -504,13 +504,38 @@ class World3D:
         self.contact_geo = torch.where(a3, geo, self.contact_geo)
         self.contact_set = cs
         self.t = t_new
+        if self.post_stab:
+            self._post_stabilize(accept, dt_try)
         return accept, dt_next, active_next, int(fl[1])
+
+    def _post_stabilize(self, accept, dt):
+        """world.py:358-370 for the worlds whose sub-step was just accepted: half of the engine's stabilising displacement is
+        applied as a velocity over the sub-step's dt, the velocities are restored, the contacts are detected again."""
+        st = self.state
+        dp = self.engine.post_stabilization(self)
+        p_ps = ops.integrate(st.p, dp / 2, dt, accept)
+        while True:
+            cs = self.contact_set.clone()
+            self.detector.detect(p_ps.detach(), self.shape, cs, accept, eps=self.eps, tol=self.tol,
+                                 fd_eps=Defaults3D.EPSILON, body_eps=self.body_eps, detach_b2=self.detach_contact_b2)
+            am = accept.bool()
+            over = int((torch.where(am, cs.status, torch.zeros_like(cs.status)) & 3).max())          # capK / maxc overflow
+            if not over:
+                break
+            self._grow_capacity(over)
+        geo = differentiable_geometry(p_ps, self.shape, cs, self.table, Defaults3D.EPSILON, self.detach_contact_b2,
+                                      self.shape_t, self.vert_leaves)
+        a3 = am[:, None, None]
+        st.p = torch.where(a3, p_ps, st.p)
+        self.contact_geo = torch.where(a3, geo, self.contact_geo)
+        self.contact_set = cs
+        self.max_nc = max(int(self.max_nc), int(cs.count.max()))
 
     def _use_speculation(self, n_active):
         """Speculate when few worlds are still active (their slots are plentiful) and no body has per-world geometry
         (the contact kernels address per-world meshes / grids by slot index)."""
         return (self.speculate and self.W >= 64 and 0 < n_active <= self.W // 8 and self._shared_geometry
-                and self.shape_t is None and not self.vert_leaves)
+                and self.shape_t is None and not self.vert_leaves and not self.post_stab)
 
     def _attempt_speculative(self, active, dt_try, end_t):
         """One round that tries dt, dt/2 and dt/4 of every still-active world AT ONCE.

@@ -105,4 +105,5 @@ def build(spec, params=None, max_iter=10, **world_kw):
     locks = [(bodies[i], a) for i, a in spec['axis_locks']]
     return World(bodies, pinned=pinned, axis_locks=locks, dt=spec['dt'], eps=spec['eps'], tol=spec['tol'],
                  fric_dirs=spec['fric_dirs'], strict_no_penetration=spec['strict_no_penetration'],
-                 time_of_contact_diff=spec['time_of_contact_diff'], max_iter=max_iter, **world_kw)
+                 time_of_contact_diff=spec['time_of_contact_diff'], max_iter=max_iter,
+                 post_stab=spec.get('post_stab', False), **world_kw)

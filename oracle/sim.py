@@ -272,8 +272,10 @@ class World:
 
     def __init__(self, bodies, pinned=(), axis_locks=(), dt=1.0 / 30, eps=DEFAULT_EPS, tol=DEFAULT_TOL,
                  fric_dirs=8, strict_no_penetration=True, time_of_contact_diff=True,
-                 stop_contact_grad=False, stop_friction_grad=False, detach_contact_b2=False, max_iter=10):
+                 stop_contact_grad=False, stop_friction_grad=False, detach_contact_b2=False, max_iter=10,
+                 post_stab=False):
         self.bodies = list(bodies)
+        self.post_stab = post_stab
         self.nb = len(self.bodies)
         # equality rows: TotalConstraint3D (6 rows, J = I6) then single-axis locks (body, axis in 0..5)
         rows = []
@@ -476,9 +478,41 @@ class World:
             self.set_p(p0.clone())
             self.set_v(v0.clone())
             self.contacts = c0
+        if self.post_stab:
+            # world.py:358-370: half of the stabilising displacement, applied as a velocity over dt; contacts re-detected
+            tmp_v = self.v
+            self.set_v(self.post_stabilization() / 2)
+            for b in self.bodies:
+                b.move(dt)
+            self.set_v(tmp_v)
+            self.find_contacts()
         self.trajectory.append((self.t, self.get_p(), self.v, self.contacts))
         self.t += dt
         return tries
+
+    def post_stabilization(self):
+        """engines.py:85-121: min 1/2 z'Mz  s.t.  Jc z <= Jc v (1 - e),  Je z = Je v;  returns dp = -z (the reference builds
+        a fresh LCPFunction() here: 20 iterations, not the engine's max_iter)."""
+        nz, neq = 6 * self.nb, len(self.eq_rows)
+        v, M, Je = self.v, self.M(), self.Je()
+        ge = Je @ v
+        if not self.contacts:
+            if neq:
+                P = torch.cat([torch.cat([M, -Je.t()], dim=1), torch.cat([Je, Je.new_zeros(neq, neq)], dim=1)])
+                x = torch.inverse(P) @ torch.cat([Je.new_zeros(nz), ge])
+            else:
+                x = torch.inverse(M) @ M.new_zeros(nz)
+            return -x[:nz]
+        Jc = self.Jc()
+        e = torch.stack([(self.bodies[i1].restitution + self.bodies[i2].restitution) / 2
+                         for _, i1, i2 in self.contacts])
+        gc = Jc @ v + (Jc @ v) * -e
+        nc = Jc.shape[0]
+        A = Je.unsqueeze(0) if neq else torch.tensor([])
+        b = ge.unsqueeze(0) if neq else torch.tensor([])
+        fn = make_lcp_function()
+        z = fn(M.unsqueeze(0), M.new_zeros(1, nz), Jc.unsqueeze(0), gc.unsqueeze(0), A, b, Jc.new_zeros(1, nc, nc))
+        return -z[0]
 
     def _time_of_contact(self, dt_, p0):
         """world.py:275-341."""

@@ -114,7 +114,7 @@ def build_reference(spec, params=None):
         joints.append(axis_cls[a](bodies[i]))
     world = World3D(bodies, joints, dt=spec['dt'], eps=spec['eps'], tol=spec['tol'], fric_dirs=spec['fric_dirs'],
                     strict_no_penetration=spec['strict_no_penetration'],
-                    time_of_contact_diff=spec['time_of_contact_diff'])
+                    time_of_contact_diff=spec['time_of_contact_diff'], post_stab=spec.get('post_stab', False))
     return world
 
 

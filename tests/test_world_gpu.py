@@ -19,7 +19,7 @@ F64 = torch.float64
 
 # (state atol, grad rtol); box_tilted balances on an edge with rank-deficient contact sets: the reference's own LU
 # round-off is amplified there (oracle-vs-reference shows the same), so only a drift bound is asserted.
-TOL = {'box_on_plane': (1e-8, 1e-5), 'bouncing_sphere': (1e-8, 1e-4), 'grid_on_pole': (1e-8, 1e-4),
+TOL = {'box_on_plane': (1e-8, 1e-5), 'box_on_plane_poststab': (1e-8, 1e-5), 'bouncing_sphere': (1e-8, 1e-4), 'grid_on_pole': (1e-8, 1e-4),
        'box_tilted': (2e-2, None), 'mixed_primitives': (1e-6, 5e-3),
        # BASELINE configurations at their named sizes (see tests/test_oracle_golden.py for the tolerances)
        'c1_bouncing_sphere': (5e-6, 5e-3), 'c3_mixed16': (1e-6, 1e-5), 'c4_cow_on_pole': (1e-6, 1e-5),
@@ -79,18 +79,20 @@ def test_single_world_rollout_matches_reference_golden(name):
         np.testing.assert_allclose(got, ref, rtol=grtol, atol=grtol * max(1e-9, np.abs(ref).max()), err_msg='grad ' + k)
 
 
-def test_batched_worlds_match_oracle_per_world():
-    """W different worlds in one batch (per-world mass / friction / push) == W separate oracle runs."""
-    W, steps = 6, 6
+@pytest.mark.parametrize('post_stab', [False, True])
+def test_batched_worlds_match_oracle_per_world(post_stab):
+    """W different worlds in one batch (per-world mass / friction / push) == W separate oracle runs; also with
+    post-stabilisation on (engines.py:85-121, world.py:358-370)."""
+    W, steps = (6, 6) if not post_stab else (3, 5)
     gen = torch.Generator().manual_seed(0)
     mass = 0.9 + 0.2 * torch.rand(W, generator=gen, dtype=F64)
     fric = 0.05 + 0.2 * torch.rand(W, generator=gen, dtype=F64)
     push = 2.0 + 3.0 * torch.rand(W, 2, generator=gen, dtype=F64)
-    spec = scenes.box_on_plane(floor=(4.0, 1.0, 4.0), steps=steps)
+    spec = dict(scenes.box_on_plane(floor=(4.0, 1.0, 4.0), steps=steps), post_stab=post_stab)
     params = dict(mass=mass.cuda().requires_grad_(True), fric_coeff=fric.cuda().requires_grad_(True),
                   push=push.cuda().requires_grad_(True))
     world = scenes.build_world(spec, device='cuda', params=params)
-    assert world.W == W
+    assert world.W == W and world.post_stab == post_stab
     loss = 0.
     traj = []
     for k in range(steps):
