@@ -284,7 +284,9 @@ class _ContactGeometry(torch.autograd.Function):
     def backward(ctx, ggeo):
         p, shape, count, body, face, abc = ctx.saved_tensors
         gp, gshape, gctri = geometry_vjp(ctx.table, p, shape, count, body, face, abc, ggeo, ctx.fd_eps, ctx.detach_b2,
-                                         None, ctx.want_shape)
+                                         None, ctx.want_shape or bool(ctx.leaves))
+        if not ctx.want_shape:
+            gshape = None
         gverts = []
         if ctx.leaves:
             gverts = [torch.zeros_like(v) for _, v in ctx.leaves]

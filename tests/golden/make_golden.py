@@ -307,6 +307,30 @@ def golden_detach_2nd_bounce():
     np.savez_compressed(os.path.join(HERE, 'detach_2nd_bounce.npz'), **d)
 
 
+def golden_mesh_sdf():
+    """The reference's own MeshSDF (SDF3D._diff_marching_cubes, bodies.py:652-704) and get_ang_inertia (:260-395), with the
+    declared marching-cubes stand-in: vertices, faces, inertia, and the gradients of
+    sum(w * verts) + sum(u * inertia(2 * verts, faces, 1.3)) w.r.t. the SDF parameters."""
+    from specs import mesh_sdf_cases
+    rng = np.random.RandomState(5)
+    d = {}
+    for name, fn, params, res in mesh_sdf_cases():
+        ps = [q.clone().requires_grad_(True) for q in params]
+        verts, faces = rb.SDF3D._diff_marching_cubes(fn, res=res)(*ps)
+        w = torch.tensor(rng.randn(*verts.shape))
+        u = torch.tensor(rng.randn(3, 3))
+        J = rb.get_ang_inertia(verts * 2.0, faces, torch.tensor(1.3, dtype=F64))
+        loss = (w * verts).sum() + (u * J).sum()
+        loss.backward()
+        d[name + '_verts'], d[name + '_faces'] = verts.detach().numpy(), faces.numpy()
+        d[name + '_w'], d[name + '_u'], d[name + '_J'] = w.numpy(), u.numpy(), J.detach().numpy()
+        d[name + '_loss'] = float(loss)
+        for k, q in enumerate(ps):
+            d['%s_grad%d' % (name, k)] = q.grad.numpy()
+        print('mesh_sdf', name, tuple(verts.shape), tuple(faces.shape), float(loss), [q.grad.tolist() for q in ps])
+    np.savez_compressed(os.path.join(HERE, 'mesh_sdf.npz'), **d)
+
+
 def golden_trajectory_loss():
     """The reference's own trajectory_loss (experiments/trajectory_fitting/optim_sphere.py:114-160) on synthetic recorded
     trajectories: 4 worlds, 14 model states vs 19 target states each, irregular and partly coinciding time stamps (the
@@ -366,6 +390,8 @@ if __name__ == '__main__':
             golden_filter_contacts()
         elif n == 'trajectory_loss':
             golden_trajectory_loss()
+        elif n == 'mesh_sdf':
+            golden_mesh_sdf()
         else:
             mk, leaves = SCENES[n]
             spec = mk()

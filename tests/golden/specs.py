@@ -130,3 +130,20 @@ def filter_cases():
     nrm[5] = 0.0; nrm[17] = 0.0
     cases.append(('three clusters', pts, nrm))
     return [(name, p, (np.tile(up, (len(p), 1)) if n is None else n)) for name, p, n in cases]
+
+
+def mesh_sdf_cases():
+    """(name, sdf_func(points, *params), params, res) for the differentiable iso-surface mesh: an off-centre sphere (radius +
+    centre) and an IGR-style decoder with its latent code as the parameter."""
+    import torch
+    from diffsdfsim_b200 import igr
+    F64 = torch.float64
+    dec = igr.init_decoder(seed=3, radius_init=0.6)
+
+    def sphere(pts, r, c):
+        return (pts - c).norm(dim=1) - r
+
+    def decoder(pts, latent):
+        return igr.decode(dec, latent, pts)
+    return [('sphere', sphere, [torch.tensor(0.55, dtype=F64), torch.tensor([0.05, -0.02, 0.1], dtype=F64)], 24),
+            ('decoder', decoder, [torch.tensor([0.12, -0.07], dtype=F64)], 24)]

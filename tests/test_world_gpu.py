@@ -507,3 +507,52 @@ def test_rounded_box_world_matches_oracle_per_world(kind):
             got = params[k].grad[w].cpu().numpy()
             np.testing.assert_allclose(got, ref, rtol=1e-4, atol=1e-4 * max(1e-9, np.abs(ref).max()),
                                        err_msg=f'{kind}: world {w} grad {k}')
+
+
+def test_latent_code_gradient_through_iso_surface_mesh_and_inertia():
+    """Shape fitting of a neural-SDF body the way the reference does it for mesh and inertia (SDF3D._diff_marching_cubes /
+    MeshSDF, bodies.py:652-704; get_ang_inertia, :260-395): the body's mesh is the differentiable iso-surface of an
+    IGR-style decoder, its inertia the volume integral of that mesh, its SDF the decoder baked to a grid.  The loss of a
+    rollout with contacts must reach the latent code, and it must do so exactly through the two documented routes: the
+    mesh-vertex adjoint of the stepping path fed to the MeshSDF backward, and the inertia adjoint."""
+    from diffsdfsim_b200 import bodies, constraints, forces, igr, meshes
+    from diffsdfsim_b200.world import World3D
+    dec = igr.init_decoder(seed=3, radius_init=0.6)
+    fn = lambda pts, z: igr.decode(dec, z, pts)
+    latent = torch.tensor([0.12, -0.07], dtype=F64, requires_grad=True)
+    scale, mass = 1.0, 1.3
+
+    def build(z, hooks=None):
+        verts, faces = meshes.iso_surface_mesh(fn, [z], res=56)
+        verts_s = (verts * scale).cuda()
+        I = meshes.mesh_inertia_torch(verts * scale, faces).cuda()                    # unit mass
+        if hooks is not None:
+            verts_s.register_hook(lambda g: hooks.__setitem__('gv', g.clone()))
+            I.register_hook(lambda g: hooks.__setitem__('gI', g.clone()))
+        grid = igr.bake_grid(dec, z.detach(), res=56)
+        floor = bodies.SDFBox([0, -0.5, 0], [6.0, 1.0, 6.0], restitution=0.0, fric_coeff=0.3, device='cuda',
+                              max_tri_length=0.25)
+        lowest = float(verts_s.detach()[:, 1].min())
+        body = bodies.SDFGrid3D([0.0, -lowest + 5e-4, 0.0], scale, grid, mesh=(verts_s, faces.cuda()), inertia=I,
+                                vel=(0.3, 0.0, 0.1, 0.5, 0.0, 0.0), mass=mass, restitution=0.2, fric_coeff=0.3, device='cuda')
+        body.add_force(forces.Gravity3D())
+        world = World3D([floor, body], [constraints.TotalConstraint3D(floor)], strict_no_penetration=False)
+        return world, body, verts, faces
+
+    hooks = {}
+    world, body, verts, faces = build(latent, hooks)
+    loss = 0.
+    for _ in range(8):
+        world.step(fixed_dt=True)
+        loss = loss + (body.pos ** 2).sum() + 0.1 * (world.v[-6:] ** 2).sum()
+    assert int(world.contact_set.count.max()) > 0, 'the body must touch the floor'
+    loss.backward()
+    g = latent.grad.clone()
+    assert torch.isfinite(g).all() and float(g.abs().sum()) > 0
+    assert 'gv' in hooks and 'gI' in hooks and float(hooks['gv'].abs().sum()) > 0 and float(hooks['gI'].abs().sum()) > 0
+    # the same number from the two adjoints the stepping path produced, pushed through the host-side shape functions
+    z2 = latent.detach().clone().requires_grad_(True)
+    v2, f2 = meshes.iso_surface_mesh(fn, [z2], res=56)
+    I2 = meshes.mesh_inertia_torch(v2 * scale, f2)
+    ((v2 * scale) * hooks['gv'].cpu()).sum().add((I2 * hooks['gI'].cpu().reshape(3, 3)).sum()).backward()
+    np.testing.assert_allclose(g.numpy(), z2.grad.numpy(), rtol=1e-10, atol=1e-14)
