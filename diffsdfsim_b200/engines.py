@@ -39,6 +39,7 @@ class _Dynamics(torch.autograd.Function):
         _lib.require_cuda(p, v)
         c = lambda t: t.contiguous()
         p, v, mass, Ibody, fric, rest, f, dt, geo = [c(t) for t in (p, v, mass, Ibody, fric, rest, f, dt, geo)]
+        A = c(A) if A is not None else None
         fd, max_iter = cfg['fric_dirs'], cfg['max_iter']
         Q, pv, G, h, Fm, nin = _assemble(L, p, v, mass, Ibody, fric, rest, f, dt, active, count, cbody, geo, fd)
         x, nu, lam, s, status, iters = lcp_solve_raw(Q, pv, G, h, A, b, Fm, nin, max_iter=max_iter, check_spd=False,
@@ -70,9 +71,10 @@ class _Dynamics(torch.autograd.Function):
             am = active.bool().reshape(W, 1)
             gpass = torch.where(am, torch.zeros_like(gz), -gz).reshape(W, nb, 6)   # inactive worlds: new_v = v
             gz = torch.where(am, gz, torch.zeros_like(gz))
-        dQ, dp, dG, dh, _, _, dF = lcp_backward_raw(Q, G, A, Fm, x, nu, lam, s, gz, nin,
-                                                    need=(True, True, True, True, False, False, True),
-                                                    nineq_smem=cfg['ni_smem'])
+        want_A = bool(ctx.needs_input_grad[11]) and A is not None and A.numel() > 0
+        dQ, dp, dG, dh, dA, _, dF = lcp_backward_raw(Q, G, A, Fm, x, nu, lam, s, gz, nin,
+                                                     need=(True, True, True, True, want_A, False, True),
+                                                     nineq_smem=cfg['ni_smem'])
         dev = p.device
         gp = torch.empty_like(p)
         gv = torch.empty_like(v)
@@ -88,7 +90,7 @@ class _Dynamics(torch.autograd.Function):
         _lib.check(rc, 'dsdf_dynamics_assemble_backward')
         if gpass is not None:
             gv = gv + gpass
-        return gp, gv, gmass, gI, gfric, grest, gf, gdt, ggeo, None, None, None, None, None, None
+        return gp, gv, gmass, gI, gfric, grest, gf, gdt, ggeo, None, None, (dA if want_A else None), None, None, None
 
 
 class _DynamicsFused(torch.autograd.Function):
@@ -195,7 +197,7 @@ class PdipmEngine(Engine):
                    stop_friction_grad=world.stop_friction_grad,
                    ni_smem=max(world.max_nc, 1) * (2 + world.fric_dirs), nc_smem=max(world.max_nc, 1))
         cs = world.contact_set
-        if self.dense:
+        if self.dense or world._general_joints:
             new_v, status = _Dynamics.apply(st.p, st.v, st.mass, st.Ibody, st.fric, st.rest, f, dt, world.contact_geo,
                                             cs.count, cs.body, world.A, world.b, active, cfg)
         else:

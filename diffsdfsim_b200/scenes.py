@@ -26,8 +26,8 @@ def body(kind, pos, *, dims=None, rad=None, height=None, grid=None, scale=None, 
 
 
 def scene(bodies, *, no_contact=(), axis_locks=(), dt=1.0 / 30, eps=EPS, tol=1e-8, fric_dirs=8,
-          strict_no_penetration=True, time_of_contact_diff=True, steps=10, post_stab=False):
-    return dict(post_stab=post_stab, bodies=bodies, no_contact=list(no_contact), axis_locks=list(axis_locks), dt=dt, eps=eps,
+          strict_no_penetration=True, time_of_contact_diff=True, steps=10, post_stab=False, grippers=()):
+    return dict(post_stab=post_stab, grippers=[tuple(g) for g in grippers], bodies=bodies, no_contact=list(no_contact), axis_locks=list(axis_locks), dt=dt, eps=eps,
                 tol=tol, fric_dirs=fric_dirs, strict_no_penetration=strict_no_penetration,
                 time_of_contact_diff=time_of_contact_diff, steps=steps)
 
@@ -95,6 +95,8 @@ def make_bodies(spec, device=None, params=None, W=1):
     axis_cls = {3: C.XConstraint, 4: C.YConstraint, 5: C.ZConstraint}
     for i, a in spec['axis_locks']:
         cons.append(axis_cls[a](out[i]))
+    for i1, i2, axis in spec.get('grippers', ()):
+        cons.append(C.GripperJoint(out[i1], out[i2], axis))
     return out, cons
 
 
@@ -126,6 +128,18 @@ def box_on_plane(floor=(20.0, 1.0, 20.0), box=(1.0, 1.0, 1.0), mass=1.0, fric=0.
         body('box', pos, dims=list(box), mass=mass, fric_coeff=fric, restitution=restitution, gravity=True,
              ext_force=[0, 0, 0, push[0], 0, push[1]]),
     ], strict_no_penetration=False, time_of_contact_diff=toc, steps=steps)
+
+
+def gripper_pair(steps=8):
+    """Two boxes coupled by a GripperJoint (sdf_physics/physics3d/constraints.py:148-195): the large one rests on a pinned
+    floor, the small one hangs beside it, may only slide along the large one's x axis and is pushed along x (free) and z
+    (transmitted through the joint).  11 equality rows (6 pin + 5 joint), contacts between floor and large box."""
+    return scene([
+        body('box', [0, -0.5, 0], dims=[4.0, 1.0, 4.0], pinned=True, fric_coeff=0.2, restitution=0.2, max_tri_length=0.25),
+        body('box', [0, 0.5 + 2 * EPS, 0], dims=[1.0, 1.0, 1.0], mass=1.0, fric_coeff=0.2, restitution=0.2, gravity=True),
+        body('box', [1.4, 0.9, 0], dims=[0.5, 0.5, 0.5], mass=0.4, fric_coeff=0.2, restitution=0.2, gravity=True,
+             ext_force=[0, 0, 0, 1.5, 0, 0.8]),
+    ], no_contact=[(1, 2)], grippers=[(1, 2, (1.0, 0.0, 0.0))], strict_no_penetration=False, steps=steps)
 
 
 def bouncing_sphere(rad=0.5, height=1.0, vel=(0, 0, 0, 2.0, 0, 0), floor=(20.0, 1.0, 20.0), steps=20,

@@ -158,18 +158,30 @@ class World3D:
 
         # equality rows: constant 0/1 selections (constraints.py)
         self.joints = []
-        rows = []
+        rows, plan = [], []          # plan: Je row blocks in constraint order -- ('sel', first row, n) / ('gen', first row, joint)
         for j in constraints:
             i1 = self.bodies.index(j.body1)
-            self.joints.append((j, i1, None))
-            rows += [(i1, a) for a in j.rows()]
+            i2 = self.bodies.index(j.body2) if getattr(j, 'body2', None) is not None else None
+            self.joints.append((j, i1, i2))
+            if getattr(j, 'general', False):
+                plan.append(('gen', len(rows), (j, i1, i2)))
+                rows += [(-1, -1)] * j.num_constraints
+            else:
+                sel = [(i1, a) for a in j.rows()]
+                plan.append(('sel', len(rows), len(sel)))
+                rows += sel
         self.num_constraints = len(rows)
+        self._general_joints = [blk for kind, _, blk in plan if kind == 'gen']
+        self._je_plan = plan
         nz = 6 * nb
         A = torch.zeros(len(rows), nz, dtype=F64)
         for r, (i, a) in enumerate(rows):
-            A[r, 6 * i + a] = 1
-        self.A = A.to(dev).unsqueeze(0).expand(W, -1, -1).contiguous() if rows else None
+            if i >= 0:
+                A[r, 6 * i + a] = 1
+        self._A_static = A.to(dev).unsqueeze(0).expand(W, -1, -1).contiguous() if rows else None
         self.b = torch.zeros(W, len(rows), dtype=F64, device=dev) if rows else None
+        if self._general_joints:
+            rows = []                # the fused kernels only know selection rows: such a world uses the dense operator
         self.eq_rows = torch.tensor(rows, dtype=torch.int32, device=dev).reshape(-1, 2).contiguous()
 
         # contact detection set-up (replaces the py3ode HashSpace of world.py:69-72)
@@ -259,6 +271,24 @@ class World3D:
         Q = self.lcp_matrices()[0]
         return Q if self.batched else Q[0]
 
+    @property
+    def A(self):
+        """Je for all worlds (W,neq,nz), rows in constraint order (world.py:411-428).  Constant for the selection
+        constraints; joints coupling two bodies (GripperJoint) contribute pose-dependent, differentiable blocks."""
+        if not self._general_joints:
+            return self._A_static
+        st = self.state
+        A = self._A_static.clone()
+        for kind, r0, blk in self._je_plan:
+            if kind != 'gen':
+                continue
+            j, i1, i2 = blk
+            J1, J2 = j.J(st.p[:, i1], st.p[:, i2])
+            n = j.num_constraints
+            A[:, r0:r0 + n, 6 * i1:6 * i1 + 6] = J1
+            A[:, r0:r0 + n, 6 * i2:6 * i2 + 6] = J2
+        return A
+
     def Je(self):
         if self.A is None:
             return torch.zeros(0, 6 * self.nb, dtype=F64, device=self.device)
@@ -330,7 +360,7 @@ class World3D:
         restatement of World.H, per-sub-step (vectorised) forces and pre-filter recording use the host-driven loop."""
         return (self.device_loop and self.device.type == 'cuda' and type(self.engine) is engines_module.PdipmEngine
                 and self.toc_native and not self._f_vectorized and not self.detector.record_prefilter
-                and not self.post_stab)
+                and not self.post_stab and not self._general_joints)
 
     def _snapshot(self):
         st = self.state
@@ -535,7 +565,7 @@ class World3D:
         """Speculate when few worlds are still active (their slots are plentiful) and no body has per-world geometry
         (the contact kernels address per-world meshes / grids by slot index)."""
         return (self.speculate and self.W >= 64 and 0 < n_active <= self.W // 8 and self._shared_geometry
-                and self.shape_t is None and not self.vert_leaves and not self.post_stab)
+                and self.shape_t is None and not self.vert_leaves and not self.post_stab and not self._general_joints)
 
     def _attempt_speculative(self, active, dt_try, end_t):
         """One round that tries dt, dt/2 and dt/4 of every still-active world AT ONCE.

@@ -106,4 +106,4 @@ def build(spec, params=None, max_iter=10, **world_kw):
     return World(bodies, pinned=pinned, axis_locks=locks, dt=spec['dt'], eps=spec['eps'], tol=spec['tol'],
                  fric_dirs=spec['fric_dirs'], strict_no_penetration=spec['strict_no_penetration'],
                  time_of_contact_diff=spec['time_of_contact_diff'], max_iter=max_iter,
-                 post_stab=spec.get('post_stab', False), **world_kw)
+                 post_stab=spec.get('post_stab', False), grippers=spec.get('grippers', ()), **world_kw)

@@ -273,9 +273,10 @@ class World:
     def __init__(self, bodies, pinned=(), axis_locks=(), dt=1.0 / 30, eps=DEFAULT_EPS, tol=DEFAULT_TOL,
                  fric_dirs=8, strict_no_penetration=True, time_of_contact_diff=True,
                  stop_contact_grad=False, stop_friction_grad=False, detach_contact_b2=False, max_iter=10,
-                 post_stab=False):
+                 post_stab=False, grippers=()):
         self.bodies = list(bodies)
         self.post_stab = post_stab
+        self.grippers = [(int(i1), int(i2), tens(list(axis))) for i1, i2, axis in grippers]
         self.nb = len(self.bodies)
         # equality rows: TotalConstraint3D (6 rows, J = I6) then single-axis locks (body, axis in 0..5)
         rows = []
@@ -360,7 +361,28 @@ class World:
         J = torch.zeros(len(self.eq_rows), 6 * self.nb, dtype=F64)
         for r, (i, a) in enumerate(self.eq_rows):
             J[r, 6 * i + a] = 1.
-        return J
+        blocks = [J]
+        for i1, i2, axis in self.grippers:
+            # GripperJoint.J (physics3d/constraints.py:163-184): equal angular velocities; no relative linear motion of
+            # the joint point (body1's origin) along the two directions orthogonal to the axis (body1 frame)
+            b1, b2 = self.bodies[i1], self.bodies[i2]
+            ax = T.quaternion_apply(b1.rot, axis)
+            eye = torch.eye(3, dtype=F64)
+            d1 = torch.linalg.cross(eye[int(ax.abs().argmin())], ax)
+            d2 = torch.linalg.cross(d1, ax)
+            dirs = normalize(torch.stack([d1, d2]), dim=1)
+            pos2 = b1.pos - b2.pos
+            z = pos2.new_zeros(())
+            skew2 = torch.stack([torch.stack([z, -pos2[2], pos2[1]]), torch.stack([pos2[2], z, -pos2[0]]),
+                                 torch.stack([-pos2[1], pos2[0], z])])
+            Jg = torch.zeros(5, 6 * self.nb, dtype=F64)
+            Jg[:3, 6 * i1:6 * i1 + 3] = eye
+            Jg[:3, 6 * i2:6 * i2 + 3] = -eye
+            Jg[3:, 6 * i1 + 3:6 * i1 + 6] = dirs
+            Jg[3:, 6 * i2:6 * i2 + 3] = dirs @ skew2
+            Jg[3:, 6 * i2 + 3:6 * i2 + 6] = -dirs
+            blocks.append(Jg)
+        return torch.cat(blocks) if len(blocks) > 1 else J
 
     def Jc(self):
         J = torch.zeros(len(self.contacts), 6 * self.nb, dtype=F64)
@@ -391,8 +413,8 @@ class World:
 
     def solve_dynamics(self, dt):
         """engines.py:31-83."""
-        nz, neq = 6 * self.nb, len(self.eq_rows)
         Je = self.Je()
+        nz, neq = 6 * self.nb, Je.shape[0]
         f = torch.cat([b.force(self.t) for b in self.bodies])
         M = self.M()
         u = M @ self.v + dt * f
@@ -493,8 +515,8 @@ class World:
     def post_stabilization(self):
         """engines.py:85-121: min 1/2 z'Mz  s.t.  Jc z <= Jc v (1 - e),  Je z = Je v;  returns dp = -z (the reference builds
         a fresh LCPFunction() here: 20 iterations, not the engine's max_iter)."""
-        nz, neq = 6 * self.nb, len(self.eq_rows)
         v, M, Je = self.v, self.M(), self.Je()
+        nz, neq = 6 * self.nb, Je.shape[0]
         ge = Je @ v
         if not self.contacts:
             if neq:

@@ -112,6 +112,8 @@ def build_reference(spec, params=None):
     axis_cls = {3: rcon.XConstraint, 4: rcon.YConstraint, 5: rcon.ZConstraint}
     for i, a in spec['axis_locks']:
         joints.append(axis_cls[a](bodies[i]))
+    for i1, i2, axis in spec.get('grippers', ()):
+        joints.append(rcon.GripperJoint(bodies[i1], bodies[i2], axis=list(axis)))
     world = World3D(bodies, joints, dt=spec['dt'], eps=spec['eps'], tol=spec['tol'], fric_dirs=spec['fric_dirs'],
                     strict_no_penetration=spec['strict_no_penetration'],
                     time_of_contact_diff=spec['time_of_contact_diff'], post_stab=spec.get('post_stab', False))

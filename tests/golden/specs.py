@@ -10,6 +10,8 @@ SCENES = {
     # post-stabilisation on (engines.py:85-121, world.py:358-370; off by default in the reference)
     'box_on_plane_poststab': (lambda: dict(scenes.box_on_plane(floor=(4.0, 1.0, 4.0), steps=8), post_stab=True),
                               dict(mass=1.0, fric_coeff=0.2, push=[3.0, 2.0])),
+    # a two-body joint with pose-dependent Je rows (GripperJoint, physics3d/constraints.py:148-195)
+    'gripper_pair': (lambda: scenes.gripper_pair(steps=8), dict(mass=0.4, fric_coeff=0.2, push=[1.5, 0.8])),
     'box_tilted': (lambda: scenes.box_on_plane(floor=(4.0, 1.0, 4.0), tilt=0.2, steps=10, floor_tri=0.2),
                    dict(mass=1.1, fric_coeff=0.15, push=[2.0, 4.0])),
     'bouncing_sphere': (lambda: scenes.bouncing_sphere(floor=(4.0, 1.0, 4.0), steps=14, floor_tri=0.2),

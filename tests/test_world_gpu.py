@@ -19,7 +19,7 @@ F64 = torch.float64
 
 # (state atol, grad rtol); box_tilted balances on an edge with rank-deficient contact sets: the reference's own LU
 # round-off is amplified there (oracle-vs-reference shows the same), so only a drift bound is asserted.
-TOL = {'box_on_plane': (1e-8, 1e-5), 'box_on_plane_poststab': (1e-8, 1e-5), 'bouncing_sphere': (1e-8, 1e-4), 'grid_on_pole': (1e-8, 1e-4),
+TOL = {'box_on_plane': (1e-8, 1e-5), 'box_on_plane_poststab': (1e-8, 1e-5), 'gripper_pair': (1e-8, 1e-4), 'bouncing_sphere': (1e-8, 1e-4), 'grid_on_pole': (1e-8, 1e-4),
        'box_tilted': (2e-2, None), 'mixed_primitives': (1e-6, 5e-3),
        # BASELINE configurations at their named sizes (see tests/test_oracle_golden.py for the tolerances)
        'c1_bouncing_sphere': (5e-6, 5e-3), 'c3_mixed16': (1e-6, 1e-5), 'c4_cow_on_pole': (1e-6, 1e-5),
