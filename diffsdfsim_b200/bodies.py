@@ -276,6 +276,31 @@ class SDFGrid3D(SDF3D):
         return mass.reshape(-1, 1, 1) * I
 
 
+class SDFDecoder3D(SDFGrid3D):
+    """A body whose shape is a neural SDF ``sdf_func(points (N,3), *params) -> (N,)`` on [-1,1]^3 (times ``scale``) -- the
+    reference's IGR-decoder bodies (SDF3D with ``sdf_func=decode_igr(network)``, ``params=[latent]``, bodies.py:627-760,
+    physics3d/utils.py:330-350) in the form BASELINE's config 4 prescribes for this path: the decoder is BAKED to a res^3
+    grid that the contact kernels query (``igr.bake_grid`` semantics), while mesh and inertia stay differentiable
+    functions of ``params`` exactly as in the reference (``MeshSDF`` backward, bodies.py:652-704; volume-integral
+    inertia, :260-395).  Gradients therefore reach ``params`` through the mesh vertices and the inertia; the baked SDF
+    values themselves carry none (the reference's own ``DiffGridSDF`` gives grid values no gradient either, :246-257)."""
+
+    def __init__(self, pos, scale, sdf_func, params, res=64, mesh_res=None, device=None, **kw):
+        params = [q if isinstance(q, torch.Tensor) else torch.as_tensor(q, dtype=F64) for q in params]
+        t = torch.linspace(-1.0, 1.0, res, dtype=F64)
+        pts = torch.stack(torch.meshgrid(t, t, t, indexing='ij'), 3).reshape(-1, 3)
+        with torch.no_grad():
+            grid = torch.cat([sdf_func(pts[i:i + (1 << 16)], *[q.detach().cpu() for q in params])
+                              for i in range(0, pts.shape[0], 1 << 16)]).reshape(res, res, res)
+        verts, faces = meshes.iso_surface_mesh(sdf_func, params, res=mesh_res or res)
+        sc = float(scale)
+        inertia = meshes.mesh_inertia_torch(verts * sc, faces)
+        if device is not None:
+            verts, faces, inertia = verts.to(device), faces.to(device), inertia.to(device)
+        self.sdf_params = params
+        super().__init__(pos, scale, grid, mesh=(verts * sc, faces), inertia=inertia, device=device, **kw)
+
+
 def _sampled_mesh(kind, shape3, extra, scale, res=96):
     """Iso-surface mesh of an analytic SDF body sampled on a res^3 lattice over its cube (what the reference extracts with
     128^3 marching cubes when custom_mesh=False, bodies.py:652-712): meshes.surface_nets of meshes.sample_sdf."""

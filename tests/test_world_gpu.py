@@ -556,3 +556,27 @@ def test_latent_code_gradient_through_iso_surface_mesh_and_inertia():
     I2 = meshes.mesh_inertia_torch(v2 * scale, f2)
     ((v2 * scale) * hooks['gv'].cpu()).sum().add((I2 * hooks['gI'].cpu().reshape(3, 3)).sum()).backward()
     np.testing.assert_allclose(g.numpy(), z2.grad.numpy(), rtol=1e-10, atol=1e-14)
+
+
+def test_decoder_body_class_reaches_its_latent_code():
+    """bodies.SDFDecoder3D: grid bake + differentiable mesh + differentiable inertia behind one constructor."""
+    from diffsdfsim_b200 import bodies, constraints, forces, igr
+    from diffsdfsim_b200.world import World3D
+    dec = igr.init_decoder(seed=3, radius_init=0.6)
+    latent = torch.tensor([0.12, -0.07], dtype=F64, requires_grad=True)
+    floor = bodies.SDFBox([0, -0.5, 0], [6.0, 1.0, 6.0], restitution=0.0, fric_coeff=0.3, device='cuda', max_tri_length=0.25)
+    body = bodies.SDFDecoder3D([0.0, 1.0, 0.0], 1.0, lambda pts, z: igr.decode(dec, z, pts), [latent], res=56,
+                               vel=(0.3, 0.0, 0.1, 0.5, 0.0, 0.0), mass=1.3, restitution=0.2, fric_coeff=0.3, device='cuda')
+    lowest = float(body.verts.detach()[:, 1].min())
+    body.set_p(torch.tensor([1.0, 0, 0, 0, 0.0, -lowest + 5e-4, 0.0], dtype=F64, device='cuda'))
+    body.add_force(forces.Gravity3D())
+    world = World3D([floor, body], [constraints.TotalConstraint3D(floor)], strict_no_penetration=False)
+    loss = 0.
+    for _ in range(6):
+        world.step(fixed_dt=True)
+        loss = loss + (body.pos ** 2).sum() + 0.1 * (world.v[-6:] ** 2).sum()
+    assert int(world.contact_set.count.max()) > 0
+    loss.backward()
+    assert torch.isfinite(latent.grad).all() and float(latent.grad.abs().sum()) > 0
+    sd = body.query_sdfs(torch.zeros(1, 3, dtype=F64, device='cuda'), return_grads=False)
+    np.testing.assert_allclose(float(sd[0]), float(igr.decode(dec, latent.detach(), torch.zeros(1, 3, dtype=F64))[0]), atol=5e-3)   # trilinear interpolation of the 56^3 bake
