@@ -48,12 +48,13 @@ def test_single_world_rollout_matches_reference_golden(name):
                                maxc={'box_tilted': 320, 'mixed_primitives': 32}.get(name, 16))
     atol, grtol = TOL[name]
     loss = 0.
-    drift, tries_log = [], []
+    drift, tries_log, counts_log = [], [], []
     for k in range(spec['steps']):
         before = world.stats['attempts'].clone()
         world.step(fixed_dt=True)
         tries = int((world.stats['attempts'] - before)[0])
         tries_log.append(tries)
+        counts_log.append(int(world.contact_set.count[0]))
         p, v = world.get_p().detach().cpu().numpy(), world.v.detach().cpu().numpy()
         drift.append((np.abs(p - g['p'][k]).max(), np.abs(v - g['v'][k]).max()))
         if name != 'box_tilted':
@@ -68,6 +69,10 @@ def test_single_world_rollout_matches_reference_golden(name):
         # a box balancing on an edge: report the divergence curve instead of hiding it behind the loose tolerance
         print('  per-step pose drift vs the reference:', ' '.join('%.1e' % d[0] for d in drift))
         print('  solver attempts (ours / reference):', tries_log, [int(t) for t in g['tries']])
+        ref_counts = [int(g['con_off'][k + 1] - g['con_off'][k]) for k in range(spec['steps'])]
+        diff = [k for k in range(spec['steps']) if counts_log[k] != ref_counts[k] or tries_log[k] != int(g['tries'][k])]
+        print('  contacts per step (ours / reference):', counts_log, ref_counts,
+              '-- first step with a different contact count or attempt count:', diff[0] if diff else 'none')
     np.testing.assert_allclose(float(loss), float(g['loss']),
                                rtol={'box_tilted': 1e-2, 'mixed_primitives': 1e-5, 'c3_mixed16': 1e-5, 'c3_mixed16_floor': 1e-5}.get(name, 1e-6))
     if grtol is None:
