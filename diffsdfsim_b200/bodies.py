@@ -298,7 +298,43 @@ class SDFDecoder3D(SDFGrid3D):
         if device is not None:
             verts, faces, inertia = verts.to(device), faces.to(device), inertia.to(device)
         self.sdf_params = params
+        self.sdf_func = sdf_func
         super().__init__(pos, scale, grid, mesh=(verts * sc, faces), inertia=inertia, device=device, **kw)
+
+    def query_sdfs(self, pts_loc, return_grads=True, return_overlapmask=False, exact=False):
+        """``exact=False`` (default): the baked grid through the CUDA query operator, like every kernel of the stepping
+        path.  ``exact=True``: the decoder itself, evaluated in torch exactly as the reference's ``SDF3D.query_sdfs`` does
+        for bodies without a closed-form gradient (bodies.py:721-760): value = ``sdf_func(p / scale) * scale`` inside the
+        cube (``scale`` outside), direction = normalised autograd gradient; the values stay attached to ``params``
+        (detached when directions are requested for points that do not require grad, :744-745) -- what the point-cloud
+        fitting loss differentiates (``losses.pointcloud_sdf_loss(..., exact=True)``).  Single world: pts_loc (N,3)."""
+        if not exact:
+            return super().query_sdfs(pts_loc, return_grads=return_grads, return_overlapmask=return_overlapmask)
+        scale = self.scale.reshape(-1)[0].to(pts_loc.device)
+        params = [q.to(pts_loc.device) for q in self.sdf_params]
+        mask = torch.all(pts_loc.abs() <= scale, dim=1)
+        sdfs = torch.ones(pts_loc.shape[0], dtype=pts_loc.dtype, device=pts_loc.device)
+        grads = torch.zeros_like(pts_loc)
+        if bool(mask.any()):
+            pts_in = pts_loc[mask] / scale
+            if return_grads:
+                with torch.enable_grad():
+                    leaf = pts_in.is_leaf
+                    if not pts_in.requires_grad:
+                        pts_in.requires_grad_(True)
+                    vals = self.sdf_func(pts_in, *params)
+                    g = torch.autograd.grad(vals, pts_in, torch.ones_like(vals), retain_graph=not leaf)[0]
+                sdfs = sdfs.clone()
+                sdfs[mask] = vals
+                grads[mask] = torch.nn.functional.normalize(g, dim=1)
+                if leaf:
+                    sdfs = sdfs.detach()
+            else:
+                sdfs = sdfs.clone()
+                sdfs[mask] = self.sdf_func(pts_in, *params)
+        sdfs = sdfs * scale
+        res = (sdfs,) + ((grads,) if return_grads else ()) + ((mask,) if return_overlapmask else ())
+        return res if len(res) > 1 else res[0]
 
 
 def _sampled_mesh(kind, shape3, extra, scale, res=96):

@@ -75,7 +75,7 @@ def run_world_fixed_dt(world, run_time, detach_2nd_bounce=False):
     return n_steps
 
 
-def pointcloud_sdf_loss(body, points_world, pos=None, rot=None):
+def pointcloud_sdf_loss(body, points_world, pos=None, rot=None, exact=False):
     """(sum of squared SDF values of the observed points inside the body's cube, number of such points).
 
     points_world (N,3) or (W,N,3); pos (.,3) / rot (.,3,3) default to the body's current pose.  Points outside the cube
@@ -88,7 +88,11 @@ def pointcloud_sdf_loss(body, points_world, pos=None, rot=None):
     B = max(pts.shape[0], pos.shape[0])
     pts = pts.expand(B, -1, 3)
     loc = torch.einsum('bji,bnj->bni', rot.expand(B, 3, 3), pts - pos.expand(B, 3)[:, None, :])   # R^T (x - pos)
-    sdf, mask = body.query_sdfs(loc.contiguous(), return_grads=False, return_overlapmask=True)
+    if exact:          # neural-SDF bodies: the decoder itself, differentiable w.r.t. its parameters (single world)
+        sdf, mask = body.query_sdfs(loc[0].contiguous(), return_grads=False, return_overlapmask=True, exact=True)
+        sdf, mask = sdf[None], mask[None]
+    else:
+        sdf, mask = body.query_sdfs(loc.contiguous(), return_grads=False, return_overlapmask=True)
     sdf = torch.where(mask, sdf, torch.zeros_like(sdf))
     loss, n = (sdf ** 2).sum(-1), mask.sum(-1)
     single = points_world.dim() == 2 and body.p.dim() == 1

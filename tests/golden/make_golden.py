@@ -333,6 +333,30 @@ def golden_mesh_sdf():
     np.savez_compressed(os.path.join(HERE, 'mesh_sdf.npz'), **d)
 
 
+def golden_neural_query():
+    """The reference's SDF3D.query_sdfs (bodies.py:721-760) on a neural-SDF body (sdf_func = an IGR-style decoder, params =
+    [latent], no closed-form gradient): values, directions, overlap mask at points in and outside the cube, and the
+    gradient of the point-cloud loss sum(sdf^2) (optim_pointcloud.py:193-199) w.r.t. the latent code."""
+    from diffsdfsim_b200 import igr
+    dec = igr.init_decoder(seed=3, radius_init=0.6)
+    fn = lambda pts, z: igr.decode(dec, z, pts)
+    latent = torch.tensor([0.12, -0.07], dtype=F64, requires_grad=True)
+    tet_v = torch.tensor([[0., 0, 0], [1, 0, 0], [0, 1, 0], [0, 0, 1]], dtype=F64) * 0.3
+    tet_f = torch.tensor([[0, 2, 1], [0, 1, 3], [0, 3, 2], [1, 2, 3]])
+    body = _inject(rb.SDF3D, tet_v, tet_f)(torch.tensor([0.1, 0.2, -0.1], dtype=F64), 1.5, fn, [latent])
+    rng = np.random.RandomState(11)
+    pts = torch.tensor(rng.uniform(-1.8, 1.8, (400, 3)))
+    sd, gr, mask = body.query_sdfs(pts.clone(), return_grads=True, return_overlapmask=True)
+    sd2, mask2 = body.query_sdfs(pts.clone(), return_grads=False, return_overlapmask=True)
+    sdz = sd2.clone()
+    sdz[mask2 == False] = 0
+    loss = torch.sum(sdz ** 2)
+    loss.backward()
+    print('neural_query', int(mask.sum()), float(loss), latent.grad.tolist())
+    np.savez_compressed(os.path.join(HERE, 'neural_query.npz'), pts=pts.numpy(), sdf=sd.detach().numpy(), dir=gr.detach().numpy(),
+                        mask=mask.numpy(), loss=float(loss), glatent=latent.grad.numpy())
+
+
 def golden_trajectory_loss():
     """The reference's own trajectory_loss (experiments/trajectory_fitting/optim_sphere.py:114-160) on synthetic recorded
     trajectories: 4 worlds, 14 model states vs 19 target states each, irregular and partly coinciding time stamps (the
@@ -394,6 +418,8 @@ if __name__ == '__main__':
             golden_trajectory_loss()
         elif n == 'mesh_sdf':
             golden_mesh_sdf()
+        elif n == 'neural_query':
+            golden_neural_query()
         else:
             mk, leaves = SCENES[n]
             spec = mk()

@@ -116,3 +116,29 @@ def test_differentiable_iso_surface_mesh_and_inertia_match_the_reference_functio
         for k, q in enumerate(ps):
             np.testing.assert_allclose(q.grad.numpy(), g['%s_grad%d' % (name, k)], rtol=1e-9, atol=1e-12,
                                        err_msg='%s: gradient of parameter %d' % (name, k))
+
+
+def test_neural_sdf_exact_query_matches_the_reference_query_sdfs():
+    """bodies.SDFDecoder3D.query_sdfs(exact=True) -- the decoder evaluated like the reference's SDF3D.query_sdfs for bodies
+    without a closed-form gradient (bodies.py:721-760) -- against outputs of the reference method itself
+    (tests/golden/make_golden.py neural_query): values, directions, overlap mask, and the gradient of the point-cloud loss
+    w.r.t. the latent code."""
+    import os
+    import numpy as np
+    import torch
+    from diffsdfsim_b200 import bodies, igr
+    g = np.load(os.path.join(os.path.dirname(__file__), 'golden', 'neural_query.npz'))
+    dec = igr.init_decoder(seed=3, radius_init=0.6)
+    latent = torch.tensor([0.12, -0.07], dtype=torch.float64, requires_grad=True)
+    body = bodies.SDFDecoder3D([0.1, 0.2, -0.1], 1.5, lambda pts, z: igr.decode(dec, z, pts), [latent], res=16)
+    pts = torch.tensor(g['pts'])
+    sd, gr, mask = body.query_sdfs(pts.clone(), return_grads=True, return_overlapmask=True, exact=True)
+    np.testing.assert_array_equal(mask.numpy(), g['mask'])
+    np.testing.assert_allclose(sd.detach().numpy(), g['sdf'], rtol=1e-12, atol=1e-14)
+    np.testing.assert_allclose(gr.detach().numpy(), g['dir'], rtol=1e-10, atol=1e-13)
+    assert not sd.requires_grad                      # bodies.py:744-745: detached when the points are a leaf
+    sd2, mask2 = body.query_sdfs(pts.clone(), return_grads=False, return_overlapmask=True, exact=True)
+    loss = (torch.where(mask2, sd2, torch.zeros_like(sd2)) ** 2).sum()
+    np.testing.assert_allclose(float(loss.detach()), float(g['loss']), rtol=1e-12)
+    loss.backward()
+    np.testing.assert_allclose(latent.grad.numpy(), g['glatent'], rtol=1e-10)
